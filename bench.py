@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — flow pairs/s @480x640 on N B200s (BASELINE.json metric) with the splat kernel's HBM roofline.
+
+One step = one pass of the hot path over one batch of synthetic 480x640 RGB-D frames resident in HBM: for every
+frame one *flow pair* = virtual-disparity flow synthesis + the C=6 z-buffered forward-warp splat + mask /
+fix_warped_depth (preprocess.py:356-365, inpaint excluded) — a single launch of the fused pair kernel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU; frames shard by image index)
+
+Prints ONE JSON line (rank 0).  Keys beyond the driver's contract:
+    roofline       fused pair kernel: algorithmic bytes (56 B/px) / CUDA-event time vs MEASURED_PEAKS hbm_gbs
+    cpu_baseline   the oracle port of the same workload on the host cores (bounded sample)
+    e2e            the same metric through the host-buffer C-ABI front end (pinned host memory, H2D + D2H timed)
+    general_splat  the packed-key atomicMin z-test + gather path on the same workload (3 launches / step)
+    sixdof         cfg3-style 6-DoF reprojection + C=7 splat at 1080p (secondary)
+    ref_fw_cuda    the reference's own fw_cuda kernel (compiled unmodified, oracle/_ref) on the same GPU
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W = 480, 640
+PAIR_BYTES_PER_PX = 56          # img 3 + depth 1 in; img1 3, depth1 1, back_flow 2, flow 2, valid 1, collision 1 out
+FW_BYTES_PER_PX = lambda C: 4 * (2 * C + 5)  # noqa: E731  splat at the FW.forward boundary
+POOL = 16                       # distinct synthetic frames; the batch cycles through them
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_pool(n=POOL):
+    from opticalflowfromdepth_b200 import synthetic
+
+    frames = [synthetic.diml_frame(k, H, W) for k in range(n)]
+    return np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+
+
+def s_values(n, seed=0):
+    """s*B*f per frame: s in [0.8, 1.1) (preprocess.py:240), B*f = 50."""
+    rng = np.random.default_rng(seed)
+    return ((rng.random(n) * 0.3 + 0.8).astype(np.float32) * np.float32(50.0)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference path's CPU implementation = the oracle port (the reference's only splat is a
+    CUDA kernel, so no CPU original exists), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    import oracle
+    from oracle import flow as oflow
+
+    cores = os.cpu_count() or 1
+    frames = max(cores, 8)
+    img, raw = make_pool(min(POOL, frames))
+    depth = np.stack([oflow.normalize_depth(torch.from_numpy(raw[k].copy())).numpy() for k in range(raw.shape[0])])
+    idx = np.arange(frames) % img.shape[0]
+    img, depth, sBf = np.ascontiguousarray(img[idx]), np.ascontiguousarray(depth[idx]), s_values(frames)
+    steps = min(args.steps, 10)
+    for _ in range(min(args.warmup, 2)):
+        oracle.disparity_pair(img, depth, sBf, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.disparity_pair(img, depth, sBf, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = frames * steps / dt
+    sample = f"{frames} frames/step x {steps} steps of the same 480x640 workload, {cores} pthreads over frames"
+    line = {
+        "impl": "reference", "metric": "flow pairs/s @480x640", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg5 480x640 DIML-shaped frames: virtual-disparity flow pair (flow synthesis + C=6 z-buffered splat)",
+                   "frames_per_step": frames, "H": H, "W": W},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's forward-warp exists only as a CUDA kernel (alt_cuda/fw_cuda_kernel.cu); this arm times its "
+                "CPU restatement (oracle/ofd_oracle.c); the kernel itself on the B200 is reported as ref_fw_cuda by the default arm",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def timed(fn, steps, warmup, stream_sync, barrier):
+    """W warm-up calls, then K calls bracketed by barrier + synchronize, CUDA events on the current stream."""
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    stream_sync()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    stream_sync()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3  # seconds
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (ROOT / "opticalflowfromdepth_b200" / "libofd_b200.so").exists():
+        if rank == 0:
+            ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from opticalflowfromdepth_b200 import _lib, geometry, ops, sweep, synthesis
+
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    sync = lambda: torch.cuda.synchronize(dev)  # noqa: E731
+
+    F = args.frames
+    K, Wm = args.steps, max(args.warmup, 3)
+    peak, peak_src = measured_peaks()
+
+    # ---- synthetic inputs, resident in HBM; this rank's frames are the indices idx % world == rank -----------------
+    img_pool, raw_pool = make_pool()
+    my_idx = np.array(list(sweep.shard_strided(F * world, world, rank)))
+    pool_idx = torch.from_numpy(my_idx % POOL).to(dev)
+    img = torch.from_numpy(img_pool).to(dev)[pool_idx].contiguous()
+    depth = ops.normalize_depth(torch.from_numpy(raw_pool).to(dev))[pool_idx].contiguous()
+    sBf = torch.from_numpy(s_values(F * world)[my_idx]).to(dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    outs = (torch.empty((F, 3, H, W), **f32), torch.empty((F, 1, H, W), **f32), torch.empty((F, 2, H, W), **f32),
+            torch.empty((F, 2, H, W), **f32), torch.empty((F, 1, H, W), **f32), torch.empty((F, 1, H, W), **f32))
+    counters = ops.new_counters(dev)
+
+    def step():
+        ops.disparity_pair(img, depth, sBf, out=outs)
+
+    # ---- headline: K steps, device timed, max over ranks ---------------------------------------------------------------
+    with ClockSampler(local) as clk:
+        elapsed = timed(step, K, Wm, sync, barrier)
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t.item())
+    value = world * F * K / elapsed_max
+    # the step is ONE launch of the fused pair kernel, so its average launch duration is elapsed / K
+    kernel_s = elapsed / K
+    achieved = PAIR_BYTES_PER_PX * H * W * F / kernel_s / 1e9
+
+    # counters of one counted step (outside the timed region), summed over ranks (the path's only collective)
+    ops.disparity_pair(img, depth, sBf, out=outs, counters=counters)
+    counters[_lib.CNT_FRAMES] += F
+    counters[_lib.CNT_PAIRS] += F
+    totals = sweep.reduce_counters(counters)
+
+    line = {
+        "metric": "flow pairs/s @480x640", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": 1e3 * elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg5 480x640 DIML-shaped frames: virtual-disparity flow pair (flow synthesis + C=6 z-buffered splat)",
+                   "frames_per_step_per_gpu": F, "H": H, "W": W, "parallelism": f"frames sharded by image index over {world} GPU(s), no collective on the hot path",
+                   "l2": f"inputs {F * 4 * H * W * 4 / 1e6:.0f} MB + outputs {F * 10 * H * W * 4 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)"},
+        "gpu_launches": K,
+        "roofline": {"bound": "hbm", "kernel": "pair_row_kernel<float,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_px": PAIR_BYTES_PER_PX, "bytes_per_launch": PAIR_BYTES_PER_PX * H * W * F},
+        "counters": totals,
+    }
+
+    if rank == 0:
+        line["clocks"] = clk.summary()
+
+    # ---- secondary numbers, rank 0 only when N > 1 keeps the scaling runs short ------------------------------------------
+    if world == 1 or args.extras:
+        extras = {}
+        # (a) the general path on the same workload: disparity flow + packed-key z-test + gather (3 launches / step)
+        Fg = min(F, 64)
+        ws_warm = ops.frame_splat(img[:Fg], depth[:Fg], ops.disparity_flow(depth[:Fg], sBf[:Fg]), None)
+        del ws_warm
+
+        def gstep():
+            fl = ops.disparity_flow(depth[:Fg], sBf[:Fg])
+            ops.frame_splat(img[:Fg], depth[:Fg], fl, None)
+
+        tg = timed(gstep, max(K // 2, 5), 3, sync, barrier)
+        per = tg / max(K // 2, 5)
+        extras["general_splat"] = {"pairs_per_s": Fg / per, "ms_per_step": 1e3 * per, "frames_per_step": Fg, "launches_per_step": 3,
+                                   "achieved_GBps": (PAIR_BYTES_PER_PX + 16) * H * W * Fg / per / 1e9,
+                                   "note": "algorithmic bytes 72 B/px: the flow plane is written by one kernel and re-read by z-test and gather"}
+        # (b) cfg3-style: 6-DoF reprojection + C=7 splat + hole mask at 1080p
+        try:
+            Hb, Wb, Fb = 1080, 1920, 8
+            big_img = torch.rand(Fb, 3, Hb, Wb, device=dev) * 255
+            from opticalflowfromdepth_b200 import synthetic
+            raw = np.stack([synthetic.diml_frame(100 + k, Hb, Wb)[1] for k in range(2)])
+            big_depth = ops.normalize_depth(torch.from_numpy(raw).to(dev))[torch.arange(Fb, device=dev) % 2].contiguous()
+            Kc, invK = synthesis.Plausible.K((Hb, Wb))
+            cams = []
+            for k in range(Fb):
+                torch.manual_seed(12345 + k)
+                T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
+                cams.append(geometry.camera_constants(Kc, invK, T1))
+            cam = torch.cat(cams).to(dev)
+            vin = torch.ones(Fb, 1, Hb, Wb, device=dev)
+
+            def bstep():
+                fl = ops.reproject_flow(big_depth, cam)
+                ops.frame_splat(big_img, big_depth, fl, vin)
+
+            tb = timed(bstep, 10, 3, sync, barrier) / 10
+            extras["sixdof_1080p"] = {"frames_per_s": Fb / tb, "ms_per_step": 1e3 * tb, "frames_per_step": Fb, "launches_per_step": 3,
+                                      "achieved_GBps": (64 + 16) * Hb * Wb * Fb / tb / 1e9,
+                                      "note": "64 B/px fused-pair algorithmic bytes (SURVEY 8d) + 16 B/px for the materialised flow plane"}
+            del big_img, big_depth, vin
+        except Exception as e:  # secondary: never break the headline
+            extras["sixdof_1080p"] = {"error": repr(e)}
+        # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
+        try:
+            import oracle
+
+            ref = oracle.load_ref_fw_cuda()
+            fl = ops.disparity_flow(depth[:1], sBf[:1])
+            obj = torch.cat((img[:1], depth[:1], fl * -1.0), 1).contiguous()
+            gx, gy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+
+            def ref_call():
+                # alt_cuda/fw.py:27-43 (host meshgrid + H2D every call) then the extension
+                p0 = torch.stack((gx, gy), 0).float().repeat(1, 1, 1, 1).to(dev)
+                p1 = p0 + fl
+                sy = torch.clamp(p1[:, 1:2], min=0, max=H - 1).contiguous().long().float()
+                sx = torch.clamp(p1[:, 0:1], min=0, max=W - 1).contiguous().long().float()
+                return ref.forward_warping(obj, sy, sx, depth[:1])
+
+            ref_call()
+            sync()
+            t0 = time.perf_counter()
+            n_ref = 3
+            for _ in range(n_ref):
+                ref_call()
+            sync()
+            per_ref = (time.perf_counter() - t0) / n_ref
+            extras["ref_fw_cuda"] = {"pairs_per_s": 1.0 / per_ref, "ms_per_call": 1e3 * per_ref,
+                                     "achieved_GBps": FW_BYTES_PER_PX(6) * H * W / per_ref / 1e9,
+                                     "what": "reference fw_cuda (alt_cuda/fw_cuda_kernel.cu, unmodified, sm_100a) driven by the fw.py prologue, C=6, one 480x640 frame per call"}
+        except Exception as e:
+            extras["ref_fw_cuda"] = {"unavailable": repr(e)}
+        line.update(extras)
+
+    # ---- e2e: host buffers -> C-ABI pipeline -> host buffers, copies inside the timed region ---------------------------
+    Fe = args.e2e_frames
+    h_img = torch.from_numpy(img_pool)[torch.arange(Fe) % POOL].contiguous().pin_memory()
+    h_depth = depth[torch.arange(Fe, device=dev) % F].cpu().contiguous().pin_memory()
+    h_s = torch.from_numpy(s_values(Fe)).contiguous()
+    h_out = [torch.empty((Fe, c, H, W), dtype=torch.float32).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+    pipe = ops.PairPipeline(local, H, W, chunk_frames=args.e2e_chunk)
+    for _ in range(2):
+        pipe.run(h_img, h_depth, h_s, *h_out)
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        pipe.run(h_img, h_depth, h_s, *h_out)  # returns after the last D2H byte has landed
+    te = time.perf_counter() - t0
+    pipe.close()
+    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    line["e2e"] = {"value": world * Fe * Ke / float(te_t.item()), "unit": "pairs/s",
+                   "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * 10 * H * W * 4,
+                   "frames_per_step": Fe, "steps": Ke,
+                   "api": "ofd_pair_pipeline_run (C ABI, pinned host buffers in and out, 3-slot H2D/kernel/D2H pipeline)"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+
+        cores = os.cpu_count() or 1
+        n = max(cores, 8)
+        ci = np.ascontiguousarray(img_pool[np.arange(n) % POOL])
+        cd = depth[torch.arange(n, device=dev) % F].cpu().numpy()
+        cs = s_values(n)
+        oracle.disparity_pair(ci, cd, cs, nthreads=cores)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 10.0 and reps < 50:
+            oracle.disparity_pair(ci, cd, cs, nthreads=cores)
+            reps += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n * reps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} frames x {reps} repeats of the same 480x640 workload, {cores} pthreads over frames (oracle/ofd_oracle.c)"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--e2e-chunk", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

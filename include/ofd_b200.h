@@ -1,0 +1,201 @@
+/*
+ * ofd_b200.h — C ABI of libofd_b200.so, the B200-native (sm_100a) flow-synthesis hot path.
+ *
+ * This library replaces the reference's torch extension `fw_cuda`
+ * (alt_cuda/fw_cuda.cpp:15-30, alt_cuda/fw_cuda_kernel.cu:10-83) and fuses the per-pixel work the
+ * reference does in torch around it (alt_cuda/fw.py:19-59, preprocess.py:237-326, geometry.py:17-67,
+ * utils.py:102-126, bilateral_filter.py:13-60).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - tensors are dense NCHW, batch-major, no strides; `B` frames of `H x W`, H*W < 2^31;
+ *   - `stream` is a cudaStream_t (opaque here so the header needs no CUDA include);
+ *   - every entry point returns 0 on success, a negative OFD_E_* code for a rejected call (nothing was
+ *     launched) or a positive cudaError_t; ofd_last_error_string() explains the last failure on the
+ *     calling thread.  Nothing throws across this ABI, launches are asynchronous on `stream`;
+ *   - the library keeps no global mutable state; scratch ("key workspace") is caller-owned.
+ *
+ * Key workspace.  The z-buffer is a plane of packed 64-bit keys  (ordered_depth_bits << 32 | source_raster_id),
+ * 8 bytes per target pixel.  It must hold the "untouched" pattern (all bytes 0xFF) when a splat starts; every
+ * splat entry point leaves it in that state again when it returns success (the gather pass re-arms the keys it
+ * consumed), so ofd_workspace_reset() is only needed once after allocation or after a failed call.
+ */
+#ifndef OFD_B200_H_
+#define OFD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ofd_stream_t; /* cudaStream_t */
+
+/* ---- return codes ------------------------------------------------------------------------------------- */
+#define OFD_OK 0
+#define OFD_E_NULL (-1)      /* a required pointer is NULL                       */
+#define OFD_E_SHAPE (-2)     /* B/C/H/W out of the supported range               */
+#define OFD_E_DTYPE (-3)     /* unsupported dtype code                           */
+#define OFD_E_ARG (-4)       /* any other invalid argument (epilogue, window...) */
+#define OFD_E_WORKSPACE (-5) /* workspace too small / misaligned                 */
+
+/* dtype codes */
+#define OFD_F32 0
+#define OFD_F64 1
+
+/* gather epilogues (ofd_splat_flow) */
+#define OFD_EPI_NONE 0   /* alt_cuda/fw.py:19-59: raw FW.forward result                                   */
+#define OFD_EPI_CONCAT 1 /* preprocess.py:307-313 ConcatFlow: out = (warp + aux) * valid                  */
+#define OFD_EPI_BACK 2   /* preprocess.py:321-326 BackFlow:   out = (warp * -1) * valid                   */
+
+#define OFD_MAX_CHANNELS 8
+
+/* counters written by the gather pass when a counter block is supplied (uint64 each, accumulated) */
+#define OFD_CNT_HIT 0       /* target pixels with valid == 1                                  */
+#define OFD_CNT_HOLE 1      /* target pixels with valid == 0                                  */
+#define OFD_CNT_COLLISION 2 /* target pixels with collision == 1                              */
+#define OFD_CNT_DROPPED 3   /* sources dropped: NaN flow / out-of-range explicit target       */
+#define OFD_CNT_TIE_SRC 4   /* sources that tie the winning depth but lose on raster index    */
+#define OFD_CNT_FRAMES 5
+#define OFD_CNT_PAIRS 6
+#define OFD_CNT_SLOTS 8
+
+int ofd_version(void);
+const char* ofd_last_error_string(void);
+
+/* Bytes of key workspace a splat over B frames of HxW needs. */
+size_t ofd_workspace_bytes(int B, int H, int W);
+/* Fill a fresh (or possibly dirty) workspace with the "untouched" key pattern. */
+int ofd_workspace_reset(void* ws, size_t bytes, ofd_stream_t stream);
+
+/*
+ * ofd_splat_targets — the exact contract of fw_cuda.forward_warping (alt_cuda/fw_cuda.cpp:15-26):
+ *   obj[B,C,H,W], safe_y/safe_x/depth[B,1,H,W] of one dtype -> out[B,C,H,W], valid/collision[B,1,H,W].
+ *   Target of source (j,i) is (int)safe_y, (int)safe_x (float->int truncation of the accessor index,
+ *   fw_cuda_kernel.cu:31-32).  Winner per target = min depth among sources with depth < 1000, ties -> lowest
+ *   raster index (the serial loop order, :28-29,34); valid = any hit; collision = hit but no winner (:39-44).
+ *   Divergence (documented): a target outside [0,H)x[0,W) or NaN is undefined behaviour in the reference;
+ *   here that source is dropped and counted in OFD_CNT_DROPPED.
+ *   `winner` (optional, int32 [B,1,H,W]) receives the winning source raster id, -1 for holes, -2 for collisions.
+ *   dtype: OFD_F32 only (OFD_F64 -> OFD_E_DTYPE; the Python shim handles double by the two-plane path).
+ */
+int ofd_splat_targets(const void* obj, const void* safe_y, const void* safe_x, const void* depth, int dtype,
+                      int B, int C, int H, int W, void* out, void* valid, void* collision, int32_t* winner,
+                      uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+
+/*
+ * ofd_splat_flow — FW.forward (alt_cuda/fw.py:19-59) with the torch prologue fused into the z-test:
+ *   target = trunc(clamp((i,j) + flow, 0, (W-1,H-1))) evaluated in the flow's dtype (fw.py:31,37-42);
+ *   flow is [B,2,H,W] float32 (flow_dtype OFD_F32) or float64 (OFD_F64); obj/depth/out are float32.
+ *   Divergence (documented): NaN flow is UB in the reference; here the source is dropped and counted.
+ *   epilogue: OFD_EPI_*; `aux` is flowAB[B,2,H,W] for OFD_EPI_CONCAT (C must be 2), else NULL.
+ */
+int ofd_splat_flow(const float* obj, const void* flow, int flow_dtype, const float* depth, int B, int C, int H,
+                   int W, float* out, float* valid, float* collision, int32_t* winner, int epilogue,
+                   const float* aux, uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+
+/*
+ * ofd_disparity_flow — Convert.depth_to_disparity + disparity_to_flow(random_sign=False)
+ * (preprocess.py:239-254): flow = (-(sBf / depth), -0.0), sBf = float32(s*B*f) promoted to the depth dtype.
+ *   depth[B,1,H,W] (depth_dtype f32|f64) -> flow[B,2,H,W] of the same dtype; sBf[B] float32 on the DEVICE.
+ */
+int ofd_disparity_flow(const void* depth, int depth_dtype, const float* sBf, int B, int H, int W, void* flow,
+                       ofd_stream_t stream);
+
+/*
+ * ofd_disparity_pair — one whole "flow pair" of preprocess.py:355-366 (minus inpaint) in ONE kernel:
+ *   flow01 = (-(sBf/depth0), -0.0); splat of obj = img0(3) | depth0(1) | -flow01(2) along flow01 z-tested
+ *   with depth0; results masked by valid; fix_warped_depth (utils.py:123-126) on the warped depth.
+ *   Because flow.y == -0.0 exactly, every source stays in its row: the z-buffer lives in shared memory,
+ *   no global atomics and no key workspace.
+ *   in : img0[B,3,H,W] f32, depth0[B,1,H,W] (depth_dtype f32|f64), sBf[B] (device, float32)
+ *   out: img1[B,3,H,W], depth1[B,1,H,W], back_flow[B,2,H,W], flow[B,2,H,W] (f32; NULL to skip),
+ *        valid[B,1,H,W], collision[B,1,H,W] (NULL to skip).
+ */
+int ofd_disparity_pair(const float* img0, const void* depth0, int depth_dtype, const float* sBf, int B, int H,
+                       int W, float* img1, float* depth1, float* back_flow, float* flow, float* valid,
+                       float* collision, uint64_t* counters, ofd_stream_t stream);
+
+/*
+ * ofd_reproject_flow — Convert.depth_to_random_flow (preprocess.py:265-298) = geometry.BackprojectDepth.forward
+ * (geometry.py:37-42) + geometry.Project3D.forward (geometry.py:56-67) + de-normalisation, per pixel, fused:
+ *   ray = invK3 (x,y,1);  X = depth*ray (float32);  c = P (X,1);  u = c.x/(c.z+eps), v = c.y/(c.z+eps);
+ *   u <- ((u/(W-1) - .5)*2 + 1)/2*(W-1)  (same for v with H);  flow = (u - x, v - y).
+ *   cam: per frame 21 floats on the DEVICE = invK3 row-major (9) followed by P = (K T)[:3,:] row-major (12).
+ *   depth[B,1,H,W] f32|f64 (depth*ray is evaluated in the depth dtype then rounded to f32, geometry.py:39-40).
+ */
+int ofd_reproject_flow(const void* depth, int depth_dtype, const float* cam, float eps, int B, int H, int W,
+                       float* flow, ofd_stream_t stream);
+
+/*
+ * Class-level geometry entry points, kept so geometry.py's modules stay drop-in (the fused ofd_reproject_flow is
+ * the fast path).  ofd_backproject = BackprojectDepth.forward (geometry.py:37-42): depth[B,1,H,W] (f32|f64),
+ * invk3[B,9] -> cam_points[B,4,H*W] f32.  ofd_project = Project3D.forward (geometry.py:56-67): cam_points, P[B,12]
+ * -> pix_coords[B,H,W,2] in [-1,1] and z[B,1,H*W].  All pointers are device pointers.
+ */
+int ofd_backproject(const void* depth, int depth_dtype, const float* invk3, int B, int H, int W, float* cam_points,
+                    ofd_stream_t stream);
+int ofd_project(const float* cam_points, const float* P, float eps, int B, int H, int W, float* pix_coords, float* z,
+                ofd_stream_t stream);
+
+/*
+ * ofd_frame_splat — one image+flow splat of the frame pipeline (preprocess.py:372-382 / 385-394 / 401-411):
+ *   obj = img(3) | depth(1) | -flow(2) | valid_in(1, optional) gathered from separate planes (no torch.cat);
+ *   z-test with `depth` along `flow` (float32 [B,2,H,W]); epilogue: valid' = valid * warp(valid_in) (or valid),
+ *   all outputs * valid', fix_warped_depth on the warped depth.
+ *   out: img_out[B,3,H,W], depth_out[B,1,H,W], back_flow[B,2,H,W], valid_out[B,1,H,W] (= valid'),
+ *        collision[B,1,H,W] (NULL to skip), raw_valid[B,1,H,W] (NULL to skip).
+ */
+int ofd_frame_splat(const float* img, const float* depth, const float* flow, const float* valid_in, int B, int H,
+                    int W, float* img_out, float* depth_out, float* back_flow, float* valid_out, float* collision,
+                    float* raw_valid, uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+
+/*
+ * ofd_normalize_depth — utils.normalize_depth (utils.py:102-116) per frame: 0 -> 100, >100 -> 100, min over
+ * all, 100 -> 0, max, affine map to [1,99], formerly-invalid pixels -> 100.  Out of place (the reference's
+ * half-mutation of its argument is not reproduced).  scratch: 2*B uint64 words (device).
+ */
+int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void* out, void* scratch,
+                        ofd_stream_t stream);
+
+/* ofd_fix_warped_depth — utils.fix_warped_depth (utils.py:123-126), in place: 0 -> 100, > 99.5 -> 100. */
+int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream);
+
+/*
+ * ofd_special_flow — SpecialFlow.forward (preprocess.py:24-105): analytic augmentation flows.
+ *   kind 5 flip (vertical, :47-60; no params), 6 rotate (:62-79), 7 shear (:81-99).
+ *   params_host (HOST, 10 floats, kinds 6/7): cx, cy, M row-major (4), Mrev row-major (4) with
+ *   p1 = (p0 - c) @ M + c, p_prev = (p0 - c) @ Mrev + c; kind 7 ignores the centre (p1 = p0 @ M).
+ *   out: flow[2,H,W] = p1 - p0 and back_flow[2,H,W] = p_prev - p0 (float32).
+ */
+int ofd_special_flow(int kind, const float* params_host, int H, int W, float* flow, float* back_flow,
+                     ofd_stream_t stream);
+
+/*
+ * ofd_bilateral_iter — one iteration of sparse_bilateral_filtering (bilateral_filter.py:33-58):
+ *   discontinuity map from `depth_in` (|1/d - 1/d'| > thr on 4-neighbours of the interior, :63-116), forced to 1
+ *   where depth_orig == 0 (:46), border ring edge-replicated (:141-147), then the gated median of window x window
+ *   (:167-198) with the reference's float32 cumsum rank rule.  dtype f32|f64 applies to all three planes.
+ */
+int ofd_bilateral_iter(const void* depth_in, const void* depth_orig, int dtype, int H, int W, int window,
+                       double threshold, void* depth_out, ofd_stream_t stream);
+
+/*
+ * Host-buffer front end of the flow-pair path (what a reference-side caller holding numpy arrays or pinned CPU
+ * tensors binds; the reference crosses host<->device around every FW call, preprocess.py:350-366,437-447).
+ * A pipeline owns three device staging slots with one stream each: chunk k does host->device copies, the pair
+ * kernel and device->host copies on slot k%3, so both copy engines and the SMs overlap.  Host buffers should be
+ * page-locked for the copies to overlap.  `run` returns after every result byte has landed in the host buffers.
+ */
+typedef struct ofd_pair_pipeline ofd_pair_pipeline;
+int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out);
+int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host,
+                          const float* sBf_host, int B, float* img1_host, float* depth1_host, float* back_flow_host,
+                          float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/);
+void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFD_B200_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of libofd_b200.so (include/ofd_b200.h).  There is NO fallback: if the library is missing the
+import of any operator fails loudly, and every non-zero return code raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libofd_b200.so"
+
+F32, F64 = 0, 1
+EPI_NONE, EPI_CONCAT, EPI_BACK = 0, 1, 2
+MAX_CHANNELS = 8
+CNT_HIT, CNT_HOLE, CNT_COLLISION, CNT_DROPPED, CNT_TIE_SRC, CNT_FRAMES, CNT_PAIRS, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 6, 8
+
+_p, _i, _sz, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
+
+# name -> (restype, argtypes): one entry per symbol declared in include/ofd_b200.h
+SIGNATURES = {
+    "ofd_version": (_i, []),
+    "ofd_last_error_string": (C.c_char_p, []),
+    "ofd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ofd_workspace_reset": (_i, [_p, _sz, _p]),
+    "ofd_splat_targets": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ofd_splat_flow": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "ofd_disparity_flow": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
+    "ofd_disparity_pair": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ofd_reproject_flow": (_i, [_p, _i, _p, _f, _i, _i, _i, _p, _p]),
+    "ofd_backproject": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
+    "ofd_project": (_i, [_p, _p, _f, _i, _i, _i, _p, _p, _p]),
+    "ofd_frame_splat": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ofd_fix_warped_depth": (_i, [_p, _sz, _p]),
+    "ofd_special_flow": (_i, [_i, _p, _i, _i, _p, _p, _p]),
+    "ofd_bilateral_iter": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
+    "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
+    "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "ofd_pair_pipeline_destroy": (None, [_p]),
+}
+
+
+class OfdError(RuntimeError):
+    def __init__(self, fn: str, code: int, msg: str):
+        super().__init__(f"{fn} failed with code {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once.  Raises if it has not been built (python -m opticalflowfromdepth_b200._build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m opticalflowfromdepth_b200._build` "
+                "(or __graft_entry__.build()); there is no CPU or PyTorch fallback for this path"
+            )
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise OfdError on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise OfdError(name, rc, lib.ofd_last_error_string().decode("utf-8", "replace"))

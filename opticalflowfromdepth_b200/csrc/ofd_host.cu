@@ -1,0 +1,112 @@
+// ofd_host.cu — host-buffer front end of the flow-pair path: what a caller holding numpy / pinned CPU tensors
+// binds (the reference moves every frame host->device->host around its FW call, preprocess.py:350-366,437-447).
+// A pipeline owns NSLOT device staging slots, each with its own stream; chunk k runs H2D -> pair kernel -> D2H
+// on slot k % NSLOT, so the two copy engines and the SMs overlap across chunks.
+#include <new>
+
+#include "ofd_common.cuh"
+
+struct ofd_pair_pipeline {
+    static constexpr int NSLOT = 3;
+    int device, H, W, chunk;
+    cudaStream_t st[NSLOT];
+    float* d_in[NSLOT];   // img0 (3) | depth0 (1) per frame, frames contiguous per plane group
+    float* d_out[NSLOT];  // img1 (3) | depth1 (1) | back_flow (2) | flow (2) | valid (1) | collision (1)
+    float* d_s[NSLOT];
+};
+
+using namespace ofd;
+
+#define OFD_CUDA(call)                                                                    \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out) {
+    if (!out) return fail(OFD_E_NULL, "ofd_pair_pipeline_create: out is NULL");
+    if (H <= 0 || W <= 0 || chunk_frames <= 0 || chunk_frames > 65535)
+        return fail(OFD_E_SHAPE, "ofd_pair_pipeline_create: bad H/W/chunk_frames");
+    OFD_CUDA(cudaSetDevice(device));
+    ofd_pair_pipeline* p = new (std::nothrow) ofd_pair_pipeline();
+    if (!p) return fail(OFD_E_ARG, "ofd_pair_pipeline_create: out of host memory");
+    p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
+    const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) p->st[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr;
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_in[s], n * 4 * hw * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_out[s], n * 10 * hw * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_s[s], n * sizeof(float));
+        if (e != cudaSuccess) {
+            int rc = fail((int)e, "ofd_pair_pipeline_create: %s", cudaGetErrorString(e));
+            void ofd_pair_pipeline_destroy(ofd_pair_pipeline*);
+            ofd_pair_pipeline_destroy(p);
+            return rc;
+        }
+    }
+    *out = p;
+    return OFD_OK;
+}
+
+void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
+        if (p->st[s]) cudaStreamSynchronize(p->st[s]), cudaStreamDestroy(p->st[s]);
+        cudaFree(p->d_in[s]);
+        cudaFree(p->d_out[s]);
+        cudaFree(p->d_s[s]);
+    }
+    delete p;
+}
+
+// All *_host pointers are HOST memory (page-locked for overlap), dense [B,C,H,W]; flow/collision may be NULL.
+int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host, const float* sBf_host,
+                          int B, float* img1_host, float* depth1_host, float* back_flow_host, float* flow_host,
+                          float* valid_host, float* collision_host) {
+    const char* fn = "ofd_pair_pipeline_run";
+    if (!p) return fail(OFD_E_NULL, "%s: pipeline is NULL", fn);
+    if (B < 0) return fail(OFD_E_SHAPE, "%s: negative B", fn);
+    if (B == 0) return OFD_OK;
+    if (!img0_host || !depth0_host || !sBf_host || !img1_host || !depth1_host || !back_flow_host || !valid_host)
+        return fail(OFD_E_NULL, "%s: NULL host pointer", fn);
+    OFD_CUDA(cudaSetDevice(p->device));
+    const size_t hw = (size_t)p->H * p->W, F = sizeof(float);
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += p->chunk, ++k) {
+        const int s = k % ofd_pair_pipeline::NSLOT;
+        const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
+        cudaStream_t st = p->st[s];
+        float* din = p->d_in[s];
+        float* dimg = din;
+        float* ddep = din + n * 3 * hw;
+        float* dout = p->d_out[s];
+        float* o_img = dout;
+        float* o_dep = o_img + n * 3 * hw;
+        float* o_bf = o_dep + n * hw;
+        float* o_fl = o_bf + n * 2 * hw;
+        float* o_val = o_fl + n * 2 * hw;
+        float* o_col = o_val + n * hw;
+        OFD_CUDA(cudaMemcpyAsync(dimg, img0_host + (size_t)b0 * 3 * hw, n * 3 * hw * F, cudaMemcpyHostToDevice, st));
+        OFD_CUDA(cudaMemcpyAsync(ddep, depth0_host + (size_t)b0 * hw, n * hw * F, cudaMemcpyHostToDevice, st));
+        OFD_CUDA(cudaMemcpyAsync(p->d_s[s], sBf_host + b0, n * F, cudaMemcpyHostToDevice, st));
+        int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[s], (int)n, p->H, p->W, o_img, o_dep, o_bf,
+                                    flow_host ? o_fl : nullptr, o_val, collision_host ? o_col : nullptr, nullptr, st);
+        if (rc) return rc;
+        OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
+        OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
+        OFD_CUDA(cudaMemcpyAsync(back_flow_host + (size_t)b0 * 2 * hw, o_bf, n * 2 * hw * F, cudaMemcpyDeviceToHost, st));
+        if (flow_host)
+            OFD_CUDA(cudaMemcpyAsync(flow_host + (size_t)b0 * 2 * hw, o_fl, n * 2 * hw * F, cudaMemcpyDeviceToHost, st));
+        OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
+        if (collision_host)
+            OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
+    return OFD_OK;
+}
+
+}  // extern "C"

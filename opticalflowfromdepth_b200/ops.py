@@ -1,0 +1,269 @@
+"""Tensor-level operators over the C ABI (include/ofd_b200.h).  torch is used only for device memory and streams.
+
+Every function takes contiguous CUDA tensors, launches on torch's current stream and returns new tensors.
+Batched layouts are [B,C,H,W]; see the header for the exact semantics and the reference lines each op replaces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BACK, EPI_CONCAT, EPI_NONE, F32, F64  # noqa: F401  (re-exported)
+
+_DT = {torch.float32: F32, torch.float64: F64}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check(name: str, t: torch.Tensor, dtype=None, shape=None):
+    # same wording as the reference's CHECK_INPUT (alt_cuda/fw_cuda.cpp:11-13)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+class _KeyWorkspace:
+    """Per (device, stream) cache of the packed-key plane.  Armed once; splats leave it armed."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device: torch.device, B: int, H: int, W: int):
+        need = _lib.load().ofd_workspace_bytes(B, H, W)
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+            _lib.call("ofd_workspace_reset", _ptr(buf), C.c_size_t(buf.numel()), _stream(device))
+            self._bufs[key] = buf
+        return buf
+
+    def poison(self, device: torch.device):
+        """Forget cached buffers of a device (after a failed call the keys may be half-consumed)."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        for k in [k for k in self._bufs if k[0] == idx]:
+            del self._bufs[k]
+
+    def clear(self):
+        self._bufs.clear()
+
+
+workspace = _KeyWorkspace()
+
+
+def new_counters(device) -> torch.Tensor:
+    """A zeroed counter block (uint64 slots, see OFD_CNT_* in the header), stored as int64."""
+    return torch.zeros(_lib.CNT_SLOTS, dtype=torch.int64, device=device)
+
+
+def _run_splat(fn: str, device, *args):
+    try:
+        _lib.call(fn, *args)
+    except Exception:
+        workspace.poison(device)
+        raise
+
+
+def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
+    """fw_cuda.forward_warping (alt_cuda/fw_cuda.cpp:15-26) on [B,C,H,W] / [B,1,H,W] float32 tensors."""
+    for n, t in (("obj", obj), ("safe_y", safe_y), ("safe_x", safe_x), ("depth", depth)):
+        _check(n, t)
+    if obj.dim() != 4:
+        raise ValueError("obj must be [B,C,H,W]")
+    B, Cc, H, W = obj.shape
+    for n, t in (("safe_y", safe_y), ("safe_x", safe_x), ("depth", depth)):
+        _check(n, t, dtype=obj.dtype, shape=(B, 1, H, W))
+    if obj.dtype != torch.float32:
+        raise TypeError("the device path is float32; use fw_cuda.forward_warping for the float64 dispatch")
+    out = torch.empty_like(obj)
+    valid = torch.empty_like(depth)
+    collision = torch.empty_like(depth)
+    winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
+    ws = workspace.get(obj.device, B, H, W)
+    _run_splat("ofd_splat_targets", obj.device, _ptr(obj), _ptr(safe_y), _ptr(safe_x), _ptr(depth), F32, B, Cc, H, W,
+               _ptr(out), _ptr(valid), _ptr(collision), _ptr(winner), _ptr(counters), _ptr(ws),
+               C.c_size_t(ws.numel()), _stream(obj.device))
+    return (out, valid, collision, winner) if want_winner else (out, valid, collision)
+
+
+def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None):
+    """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32."""
+    _check("obj", obj, dtype=torch.float32)
+    if obj.dim() != 4:
+        raise ValueError("obj must be [B,C,H,W]")
+    B, Cc, H, W = obj.shape
+    _check("flow", flow, dtype=(torch.float32, torch.float64), shape=(B, 2, H, W))
+    _check("depth", depth, dtype=torch.float32, shape=(B, 1, H, W))
+    if aux is not None:
+        _check("aux", aux, dtype=torch.float32, shape=(B, Cc, H, W))
+    out = torch.empty_like(obj)
+    valid = torch.empty_like(depth)
+    collision = torch.empty_like(depth)
+    winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
+    ws = workspace.get(obj.device, B, H, W)
+    _run_splat("ofd_splat_flow", obj.device, _ptr(obj), _ptr(flow), _DT[flow.dtype], _ptr(depth), B, Cc, H, W,
+               _ptr(out), _ptr(valid), _ptr(collision), _ptr(winner), int(epilogue), _ptr(aux), _ptr(counters),
+               _ptr(ws), C.c_size_t(ws.numel()), _stream(obj.device))
+    return (out, valid, collision, winner) if want_winner else (out, valid, collision)
+
+
+def disparity_flow(depth, sBf):
+    """Convert.depth_to_disparity + disparity_to_flow (preprocess.py:239-254): depth[B,1,H,W] -> flow[B,2,H,W]."""
+    _check("depth", depth, dtype=(torch.float32, torch.float64))
+    B, _, H, W = depth.shape
+    _check("sBf", sBf, dtype=torch.float32, shape=(B,))
+    flow = torch.empty((B, 2, H, W), dtype=depth.dtype, device=depth.device)
+    _lib.call("ofd_disparity_flow", _ptr(depth), _DT[depth.dtype], _ptr(sBf), B, H, W, _ptr(flow), _stream(depth.device))
+    return flow
+
+
+def disparity_pair(img0, depth0, sBf, want_flow=True, want_collision=True, counters=None, out=None):
+    """One fused virtual-stereo flow pair (preprocess.py:355-366 minus inpaint).
+
+    Returns (img1[B,3,H,W], depth1[B,1,H,W], back_flow[B,2,H,W], flow[B,2,H,W]|None, valid, collision|None).
+    `out` may hold those six tensors preallocated (None entries are skipped outputs) to keep the allocator out of a
+    timed loop."""
+    _check("img0", img0, dtype=torch.float32)
+    B, c3, H, W = img0.shape
+    if c3 != 3:
+        raise ValueError("img0 must be [B,3,H,W]")
+    _check("depth0", depth0, dtype=(torch.float32, torch.float64), shape=(B, 1, H, W))
+    _check("sBf", sBf, dtype=torch.float32, shape=(B,))
+    dev = img0.device
+    if out is None:
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = (torch.empty((B, 3, H, W), **f32), torch.empty((B, 1, H, W), **f32), torch.empty((B, 2, H, W), **f32),
+               torch.empty((B, 2, H, W), **f32) if want_flow else None, torch.empty((B, 1, H, W), **f32),
+               torch.empty((B, 1, H, W), **f32) if want_collision else None)
+    else:
+        for n, t, c in zip(("img1", "depth1", "back_flow", "flow", "valid", "collision"), out, (3, 1, 2, 2, 1, 1)):
+            if t is not None:
+                _check(n, t, dtype=torch.float32, shape=(B, c, H, W))
+    img1, depth1, back, flow, valid, coll = out
+    _lib.call("ofd_disparity_pair", _ptr(img0), _ptr(depth0), _DT[depth0.dtype], _ptr(sBf), B, H, W, _ptr(img1),
+              _ptr(depth1), _ptr(back), _ptr(flow), _ptr(valid), _ptr(coll), _ptr(counters), _stream(dev))
+    return img1, depth1, back, flow, valid, coll
+
+
+def reproject_flow(depth, cam, eps=1e-7):
+    """Convert.depth_to_random_flow (preprocess.py:265-298) fused: depth[B,1,H,W] f32|f64, cam[B,21] f32 -> flow[B,2,H,W]."""
+    _check("depth", depth, dtype=(torch.float32, torch.float64))
+    B, _, H, W = depth.shape
+    _check("cam", cam, dtype=torch.float32, shape=(B, 21))
+    flow = torch.empty((B, 2, H, W), dtype=torch.float32, device=depth.device)
+    _lib.call("ofd_reproject_flow", _ptr(depth), _DT[depth.dtype], _ptr(cam), C.c_float(eps), B, H, W, _ptr(flow),
+              _stream(depth.device))
+    return flow
+
+
+def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_valid=False, counters=None):
+    """Image+flow splat of the frame pipeline (preprocess.py:372-382): returns
+    (img_out, depth_out, back_flow, valid', collision|None, raw_valid|None)."""
+    _check("img", img, dtype=torch.float32)
+    B, c3, H, W = img.shape
+    if c3 != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    _check("depth", depth, dtype=torch.float32, shape=(B, 1, H, W))
+    _check("flow", flow, dtype=torch.float32, shape=(B, 2, H, W))
+    if valid_in is not None:
+        _check("valid_in", valid_in, dtype=torch.float32, shape=(B, 1, H, W))
+    dev = img.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    img_o = torch.empty((B, 3, H, W), **f32)
+    dep_o = torch.empty((B, 1, H, W), **f32)
+    back = torch.empty((B, 2, H, W), **f32)
+    valid = torch.empty((B, 1, H, W), **f32)
+    coll = torch.empty((B, 1, H, W), **f32) if want_collision else None
+    raw = torch.empty((B, 1, H, W), **f32) if want_raw_valid else None
+    ws = workspace.get(dev, B, H, W)
+    _run_splat("ofd_frame_splat", dev, _ptr(img), _ptr(depth), _ptr(flow), _ptr(valid_in), B, H, W, _ptr(img_o),
+               _ptr(dep_o), _ptr(back), _ptr(valid), _ptr(coll), _ptr(raw), _ptr(counters), _ptr(ws),
+               C.c_size_t(ws.numel()), _stream(dev))
+    return img_o, dep_o, back, valid, coll, raw
+
+
+def normalize_depth(depth):
+    """utils.normalize_depth (utils.py:102-116), out of place, per frame of depth[B,1,H,W] (f32|f64)."""
+    _check("depth", depth, dtype=(torch.float32, torch.float64))
+    B, _, H, W = depth.shape
+    out = torch.empty_like(depth)
+    scratch = torch.empty(2 * max(B, 1), dtype=torch.int64, device=depth.device)
+    _lib.call("ofd_normalize_depth", _ptr(depth), _DT[depth.dtype], B, H, W, _ptr(out), _ptr(scratch), _stream(depth.device))
+    return out
+
+
+def fix_warped_depth_(depth):
+    """utils.fix_warped_depth (utils.py:123-126), in place."""
+    _check("depth", depth, dtype=torch.float32)
+    _lib.call("ofd_fix_warped_depth", _ptr(depth), C.c_size_t(depth.numel()), _stream(depth.device))
+    return depth
+
+
+def special_flow(kind: int, params, H: int, W: int, device):
+    """SpecialFlow (preprocess.py:24-105): returns (flow[2,H,W], back_flow[2,H,W]); params = 10 host floats or None."""
+    flow = torch.empty((2, H, W), dtype=torch.float32, device=device)
+    back = torch.empty((2, H, W), dtype=torch.float32, device=device)
+    arr = None
+    if params is not None:
+        arr = (C.c_float * 10)(*[float(v) for v in params])
+    _lib.call("ofd_special_flow", int(kind), arr, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
+    return flow, back
+
+
+def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
+    """One iteration of sparse_bilateral_filtering (bilateral_filter.py:33-58) on [H,W] f32|f64 CUDA tensors."""
+    _check("depth_in", depth_in, dtype=(torch.float32, torch.float64))
+    _check("depth_orig", depth_orig, dtype=depth_in.dtype, shape=depth_in.shape)
+    if depth_in.dim() != 2:
+        raise ValueError("depth must be [H,W]")
+    H, W = depth_in.shape
+    out = torch.empty_like(depth_in)
+    _lib.call("ofd_bilateral_iter", _ptr(depth_in), _ptr(depth_orig), _DT[depth_in.dtype], H, W, int(window),
+              C.c_double(threshold), _ptr(out), _stream(depth_in.device))
+    return out
+
+
+class PairPipeline:
+    """Host-buffer front end (ofd_pair_pipeline_*): pinned CPU tensors in, pinned CPU tensors out."""
+
+    def __init__(self, device: int, H: int, W: int, chunk_frames: int = 8):
+        self._h = C.c_void_p(0)
+        self.H, self.W = H, W
+        _lib.call("ofd_pair_pipeline_create", int(device), H, W, int(chunk_frames), C.byref(self._h))
+
+    def run(self, img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision):
+        B = img0.shape[0]
+        for n, t in (("img0", img0), ("depth0", depth0), ("sBf", sBf), ("img1", img1), ("depth1", depth1),
+                     ("back_flow", back_flow), ("flow", flow), ("valid", valid), ("collision", collision)):
+            if t is None:
+                continue
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
+        _lib.call("ofd_pair_pipeline_run", self._h, _ptr(img0), _ptr(depth0), _ptr(sBf), B, _ptr(img1), _ptr(depth1),
+                  _ptr(back_flow), _ptr(flow), _ptr(valid), _ptr(collision))
+
+    def close(self):
+        if self._h:
+            _lib.load().ofd_pair_pipeline_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,300 @@
+"""Flow-synthesis operators with the names and argument meaning of the reference's preprocess.py / utils.py
+(`Plausible`, `Convert`, `ConcatFlow`, `BackFlow`, `SpecialFlow`, `augment_flow`, `normalize_depth`,
+`fix_warped_depth`, `get_random`, `set_seed`), each backed by one fused libofd_b200 kernel instead of a chain of
+torch ops, plus batched frame-level entry points (`synthesize_pairs`, `synthesize_group`).
+
+Random numbers are drawn on the host with torch's CPU generator in the reference's order (utils.py:96-100), so a
+`set_seed` + call sequence reproduces the reference's poses and disparity scales exactly.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import geometry, ops
+from .fw import FW
+
+__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "normalize_depth",
+           "fix_warped_depth", "get_random", "set_seed", "synthesize_pairs", "synthesize_group"]
+
+
+# ---- utils.py helpers ------------------------------------------------------------------------------------------
+def set_seed(seed=42):
+    """utils.set_seed (utils.py:178-188) without the cudnn switches."""
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def get_random(random_range, random_begin, random_sign=True):
+    """utils.get_random (utils.py:96-100): optional sign draw (randint) THEN the magnitude draw (rand)."""
+    sign = torch.randint(0, 2, (1,))[0] * 2 - 1 if random_sign else torch.tensor(1)
+    value = torch.rand(1)[0] * random_range + torch.tensor(random_begin)
+    return sign * value
+
+
+def normalize_depth(depth):
+    """utils.normalize_depth (utils.py:102-116) for depth[1,H,W] or [B,1,H,W] CUDA tensors; out of place."""
+    d = depth if depth.dim() == 4 else depth.unsqueeze(0)
+    with torch.cuda.device(d.device):
+        out = ops.normalize_depth(d.contiguous())
+    return out if depth.dim() == 4 else out.squeeze(0)
+
+
+def fix_warped_depth(depth):
+    """utils.fix_warped_depth (utils.py:123-126): in place, returns its argument."""
+    if depth.is_contiguous() and depth.dtype == torch.float32:
+        with torch.cuda.device(depth.device):
+            return ops.fix_warped_depth_(depth)
+    fixed = ops.fix_warped_depth_(depth.float().contiguous())
+    depth.copy_(fixed)
+    return depth
+
+
+# ---- preprocess.py:184-235 -------------------------------------------------------------------------------------
+class Plausible:
+    @staticmethod
+    def f():
+        return 1
+
+    @staticmethod
+    def B():
+        return 50
+
+    @staticmethod
+    def K(size, another=False):
+        """Pinhole intrinsics fx=.58w, fy=.58h, cx=.5w, cy=.5h as [1,4,4] and their inverse (preprocess.py:194-209)."""
+        h, w = size
+        K = torch.eye(4, dtype=torch.float32).unsqueeze(0)
+        K[0, 0, 0] = 0.58
+        K[0, 1, 1] = 0.58
+        K[0, 0, 2] = 0.5
+        K[0, 1, 2] = 0.5
+        if another:
+            K[:, :2, :2] *= 2
+        K[:, 0, :] *= w
+        K[:, 1, :] *= h
+        return K, torch.linalg.inv(K)
+
+    @staticmethod
+    def random_motion(axisangle_range, axisangle_base, translation_range, translation_base,
+                      another_axisangle=None, another_translation=None):
+        """Random pose (preprocess.py:212-235); draw order ax, ay, az, cx, cy, cz."""
+        ang = [get_random(math.pi * axisangle_range, math.pi * axisangle_base) for _ in range(3)]
+        mot = [get_random(translation_range, translation_base) for _ in range(3)]
+        axisangle = torch.tensor([[ang]], dtype=torch.float32)
+        translation = torch.tensor([[mot]], dtype=torch.float32)
+        if another_axisangle is not None and another_translation is not None:
+            T = geometry.transformation_from_parameters(axisangle + another_axisangle, translation + another_translation)
+        else:
+            T = geometry.transformation_from_parameters(axisangle, translation)
+        return T, axisangle, translation
+
+
+# ---- preprocess.py:237-298 -------------------------------------------------------------------------------------
+class Convert:
+    @staticmethod
+    def disparity_scale():
+        """s * B * f as the reference forms it (preprocess.py:240-243): a float32 0-dim tensor."""
+        s = get_random(0.3, 0.8, random_sign=False)
+        return s * Plausible.B() * Plausible.f()
+
+    @staticmethod
+    def depth_to_disparity(depth):
+        sBf = Convert.disparity_scale()
+        flow = Convert._disparity_flow(depth, sBf)
+        return flow[0:1] * -1.0  # disparity = -flow.x exactly
+
+    @staticmethod
+    def _disparity_flow(depth, sBf):
+        d = depth.unsqueeze(0).contiguous()
+        if d.dtype not in (torch.float32, torch.float64):
+            d = d.float()
+        s = torch.as_tensor(sBf, dtype=torch.float32).reshape(1).to(d.device)
+        with torch.cuda.device(d.device):
+            return ops.disparity_flow(d, s).squeeze(0)
+
+    @staticmethod
+    def depth_to_disparity_flow(depth, device=None):
+        """depth_to_disparity + disparity_to_flow(random_sign=False) in one kernel (preprocess.py:356-357)."""
+        return Convert._disparity_flow(depth.to(device) if device is not None else depth, Convert.disparity_scale())
+
+    @staticmethod
+    def disparity_to_flow(disparity, device=None, random_sign=True):
+        flow = torch.cat((disparity, torch.zeros_like(disparity)), axis=0) * -1.0
+        if random_sign:
+            flow = flow * get_random(0, 1)
+        return flow.to(device)
+
+    @staticmethod
+    def disparity_to_depth(disparity):
+        return Plausible.B() * Plausible.f() / (disparity + 0.005)
+
+    @staticmethod
+    def depth_to_random_flow(depth, device=None, segment=None, T1=None):
+        """Random 6-DoF reprojection flow (preprocess.py:265-298): depth[1,h,w] -> (flow[2,h,w] float32, T1[1,4,4])."""
+        _, h, w = depth.shape
+        K, inv_K = Plausible.K((h, w))
+        if T1 is None:
+            T1, _, _ = Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
+        dev = torch.device(device) if device is not None else depth.device
+        d = depth.to(dev).unsqueeze(0)
+        if d.dtype not in (torch.float32, torch.float64):
+            d = d.float()
+        flow = geometry.depth_to_flow(d, K, inv_K, T1.cpu())
+        return flow.squeeze(0), T1.to(dev)
+
+
+# ---- preprocess.py:301-326 -------------------------------------------------------------------------------------
+class ConcatFlow(nn.Module):
+    """flowAC on A's grid = valid * (FW(flowBC, back_flowAB, depthB) + flowAB); add+mask fused in the gather."""
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.device = device
+        self.fw = FW(device)
+
+    def forward(self, flowAB, back_flowAB, flowBC, imgB_depth):
+        concat, valid, _ = self.fw(flowBC, back_flowAB, imgB_depth, epilogue=ops.EPI_CONCAT, aux=flowAB)
+        return concat, valid
+
+
+class BackFlow(nn.Module):
+    """back_flowAB on B's grid = -valid * FW(flowAB, flowAB, depthA); negate+mask fused in the gather."""
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.device = device
+        self.fw = FW(device)
+
+    def forward(self, flowAB, imgA_depth):
+        back, valid, _ = self.fw(flowAB, flowAB, imgA_depth, epilogue=ops.EPI_BACK)
+        return back, valid
+
+
+# ---- preprocess.py:24-105 --------------------------------------------------------------------------------------
+class SpecialFlow(nn.Module):
+    """Analytic augmentation flows; returns (p1 - p0, p_prev - p0) as [2,h,w] float32 tensors.
+
+    Like the reference, a fresh instance always takes the vertical-flip branch and the [[1,s],[0,1]] shear branch
+    (the toggles at preprocess.py:49,83 flip from their initial True on first use)."""
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.device = device
+        self.horizontal_flip = True
+        self.horizontal_shear = True
+
+    def forward(self, size, augment_flow_type):
+        h, w = size
+        dev = self.device if self.device is not None else "cuda"
+        if augment_flow_type >= 7.:
+            self.horizontal_shear = not self.horizontal_shear
+            s = get_random(0.15, 0.2)
+            if self.horizontal_shear:
+                m, mrev = [1, 0, s, 1], [1, 0, -s, 1]
+            else:
+                m, mrev = [1, s, 0, 1], [1, -s, 0, 1]
+            params = [0.0, 0.0] + [float(v) for v in m + mrev]
+            kind = 7
+        elif augment_flow_type >= 6.:
+            c0 = (get_random(w / 4, w / 2) + w / 2, get_random(h / 4, h / 2) + h / 2)
+            c0 = torch.tensor(c0)
+            theta = torch.deg2rad(get_random(2, 8))
+            rot = torch.tensor([[torch.cos(theta), -torch.sin(theta)], [torch.sin(theta), torch.cos(theta)]]).type(torch.float32)
+            rev = torch.tensor([[torch.cos(-theta), -torch.sin(-theta)], [torch.sin(-theta), torch.cos(-theta)]]).type(torch.float32)
+            params = [float(c0[0]), float(c0[1])] + [float(v) for v in rot.reshape(-1)] + [float(v) for v in rev.reshape(-1)]
+            kind = 6
+        elif augment_flow_type >= 5.:
+            self.horizontal_flip = not self.horizontal_flip
+            if self.horizontal_flip:
+                raise NotImplementedError("horizontal flip is unreachable in the reference (fresh instance per call)")
+            params, kind = None, 5
+        else:
+            raise ValueError("augment_flow_type must be >= 5 for a special flow")
+        with torch.cuda.device(dev):
+            return ops.special_flow(kind, params, h, w, dev)
+
+
+def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device=None, augment_flow_type=None,
+                 inpaint=None):
+    """Geometric branch of preprocess.augment_flow (preprocess.py:116-147): 6 splats.  `inpaint(img, valid, collision)`
+    is the caller's hole filler (utils.inpaint in the reference — CPU OpenCV, outside this path); None skips it."""
+    _, h, w = img0.shape
+    if augment_flow_type is None:
+        augment_flow_type = get_random(8, 0, False)
+    if augment_flow_type < 5.:
+        raise NotImplementedError("photometric augmentation types 0-2 do no warping and are outside this path")
+    fw, cf, bf, sf = FW(device), ConcatFlow(device), BackFlow(device), SpecialFlow(device)
+    special_flow, back_special_flow = sf((h, w), augment_flow_type)
+    aug0_flow, _ = cf(back_special_flow, special_flow, flow01, img0_depth)
+    aug1_flow, _ = cf(flow01, back_flow01, special_flow, img1_depth)
+
+    def warp(img, depth):
+        allc, valid, collision = fw(torch.cat((img, depth), axis=0), special_flow, depth)
+        a_img, a_depth = allc[0:3], fix_warped_depth(allc[3:4].contiguous())
+        if inpaint is not None:
+            a_img = inpaint(a_img, valid, collision)
+        return a_img, a_depth
+
+    aug_img0, aug_img0_depth = warp(img0, img0_depth)
+    aug_img1, aug_img1_depth = warp(img1, img1_depth)
+    back_aug0_flow, _ = bf(aug0_flow, aug_img0_depth)
+    back_aug1_flow, _ = bf(aug1_flow, img0_depth)
+    return ((aug_img0, aug_img0_depth, aug0_flow, back_aug0_flow, img1, img1_depth),
+            (img0, img0_depth, aug1_flow, back_aug1_flow, aug_img1, aug_img1_depth),
+            int(augment_flow_type), (special_flow, back_special_flow))
+
+
+# ---- batched frame-level entry points ----------------------------------------------------------------------------
+@torch.no_grad()
+def synthesize_pairs(img0, depth0, sBf, want_flow=True, want_collision=True, counters=None):
+    """Batched virtual-stereo pair synthesis (preprocess.py:356-365 minus inpaint), ONE kernel for the batch.
+
+    img0[B,3,H,W] f32, depth0[B,1,H,W] f32|f64 (already normalised), sBf[B] f32 (= s*B*f per frame), all CUDA.
+    Returns dict(img1, depth1, back_flow, flow, valid, collision)."""
+    with torch.cuda.device(img0.device):
+        img1, depth1, back, flow, valid, coll = ops.disparity_pair(img0, depth0, sBf, want_flow, want_collision, counters)
+    return dict(img1=img1, depth1=depth1, back_flow=back, flow=flow, valid=valid, collision=coll)
+
+
+@torch.no_grad()
+def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
+    """The reference's 5-pair group of one frame batch (preprocess.py:356-432), inpaint optional, all on the GPU:
+    7 splats, 2 reprojections (same pose), 1 disparity flow, 2 flow concatenations = 12 kernel launches per batch.
+
+    img0[B,3,H,W], depth0[B,1,H,W] f32 (normalised), sBf[B], cam1/cam0 built from the same pose: cam[B,21] float32.
+    Returns a dict of tensors named as in preprocess.py."""
+    dev = img0.device
+    fill = (lambda im, v, c: im) if inpaint is None else inpaint
+    with torch.cuda.device(dev):
+        # pair 0->1: virtual stereo (preprocess.py:356-366)
+        img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, True, counters)
+        img1 = fill(img1, valid1, coll1)
+        # pair 1->2: random camera motion from view 1 (preprocess.py:372-382)
+        flow12 = ops.reproject_flow(depth1, cam)
+        img2, depth2, back12, valid2, coll2, _ = ops.frame_splat(img1, depth1, flow12, valid1, counters=counters)
+        img2 = fill(img2, valid2, coll2)
+        # pair 0->3: the same motion from view 0 (preprocess.py:385-394)
+        flow03 = ops.reproject_flow(depth0, cam)
+        img3, depth3, back03, valid3, coll3, _ = ops.frame_splat(img0, depth0, flow03, None, counters=counters)
+        img3 = fill(img3, valid3, coll3)
+        # pair 0->2': concatenated flow (preprocess.py:400-411)
+        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01)
+        img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, counters=counters)
+        img2p = fill(img2p, valid2p, coll2p)
+        # pair 1->3': (preprocess.py:414-424)
+        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
+        flow13_valid = flow13_valid * valid1
+        img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, counters=counters)
+        img3p = fill(img3p, valid3p, coll3p)
+    return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,
+                img2_prime=img2p, depth2_prime=depth2p, img3_prime=img3p, depth3_prime=depth3p,
+                flow01=flow01, back_flow01=back01, flow12=flow12, back_flow12=back12, flow02=flow02,
+                back_flow02_prime=back02p, flow03=flow03, back_flow03=back03, flow13=flow13, back_flow13_prime=back13p,
+                valid1=valid1, valid2=valid2, valid3=valid3, valid2_prime=valid2p, valid3_prime=valid3p)

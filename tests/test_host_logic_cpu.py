@@ -1,0 +1,87 @@
+"""Host-side logic that needs no GPU: RNG draw order, camera constants, sharding, the product/oracle firewall."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from opticalflowfromdepth_b200 import geometry, sweep, synthesis, synthetic
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_random_motion_and_disparity_scale_follow_the_reference_draw_order(golden):
+    g = golden("pipeline_case")
+    synthesis.set_seed(12345 + 11)
+    sBf = synthesis.Convert.disparity_scale()
+    T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
+    assert np.float32(sBf.item()) == g["sBf"]
+    assert np.array_equal(T1.numpy(), g["T1"])
+
+
+def test_intrinsics_match_reference(golden):
+    g = golden("reproject_cases")
+    for tag in ("f32", "f64", "f32b"):
+        h, w = g[f"{tag}_depth"].shape[1:]
+        K, invK = synthesis.Plausible.K((h, w))
+        assert np.array_equal(K.numpy(), g[f"{tag}_K"]) and np.array_equal(invK.numpy(), g[f"{tag}_invK"])
+
+
+def test_transformation_from_parameters_invert():
+    aa = torch.tensor([[[0.1, -0.12, 0.09]]])
+    tr = torch.tensor([[[0.15, -0.11, 0.18]]])
+    M = geometry.transformation_from_parameters(aa, tr)
+    Mi = geometry.transformation_from_parameters(aa, tr, invert=True)
+    assert torch.allclose(M @ Mi, torch.eye(4)[None], atol=1e-6)
+    cam = geometry.camera_constants(*synthesis.Plausible.K((48, 64)), M)
+    assert cam.shape == (1, 21) and cam.dtype == torch.float32
+
+
+def test_special_flow_parameters_follow_reference_draws(golden, monkeypatch):
+    g = golden("special_cases")
+    import contextlib
+
+    seen = {}
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(synthesis.ops, "special_flow", lambda kind, params, h, w, dev: seen.update(kind=kind, params=params) or (None, None))
+    for kind in (6, 7):
+        for rep, (h, w) in enumerate(((23, 31), (46, 62))):
+            synthesis.set_seed(1000 + 10 * kind + rep)
+            synthesis.SpecialFlow("cpu")((h, w), float(kind))
+            assert seen["kind"] == kind
+            assert np.allclose(seen["params"], g[f"k{kind}_{rep}_params"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("n,split", [(1505, 1), (1505, 4), (1698, 8), (10, 3), (7, 8), (0, 2)])
+def test_shards_partition_the_index_range(n, split):
+    for fn in (sweep.shard_range, sweep.shard_strided):
+        parts = [list(fn(n, split, k)) for k in range(split)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(n))
+    # reference arithmetic, preprocess.py:543-547
+    split_len = (n + split - 1) // split
+    for k in range(split):
+        r = sweep.shard_range(n, split, k)
+        if len(r):
+            assert r.start == k * split_len
+    assert sweep.frame_seed(5, 1, 1505) == 12345 + 5 + 1505
+
+
+def test_synthetic_frames_are_deterministic_and_dataset_shaped():
+    a, da = synthetic.diml_frame(7, 48, 64)
+    b, db = synthetic.diml_frame(7, 48, 64)
+    assert np.array_equal(a, b) and np.array_equal(da, db)
+    assert a.dtype == np.float32 and a.min() >= 0 and a.max() <= 255 and da.shape == (1, 48, 64)
+    assert 0 < da.min() and np.isfinite(da).all()
+    sizes = synthetic.redweb_sizes(16)
+    assert all(0.25e6 < h * w < 2.2e6 and h % 2 == 0 and w % 2 == 0 for h, w in sizes)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the product may import or load it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|oracle/", re.M)
+    for base in ("opticalflowfromdepth_b200", "dropin"):
+        for f in (ROOT / base).rglob("*"):
+            if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
+                assert not pat.search(f.read_text()), f"{f} references the oracle"

@@ -1,0 +1,145 @@
+"""The oracle against the golden vectors generated from the reference's own Python (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import bilateral as obil
+from oracle import flow as oflow
+
+FW_TAGS = ["A", "B", "C", "D", "E", "F"]
+
+
+@pytest.mark.parametrize("tag", FW_TAGS)
+def test_fw_prologue_and_splat_match_reference(golden, tag):
+    g = golden("fw_cases")
+    obj, flow, depth = g[f"{tag}_obj"], g[f"{tag}_flow"], g[f"{tag}_depth"]
+    sx, sy = oracle.fw_targets(flow)
+    assert np.array_equal(sx, g[f"{tag}_safe_x"]) and np.array_equal(sy, g[f"{tag}_safe_y"])
+    out, valid, coll, rc = oracle.splat_literal(obj[None], sy[None, None], sx[None, None], depth[None])
+    assert rc == 0
+    assert np.array_equal(out[0], g[f"{tag}_out"], equal_nan=True)
+    assert np.array_equal(valid[0], g[f"{tag}_valid"]) and np.array_equal(coll[0], g[f"{tag}_coll"])
+    out2, valid2, coll2, winner, dropped = oracle.fw_forward(obj, flow, depth)
+    assert dropped == 0
+    assert np.array_equal(out2, g[f"{tag}_out"], equal_nan=True)
+    assert np.array_equal(valid2, g[f"{tag}_valid"]) and np.array_equal(coll2, g[f"{tag}_coll"])
+    assert np.array_equal(winner, g[f"{tag}_winner"])
+
+
+def _lexsort_splat(safe_x, safe_y, depth, H, W):
+    """Closed form of SURVEY.md section 8c: sort sources by (target, depth, raster id); first of a group wins if depth < 1000."""
+    t = (safe_y.astype(np.int64) * W + safe_x.astype(np.int64)).ravel()
+    d = depth.ravel().astype(np.float32)
+    ok = d < 1000  # NaN -> False
+    winner = np.full(H * W, -1, np.int64)
+    hit = np.zeros(H * W, bool)
+    hit[t] = True
+    src = np.arange(H * W)
+    order = np.lexsort((src[ok], d[ok], t[ok]))
+    ts, ss = t[ok][order], src[ok][order]
+    first = np.ones(ts.size, bool)
+    first[1:] = ts[1:] != ts[:-1]
+    winner[ts[first]] = ss[first]
+    winner[hit & (winner < 0)] = -2
+    return winner.reshape(H, W)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_literal_loop_equals_shared_lut_and_closed_form(seed):
+    rng = np.random.default_rng(seed)
+    H, W, C = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(1, 8))
+    obj = rng.normal(0, 1, (C, H, W)).astype(np.float32)
+    flow = rng.normal(0, rng.uniform(0.5, 30), (2, H, W)).astype(np.float32)
+    depth = rng.integers(1, 4, (1, H, W)).astype(np.float32)  # heavy ties
+    depth[rng.random((1, H, W)) < 0.05] = 1000.0
+    depth[rng.random((1, H, W)) < 0.02] = np.nan
+    depth[rng.random((1, H, W)) < 0.02] = -0.0
+    sx, sy = oracle.fw_targets(flow)
+    o1, v1, c1, rc = oracle.splat_literal(obj[None], sy[None, None], sx[None, None], depth[None])
+    o2, v2, c2, win, _ = oracle.splat_frame(obj, sy, sx, depth)
+    assert rc == 0
+    assert np.array_equal(o1[0], o2) and np.array_equal(v1[0], v2) and np.array_equal(c1[0], c2)
+    assert np.array_equal(win, _lexsort_splat(sx, sy, depth, H, W))
+
+
+def test_convert_oracle_matches_reference(golden):
+    g = golden("convert_cases")
+    for tag in ("f32", "f64"):
+        out = oflow.normalize_depth(torch.from_numpy(g[f"norm_{tag}_in"].copy())[None]).numpy()
+        assert np.array_equal(out, g[f"norm_{tag}_out"])
+        flow = oflow.disparity_flow(torch.from_numpy(out), torch.tensor(g[f"disp_{tag}_sBf"]))
+        assert np.array_equal(flow.numpy(), g[f"disp_{tag}_flow"])
+    assert np.array_equal(oflow.fix_warped_depth(torch.from_numpy(g["fix_in"])).numpy(), g["fix_out"])
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64", "f32b"])
+def test_reproject_oracle_matches_reference(golden, tag):
+    g = golden("reproject_cases")
+    torch.set_num_threads(1)
+    flow = oflow.reproject_flow(torch.from_numpy(g[f"{tag}_depth"]), torch.from_numpy(g[f"{tag}_T1"]))
+    # same torch build, same ops: bit-identical on this machine; allow BLAS differences on another host
+    assert np.allclose(flow.numpy(), g[f"{tag}_flow"], rtol=0, atol=2e-3)
+    K, invK = oflow.intrinsics(*g[f"{tag}_depth"].shape[1:])
+    assert np.array_equal(K.numpy(), g[f"{tag}_K"]) and np.allclose(invK.numpy(), g[f"{tag}_invK"], rtol=1e-6)
+
+
+def test_special_flow_oracle_matches_reference(golden):
+    g = golden("special_cases")
+    for kind in (5, 6, 7):
+        for rep, (h, w) in enumerate(((23, 31), (46, 62))):
+            torch.manual_seed(1000 + 10 * kind + rep)
+            f, b, params = oflow.special_flow(h, w, kind)
+            assert np.allclose(f.numpy(), g[f"k{kind}_{rep}_flow"], rtol=0, atol=1e-4)
+            assert np.allclose(b.numpy(), g[f"k{kind}_{rep}_back"], rtol=0, atol=1e-4)
+            if params is not None:
+                assert np.allclose(params, g[f"k{kind}_{rep}_params"])
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64", "f32w3"])
+def test_bilateral_oracle_matches_reference(golden, tag):
+    g = golden("bilateral_cases")
+    fs = [int(v) for v in g[f"{tag}_fs"]]
+    out = obil.sparse_bilateral_filtering(g[f"{tag}_in"].copy(), fs, 0.04, len(fs))
+    assert out.dtype == g[f"{tag}_out"].dtype
+    assert np.array_equal(out, g[f"{tag}_out"], equal_nan=True)
+
+
+def test_rank_table_exceptions(golden):
+    """k(n) = n//2 except where the float32 running sum overshoots 0.5."""
+    k = obil.rank_table(49)
+    assert np.array_equal(k, golden("bilateral_cases")["rank_table"][:50])
+    odd = [n for n in range(1, 50) if k[n] != n // 2]
+    assert all(n % 2 == 0 and k[n] == n // 2 - 1 for n in odd)
+    assert odd == [20, 22, 28, 36, 40, 44, 48]
+
+
+def test_pair_oracle_equals_composition(golden):
+    """oracle.disparity_pair == disparity_flow -> FW -> mask -> fix_warped_depth composed from the pinned pieces."""
+    rng = np.random.default_rng(3)
+    B, H, W = 3, 21, 30
+    img = rng.integers(0, 256, (B, 3, H, W)).astype(np.float32)
+    depth = rng.integers(1, 30, (B, 1, H, W)).astype(np.float32)
+    depth[:, :, 2, 3] = 100.0
+    sBf = rng.uniform(40, 55, B).astype(np.float32)
+    img1, d1, back, flow, valid, coll = oracle.disparity_pair(img, depth, sBf, nthreads=2)
+    for b in range(B):
+        f = oflow.disparity_flow(torch.from_numpy(depth[b]), torch.tensor(sBf[b])).numpy()
+        assert np.array_equal(f, flow[b]) and np.all(np.signbit(flow[b, 1]))
+        obj = np.concatenate([img[b], depth[b], f * -1.0])
+        out, v, c, _, _ = oracle.fw_forward(obj, f, depth[b])
+        assert np.array_equal(v, valid[b]) and np.array_equal(c, coll[b])
+        assert np.array_equal(out[0:3] * v, img1[b])
+        assert np.array_equal(oflow.fix_warped_depth(torch.from_numpy(out[3:4] * v)).numpy(), d1[b])
+        assert np.array_equal(out[4:6] * v, back[b])
+
+
+def test_pipeline_golden_is_consistent_with_oracle(golden):
+    """Recompute pair 0->1 of the reference's group tensor (preprocess.py:437-447) with the oracle."""
+    g = golden("pipeline_case")
+    grp = g["group"]
+    depth0 = oflow.normalize_depth(torch.from_numpy(g["raw_depth"].copy())[None]).numpy()
+    assert np.array_equal(depth0, grp[3:4])
+    img1, d1, back, flow, valid, _ = oracle.disparity_pair(g["img0"][None], depth0[None], np.array([g["sBf"]], np.float32))
+    assert np.array_equal(img1[0], grp[4:7]) and np.array_equal(d1[0], grp[7:8])
+    assert np.array_equal(flow[0], grp[24:26]) and np.array_equal(back[0], grp[26:28])
