@@ -255,104 +255,109 @@ def run_ours(args):
         line["clocks"] = clk.summary()
 
     # ---- secondary numbers, rank 0 only when N > 1 keeps the scaling runs short ------------------------------------------
+    skip = set(filter(None, args.skip.split(",")))
     if world == 1 or args.extras:
         extras = {}
-        # (a) the general path on the same workload: disparity flow + packed-key z-test + gather (3 launches / step)
-        Fg = min(F, 64)
-        ws_warm = ops.frame_splat(img[:Fg], depth[:Fg], ops.disparity_flow(depth[:Fg], sBf[:Fg]), None)
-        del ws_warm
+        if "general" not in skip:
+            # (a) the general path on the same workload: disparity flow + packed-key z-test + gather (3 launches / step)
+            Fg = min(F, 64)
+            ws_warm = ops.frame_splat(img[:Fg], depth[:Fg], ops.disparity_flow(depth[:Fg], sBf[:Fg]), None)
+            del ws_warm
 
-        def gstep():
-            fl = ops.disparity_flow(depth[:Fg], sBf[:Fg])
-            ops.frame_splat(img[:Fg], depth[:Fg], fl, None)
+            def gstep():
+                fl = ops.disparity_flow(depth[:Fg], sBf[:Fg])
+                ops.frame_splat(img[:Fg], depth[:Fg], fl, None)
 
-        tg = timed(gstep, max(K // 2, 5), 3, sync, barrier)
-        per = tg / max(K // 2, 5)
-        extras["general_splat"] = {"pairs_per_s": Fg / per, "ms_per_step": 1e3 * per, "frames_per_step": Fg, "launches_per_step": 3,
-                                   "achieved_GBps": (PAIR_BYTES_PER_PX + 16) * H * W * Fg / per / 1e9,
-                                   "note": "algorithmic bytes 72 B/px: the flow plane is written by one kernel and re-read by z-test and gather"}
-        # (b) cfg3-style: 6-DoF reprojection + C=7 splat + hole mask at 1080p
-        try:
-            Hb, Wb, Fb = 1080, 1920, 8
-            big_img = torch.rand(Fb, 3, Hb, Wb, device=dev) * 255
-            from opticalflowfromdepth_b200 import synthetic
-            raw = np.stack([synthetic.diml_frame(100 + k, Hb, Wb)[1] for k in range(2)])
-            big_depth = ops.normalize_depth(torch.from_numpy(raw).to(dev))[torch.arange(Fb, device=dev) % 2].contiguous()
-            Kc, invK = synthesis.Plausible.K((Hb, Wb))
-            cams = []
-            for k in range(Fb):
-                torch.manual_seed(12345 + k)
-                T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
-                cams.append(geometry.camera_constants(Kc, invK, T1))
-            cam = torch.cat(cams).to(dev)
-            vin = torch.ones(Fb, 1, Hb, Wb, device=dev)
+            tg = timed(gstep, max(K // 2, 5), 3, sync, barrier)
+            per = tg / max(K // 2, 5)
+            extras["general_splat"] = {"pairs_per_s": Fg / per, "ms_per_step": 1e3 * per, "frames_per_step": Fg, "launches_per_step": 3,
+                                       "achieved_GBps": (PAIR_BYTES_PER_PX + 16) * H * W * Fg / per / 1e9,
+                                       "note": "algorithmic bytes 72 B/px: the flow plane is written by one kernel and re-read by z-test and gather"}
+        if "sixdof" not in skip:
+            # (b) cfg3-style: 6-DoF reprojection + C=7 splat + hole mask at 1080p
+            try:
+                Hb, Wb, Fb = 1080, 1920, 8
+                big_img = torch.rand(Fb, 3, Hb, Wb, device=dev) * 255
+                from opticalflowfromdepth_b200 import synthetic
+                raw = np.stack([synthetic.diml_frame(100 + k, Hb, Wb)[1] for k in range(2)])
+                big_depth = ops.normalize_depth(torch.from_numpy(raw).to(dev))[torch.arange(Fb, device=dev) % 2].contiguous()
+                Kc, invK = synthesis.Plausible.K((Hb, Wb))
+                cams = []
+                for k in range(Fb):
+                    torch.manual_seed(12345 + k)
+                    T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
+                    cams.append(geometry.camera_constants(Kc, invK, T1))
+                cam = torch.cat(cams).to(dev)
+                vin = torch.ones(Fb, 1, Hb, Wb, device=dev)
 
-            def bstep():
-                fl = ops.reproject_flow(big_depth, cam)
-                ops.frame_splat(big_img, big_depth, fl, vin)
+                def bstep():
+                    fl = ops.reproject_flow(big_depth, cam)
+                    ops.frame_splat(big_img, big_depth, fl, vin)
 
-            tb = timed(bstep, 10, 3, sync, barrier) / 10
-            extras["sixdof_1080p"] = {"frames_per_s": Fb / tb, "ms_per_step": 1e3 * tb, "frames_per_step": Fb, "launches_per_step": 3,
-                                      "achieved_GBps": (64 + 16) * Hb * Wb * Fb / tb / 1e9,
-                                      "note": "64 B/px fused-pair algorithmic bytes (SURVEY 8d) + 16 B/px for the materialised flow plane"}
-            del big_img, big_depth, vin
-        except Exception as e:  # secondary: never break the headline
-            extras["sixdof_1080p"] = {"error": repr(e)}
-        # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
-        try:
-            import oracle
+                tb = timed(bstep, 10, 3, sync, barrier) / 10
+                extras["sixdof_1080p"] = {"frames_per_s": Fb / tb, "ms_per_step": 1e3 * tb, "frames_per_step": Fb, "launches_per_step": 3,
+                                          "achieved_GBps": (64 + 16) * Hb * Wb * Fb / tb / 1e9,
+                                          "note": "64 B/px fused-pair algorithmic bytes (SURVEY 8d) + 16 B/px for the materialised flow plane"}
+                del big_img, big_depth, vin
+            except Exception as e:  # secondary: never break the headline
+                extras["sixdof_1080p"] = {"error": repr(e)}
+        if "ref" not in skip:
+            # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
+            try:
+                import oracle
 
-            ref = oracle.load_ref_fw_cuda()
-            fl = ops.disparity_flow(depth[:1], sBf[:1])
-            obj = torch.cat((img[:1], depth[:1], fl * -1.0), 1).contiguous()
-            gx, gy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+                ref = oracle.load_ref_fw_cuda()
+                fl = ops.disparity_flow(depth[:1], sBf[:1])
+                obj = torch.cat((img[:1], depth[:1], fl * -1.0), 1).contiguous()
+                gx, gy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
 
-            def ref_call():
-                # alt_cuda/fw.py:27-43 (host meshgrid + H2D every call) then the extension
-                p0 = torch.stack((gx, gy), 0).float().repeat(1, 1, 1, 1).to(dev)
-                p1 = p0 + fl
-                sy = torch.clamp(p1[:, 1:2], min=0, max=H - 1).contiguous().long().float()
-                sx = torch.clamp(p1[:, 0:1], min=0, max=W - 1).contiguous().long().float()
-                return ref.forward_warping(obj, sy, sx, depth[:1])
+                def ref_call():
+                    # alt_cuda/fw.py:27-43 (host meshgrid + H2D every call) then the extension
+                    p0 = torch.stack((gx, gy), 0).float().repeat(1, 1, 1, 1).to(dev)
+                    p1 = p0 + fl
+                    sy = torch.clamp(p1[:, 1:2], min=0, max=H - 1).contiguous().long().float()
+                    sx = torch.clamp(p1[:, 0:1], min=0, max=W - 1).contiguous().long().float()
+                    return ref.forward_warping(obj, sy, sx, depth[:1])
 
-            ref_call()
-            sync()
-            t0 = time.perf_counter()
-            n_ref = 3
-            for _ in range(n_ref):
                 ref_call()
-            sync()
-            per_ref = (time.perf_counter() - t0) / n_ref
-            extras["ref_fw_cuda"] = {"pairs_per_s": 1.0 / per_ref, "ms_per_call": 1e3 * per_ref,
-                                     "achieved_GBps": FW_BYTES_PER_PX(6) * H * W / per_ref / 1e9,
-                                     "what": "reference fw_cuda (alt_cuda/fw_cuda_kernel.cu, unmodified, sm_100a) driven by the fw.py prologue, C=6, one 480x640 frame per call"}
-        except Exception as e:
-            extras["ref_fw_cuda"] = {"unavailable": repr(e)}
+                sync()
+                t0 = time.perf_counter()
+                n_ref = 3
+                for _ in range(n_ref):
+                    ref_call()
+                sync()
+                per_ref = (time.perf_counter() - t0) / n_ref
+                extras["ref_fw_cuda"] = {"pairs_per_s": 1.0 / per_ref, "ms_per_call": 1e3 * per_ref,
+                                         "achieved_GBps": FW_BYTES_PER_PX(6) * H * W / per_ref / 1e9,
+                                         "what": "reference fw_cuda (alt_cuda/fw_cuda_kernel.cu, unmodified, sm_100a) driven by the fw.py prologue, C=6, one 480x640 frame per call"}
+            except Exception as e:
+                extras["ref_fw_cuda"] = {"unavailable": repr(e)}
         line.update(extras)
 
-    # ---- e2e: host buffers -> C-ABI pipeline -> host buffers, copies inside the timed region ---------------------------
-    Fe = args.e2e_frames
-    h_img = torch.from_numpy(img_pool)[torch.arange(Fe) % POOL].contiguous().pin_memory()
-    h_depth = depth[torch.arange(Fe, device=dev) % F].cpu().contiguous().pin_memory()
-    h_s = torch.from_numpy(s_values(Fe)).contiguous()
-    h_out = [torch.empty((Fe, c, H, W), dtype=torch.float32).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
-    pipe = ops.PairPipeline(local, H, W, chunk_frames=args.e2e_chunk)
-    for _ in range(2):
-        pipe.run(h_img, h_depth, h_s, *h_out)
-    barrier()
-    Ke = max(3, min(K, 10))
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        pipe.run(h_img, h_depth, h_s, *h_out)  # returns after the last D2H byte has landed
-    te = time.perf_counter() - t0
-    pipe.close()
-    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-    line["e2e"] = {"value": world * Fe * Ke / float(te_t.item()), "unit": "pairs/s",
-                   "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * 10 * H * W * 4,
-                   "frames_per_step": Fe, "steps": Ke,
-                   "api": "ofd_pair_pipeline_run (C ABI, pinned host buffers in and out, 3-slot H2D/kernel/D2H pipeline)"}
+    if "e2e" not in skip:
+        # ---- e2e: host buffers -> C-ABI pipeline -> host buffers, copies inside the timed region ---------------------------
+        Fe = args.e2e_frames
+        h_img = torch.from_numpy(img_pool)[torch.arange(Fe) % POOL].contiguous().pin_memory()
+        h_depth = depth[torch.arange(Fe, device=dev) % F].cpu().contiguous().pin_memory()
+        h_s = torch.from_numpy(s_values(Fe)).contiguous()
+        h_out = [torch.empty((Fe, c, H, W), dtype=torch.float32).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+        pipe = ops.PairPipeline(local, H, W, chunk_frames=args.e2e_chunk)
+        for _ in range(2):
+            pipe.run(h_img, h_depth, h_s, *h_out)
+        barrier()
+        Ke = max(3, min(K, 10))
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            pipe.run(h_img, h_depth, h_s, *h_out)  # returns after the last D2H byte has landed
+        te = time.perf_counter() - t0
+        pipe.close()
+        te_t = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": world * Fe * Ke / float(te_t.item()), "unit": "pairs/s",
+                       "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * 10 * H * W * 4,
+                       "frames_per_step": Fe, "steps": Ke,
+                       "api": "ofd_pair_pipeline_run (C ABI, pinned host buffers in and out, 3-slot H2D/kernel/D2H pipeline)"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -390,6 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,ref,e2e (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -188,10 +188,243 @@ __global__ void __launch_bounds__(256) pair_row_kernel(const float* __restrict__
     }
 }
 
+// ---- v2: persistent, TMA-in / TMA-out row pipeline ---------------------------------------------------------------
+// ncu on the one-row-per-CTA kernel above showed it ISSUE-bound (sm__throughput 84 %, ~330 instructions per pixel,
+// mostly 64-bit global address arithmetic and scalar stores), not HBM-bound.  Here every global access is a TMA
+// 1-D bulk copy (UBLKCP): input rows are prefetched one row ahead into a 2-stage ring, results are staged in
+// shared memory and written back by bulk stores that drain while the next row is computed; the SIMT threads only
+// touch shared memory (32-bit addressing, no per-pixel global pointer math).  Each thread owns NITER fixed pixels
+// of the row and keeps their target column and ordered depth in registers across the three z-buffer phases.
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory plan of the persistent kernel, in floats after a 64-byte header (4 mbarriers)
+template <typename DT>
+struct PairPlan {
+    static constexpr int kIn = (int)(sizeof(DT) / 4) + 3;  // raw depth row (DT) + 3 colour rows, per input stage
+    static constexpr int kOut = 8;                          // img1 x3, depth1, back_flow.x, flow.x, valid, collision
+    static constexpr int kMisc = 4 + (sizeof(DT) == 8 ? 1 : 0);  // zero row, -0 row, ord, idx (+ float depth row)
+    static __host__ __device__ size_t bytes(int W) { return 64 + (size_t)W * 4 * (2 * kIn + 2 * kOut + kMisc); }
+};
+
+template <typename DT, int NITER>
+__global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __restrict__ img0, const DT* __restrict__ depth0,
+                                                           const float* __restrict__ sBf, float* __restrict__ img1,
+                                                           float* __restrict__ depth1, float* __restrict__ back_flow,
+                                                           float* __restrict__ flow, float* __restrict__ valid,
+                                                           float* __restrict__ collision, uint64_t* __restrict__ counters,
+                                                           int B, int H, int W) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t hw = (size_t)H * W;
+    const int total_rows = B * H;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stage][0 depth, 1 colour]
+    float* base = reinterpret_cast<float*>(smem_raw + 64);
+    typedef PairPlan<DT> Plan;
+    auto in_stage = [&](int s) { return base + (size_t)s * Plan::kIn * W; };
+    auto out_stage = [&](int s) { return base + (size_t)(2 * Plan::kIn + s * Plan::kOut) * W; };
+    float* misc = base + (size_t)(2 * Plan::kIn + 2 * Plan::kOut) * W;
+    float* zero_row = misc;
+    float* negzero_row = misc + W;
+    uint32_t* sord = reinterpret_cast<uint32_t*>(misc + 2 * (size_t)W);
+    uint32_t* sidx = sord + W;
+    float* sdepth32 = misc + 4 * (size_t)W;  // only when DT is double
+
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < W; i += nt) {
+        zero_row[i] = 0.0f;
+        negzero_row[i] = -0.0f;
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    auto issue_loads = [&](int row, int s) {  // thread 0 only
+        const int b = row / H, j = row - b * H;
+        DT* sraw = reinterpret_cast<DT*>(in_stage(s));
+        float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
+        mbar_expect_tx(&bars[2 * s], (unsigned)(W * sizeof(DT)));
+        bulk_g2s(sraw, depth0 + (size_t)b * hw + (size_t)j * W, (unsigned)(W * sizeof(DT)), &bars[2 * s]);
+        mbar_expect_tx(&bars[2 * s + 1], (unsigned)(3 * W * 4));
+        const float* g = img0 + (size_t)b * 3 * hw + (size_t)j * W;
+        for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * W, g + c * hw, (unsigned)(W * 4), &bars[2 * s + 1]);
+    };
+
+    int row = blockIdx.x;
+    if (tid == 0 && row < total_rows) issue_loads(row, 0);
+    unsigned n_hit = 0, n_col = 0, n_px = 0, n_drop = 0;
+
+    for (int n = 0; row < total_rows; ++n, row += gridDim.x) {
+        const int s = n & 1;
+        const unsigned ph = (unsigned)(n >> 1) & 1u;
+        const int b = row / H, j = row - b * H;
+        const DT* sraw = reinterpret_cast<const DT*>(in_stage(s));
+        const float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
+        const float* sdep = sizeof(DT) == 4 ? reinterpret_cast<const float*>(sraw) : sdepth32;
+        float* o_img = out_stage(s);
+        float* o_dep = o_img + 3 * (size_t)W;
+        float* o_bfx = o_dep + W;
+        float* o_flx = o_bfx + W;
+        float* o_val = o_flx + W;
+        float* o_col = o_val + W;
+
+        if (tid == 0) {
+            const int next = row + gridDim.x;
+            if (next < total_rows) issue_loads(next, s ^ 1);  // stage s^1 was released by the barrier ending row n-1
+            bulk_wait_read<1>();                              // the stores of row n-2 have finished reading out_stage(s)
+        }
+#pragma unroll
+        for (int k = 0; k < NITER; ++k) {
+            const int i = tid + k * nt;
+            if (i < W) sord[i] = 0xFFFFFFFFu, sidx[i] = 0xFFFFFFFFu;
+        }
+        mbar_wait(&bars[2 * s], ph);
+        __syncthreads();
+
+        // ---- phase A: disparity, flow, target column, min ordered depth ------------------------------------------
+        const DT sc = (DT)sBf[b];
+        uint32_t tx[NITER], hi[NITER];
+#pragma unroll
+        for (int k = 0; k < NITER; ++k) {
+            const int i = tid + k * nt;
+            tx[k] = T_DROPPED;
+            hi[k] = 0;
+            if (i < W) {
+                const DT d = sraw[i];
+                const DT fx = (sc / d) * (DT)-1.0;
+                DT px = (DT)(float)i + fx;
+                if (px == px) {
+                    px = px < (DT)0 ? (DT)0 : px;
+                    px = px > (DT)(W - 1) ? (DT)(W - 1) : px;
+                    tx[k] = (uint32_t)(int)px;
+                }
+                o_flx[i] = (float)fx;
+                if (sizeof(DT) == 8) sdepth32[i] = (float)d;
+                hi[k] = depth_hi((float)d);
+                if (tx[k] != T_DROPPED)
+                    atomicMin(&sord[tx[k]], hi[k]);
+                else
+                    n_drop++;
+            }
+        }
+        __syncthreads();
+        // ---- phase C: lowest source column among the depth-minimal sources ---------------------------------------
+#pragma unroll
+        for (int k = 0; k < NITER; ++k)
+            if (tx[k] != T_DROPPED && sord[tx[k]] == hi[k]) atomicMin(&sidx[tx[k]], (uint32_t)(tid + k * nt));
+        mbar_wait(&bars[2 * s + 1], ph);
+        __syncthreads();
+        // ---- phase D: gather + epilogue into the staging rows ------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < NITER; ++k) {
+            const int t = tid + k * nt;
+            if (t < W) {
+                const uint32_t h32 = sord[t];
+                const bool hit = h32 != 0xFFFFFFFFu;
+                const bool win = h32 < HI_NOWIN;
+                const uint32_t src = win ? sidx[t] : 0u;
+                const float v = hit ? 1.0f : 0.0f;
+                float r = 0.f, g = 0.f, bl = 0.f, dd = 0.f, bx = 0.f;
+                if (win) {
+                    r = simg[src];
+                    g = simg[W + src];
+                    bl = simg[2 * W + src];
+                    dd = sdep[src];
+                    bx = o_flx[src] * -1.0f;
+                }
+                o_img[t] = r * v;
+                o_img[W + t] = g * v;
+                o_img[2 * W + t] = bl * v;
+                o_dep[t] = fix_depth(dd * v);
+                o_bfx[t] = bx * v;
+                o_val[t] = v;
+                o_col[t] = (hit && !win) ? 1.0f : 0.0f;
+                n_px++;
+                n_hit += hit;
+                n_col += (hit && !win);
+            }
+        }
+        fence_async_smem();  // generic-proxy writes of the staging rows -> visible to the TMA engine
+        __syncthreads();
+        if (tid == 0) {
+            const size_t r1 = (size_t)b * hw + (size_t)j * W;
+            const unsigned rb = (unsigned)(W * 4);
+            float* gi = img1 + (size_t)b * 3 * hw + (size_t)j * W;
+            for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * hw, o_img + (size_t)c * W, rb);
+            bulk_s2g(depth1 + r1, o_dep, rb);
+            float* gb = back_flow + (size_t)b * 2 * hw + (size_t)j * W;
+            bulk_s2g(gb, o_bfx, rb);
+            bulk_s2g(gb + hw, zero_row, rb);
+            if (flow) {
+                float* gf = flow + (size_t)b * 2 * hw + (size_t)j * W;
+                bulk_s2g(gf, o_flx, rb);
+                bulk_s2g(gf + hw, negzero_row, rb);
+            }
+            bulk_s2g(valid + r1, o_val, rb);
+            if (collision) bulk_s2g(collision + r1, o_col, rb);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all();
+    if (counters) {
+        warp_count(counters, OFD_CNT_HIT, n_hit);
+        warp_count(counters, OFD_CNT_HOLE, n_px - n_hit);
+        warp_count(counters, OFD_CNT_COLLISION, n_col);
+        warp_count(counters, OFD_CNT_DROPPED, n_drop);
+    }
+}
+
+template <typename DT>
+static int launch_pair_persistent(const char* fn, const float* img0, const DT* depth0, const float* sBf, int B, int H, int W,
+                                  float* img1, float* depth1, float* back_flow, float* flow, float* valid, float* collision,
+                                  uint64_t* counters, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const size_t smem = PairPlan<DT>::bytes(W);
+    if (smem > 227 * 1024 || (long long)B * H > 0x7FFFFFFFll) return OFD_OK;  // fall back to the one-row kernel
+    // each thread owns NITER pixels of a row; threads = ceil(W / NITER) rounded up to a warp
+    int niter = 4;
+    while ((W + niter - 1) / niter > 1024) niter *= 2;
+    if (niter > 16) return OFD_OK;
+    int threads = ((W + niter - 1) / niter + 31) / 32 * 32;
+    auto kern = niter == 4 ? pair_rows_persistent<DT, 4> : (niter == 8 ? pair_rows_persistent<DT, 8> : pair_rows_persistent<DT, 16>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
+    long long grid = (long long)sms * per_sm;
+    if (grid > (long long)B * H) grid = (long long)B * H;
+    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W);
+    *handled = true;
+    return check_launch(fn);
+}
+
+
 template <typename DT>
 static int launch_pair(const char* fn, const float* img0, const DT* depth0, const float* sBf, int B, int H, int W,
                        float* img1, float* depth1, float* back_flow, float* flow, float* valid, float* collision,
                        uint64_t* counters, cudaStream_t st) {
+    const bool aligned = (W % 4 == 0) && (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 |
+                                            (uintptr_t)back_flow | (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
+    if (aligned) {
+        bool handled = false;
+        int rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,
+                                            counters, st, &handled);
+        if (rc || handled) return rc;
+    }
     const size_t smem = PairSmem<DT>::bytes(W);
     if (smem > 227 * 1024) return fail(OFD_E_SHAPE, "%s: W=%d needs %zu B of shared memory per row (max 227 KB)", fn, W, smem);
     const bool bulk = (W % 4 == 0) && (((uintptr_t)img0 | (uintptr_t)depth0) % 16 == 0);

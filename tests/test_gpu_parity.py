@@ -260,7 +260,7 @@ def test_normalize_fix_and_disparity_flow_bit_exact(pkg, golden):
     for tag in ("f32", "f64"):
         out = pkg.ops.normalize_depth(cu(g[f"norm_{tag}_in"])[None, None])
         assert eq(out[0], g[f"norm_{tag}_out"])
-        flow = pkg.ops.disparity_flow(out, torch.tensor([g[f"disp_{tag}_sBf"]], device=DEV))
+        flow = pkg.ops.disparity_flow(out, torch.tensor([float(g[f"disp_{tag}_sBf"])], device=DEV))
         assert eq(flow[0], g[f"disp_{tag}_flow"])
     assert eq(pkg.synthesis.fix_warped_depth(cu(g["fix_in"])), g["fix_out"])
     batch = np.stack([g["norm_f32_in"], g["norm_f32_in"][::-1].copy() * 0.5])[:, None]
@@ -385,7 +385,7 @@ def test_group_vs_reference_pipeline_golden(pkg, golden):
     depth0 = pkg.ops.normalize_depth(cu(g["raw_depth"])[None, None])
     K, invK = pkg.synthesis.Plausible.K((h, w))
     cam = pkg.geometry.camera_constants(K, invK, torch.from_numpy(g["T1"])).to(DEV)
-    res = pkg.synthesis.synthesize_group(img0, depth0, torch.tensor([g["sBf"]], device=DEV), cam)
+    res = pkg.synthesis.synthesize_group(img0, depth0, torch.tensor([float(g["sBf"])], device=DEV), cam)
     sl = dict(img0=(0, 3), depth0=(3, 4), img1=(4, 7), depth1=(7, 8), img2=(8, 11), depth2=(11, 12), img3=(12, 15),
               depth3=(15, 16), img2_prime=(16, 19), depth2_prime=(19, 20), img3_prime=(20, 23), depth3_prime=(23, 24),
               flow01=(24, 26), back_flow01=(26, 28), flow12=(28, 30), back_flow12=(30, 32), flow02=(32, 34),
