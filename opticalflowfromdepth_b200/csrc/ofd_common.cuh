@@ -77,6 +77,55 @@ __device__ __forceinline__ void warp_count(uint64_t* counters, int slot, unsigne
     if ((threadIdx.x & 31) == 0 && s) atomicAdd((u64*)(counters + slot), (u64)s);
 }
 
+// ---- 6-DoF reprojection flow -----------------------------------------------------------------------------
+struct Cam {  // 21 floats per frame: invK3 row-major (9), P = (K T)[:3,:] row-major (12)
+    float k[9];
+    float p[12];
+};
+
+template <typename DT>
+__device__ __forceinline__ void reproject_px(const Cam& cam, DT depth, int i, int j, int H, int W, float eps,
+                                             float& fx, float& fy) {
+    const float x = (float)i, y = (float)j;
+    // geometry.py:38  cam_points = inv_K[:3,:3] @ (x, y, 1)
+    float ray[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float acc = __fmul_rn(cam.k[3 * r + 0], x);
+        acc = __fmaf_rn(cam.k[3 * r + 1], y, acc);
+        acc = __fmaf_rn(cam.k[3 * r + 2], 1.0f, acc);
+        ray[r] = acc;
+    }
+    // geometry.py:39-40  depth * cam_points in the depth dtype, then .type(float32)
+    float X[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) X[r] = (float)(depth * (DT)ray[r]);
+    // geometry.py:59  P @ (X, 1)
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float acc = __fmul_rn(cam.p[4 * r + 0], X[0]);
+        acc = __fmaf_rn(cam.p[4 * r + 1], X[1], acc);
+        acc = __fmaf_rn(cam.p[4 * r + 2], X[2], acc);
+        acc = __fmaf_rn(cam.p[4 * r + 3], 1.0f, acc);
+        c[r] = acc;
+    }
+    // geometry.py:61  / (z + eps)
+    const float den = __fadd_rn(c[2], eps);
+    float u = __fdiv_rn(c[0], den);
+    float v = __fdiv_rn(c[1], den);
+    // geometry.py:64-66  /= (w-1), /= (h-1), (p - 0.5) * 2
+    u = __fmul_rn(__fsub_rn(__fdiv_rn(u, (float)(W - 1)), 0.5f), 2.0f);
+    v = __fmul_rn(__fsub_rn(__fdiv_rn(v, (float)(H - 1)), 0.5f), 2.0f);
+    // preprocess.py:284-286  (p + 1) / 2, *= (w-1), *= (h-1)
+    // (x / 2 is evaluated as x * 0.5f: a power-of-two scaling, bit-identical to the IEEE division)
+    u = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.0f), 0.5f), (float)(W - 1));
+    v = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), (float)(H - 1));
+    // preprocess.py:288-291  flow = p1 - p0
+    fx = __fsub_rn(u, x);
+    fy = __fsub_rn(v, y);
+}
+
 }  // namespace ofd
 
 // ---- host side error plumbing (ofd_abi.cu owns the storage) ----------------------------------------------

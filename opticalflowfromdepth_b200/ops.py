@@ -197,6 +197,33 @@ def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_v
     return img_o, dep_o, back, valid, coll, raw
 
 
+def reproject_pair(img, depth, cam, valid_in=None, eps=1e-7, want_collision=True, want_raw_valid=False, counters=None):
+    """Fused 6-DoF flow pair (preprocess.py:372-382): the flow is computed inside the z-test and written once.
+    Returns (img_out, depth_out, back_flow, flow, valid', collision|None, raw_valid|None)."""
+    _check("img", img, dtype=torch.float32)
+    B, c3, H, W = img.shape
+    if c3 != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    _check("depth", depth, dtype=torch.float32, shape=(B, 1, H, W))
+    _check("cam", cam, dtype=torch.float32, shape=(B, 21))
+    if valid_in is not None:
+        _check("valid_in", valid_in, dtype=torch.float32, shape=(B, 1, H, W))
+    dev = img.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    img_o = torch.empty((B, 3, H, W), **f32)
+    dep_o = torch.empty((B, 1, H, W), **f32)
+    back = torch.empty((B, 2, H, W), **f32)
+    flow = torch.empty((B, 2, H, W), **f32)
+    valid = torch.empty((B, 1, H, W), **f32)
+    coll = torch.empty((B, 1, H, W), **f32) if want_collision else None
+    raw = torch.empty((B, 1, H, W), **f32) if want_raw_valid else None
+    ws = workspace.get(dev, B, H, W)
+    _run_splat("ofd_reproject_pair", dev, _ptr(img), _ptr(depth), _ptr(cam), C.c_float(eps), _ptr(valid_in), B, H, W,
+               _ptr(img_o), _ptr(dep_o), _ptr(back), _ptr(flow), _ptr(valid), _ptr(coll), _ptr(raw), _ptr(counters),
+               _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+    return img_o, dep_o, back, flow, valid, coll, raw
+
+
 def normalize_depth(depth):
     """utils.normalize_depth (utils.py:102-116), out of place, per frame of depth[B,1,H,W] (f32|f64)."""
     _check("depth", depth, dtype=(torch.float32, torch.float64))

@@ -266,7 +266,8 @@ def synthesize_pairs(img0, depth0, sBf, want_flow=True, want_collision=True, cou
 @torch.no_grad()
 def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
     """The reference's 5-pair group of one frame batch (preprocess.py:356-432), inpaint optional, all on the GPU:
-    7 splats, 2 reprojections (same pose), 1 disparity flow, 2 flow concatenations = 12 kernel launches per batch.
+    7 splats with the flow producers and consumers fused into them = 13 kernel launches per batch chunk
+    (1 fused stereo pair, 6 x (z-test + gather)).
 
     img0[B,3,H,W], depth0[B,1,H,W] f32 (normalised), sBf[B], cam1/cam0 built from the same pose: cam[B,21] float32.
     Returns a dict of tensors named as in preprocess.py."""
@@ -276,13 +277,11 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         # pair 0->1: virtual stereo (preprocess.py:356-366)
         img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, True, counters)
         img1 = fill(img1, valid1, coll1)
-        # pair 1->2: random camera motion from view 1 (preprocess.py:372-382)
-        flow12 = ops.reproject_flow(depth1, cam)
-        img2, depth2, back12, valid2, coll2, _ = ops.frame_splat(img1, depth1, flow12, valid1, counters=counters)
+        # pair 1->2: random camera motion from view 1 (preprocess.py:372-382); flow computed inside the z-test
+        img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
         img2 = fill(img2, valid2, coll2)
         # pair 0->3: the same motion from view 0 (preprocess.py:385-394)
-        flow03 = ops.reproject_flow(depth0, cam)
-        img3, depth3, back03, valid3, coll3, _ = ops.frame_splat(img0, depth0, flow03, None, counters=counters)
+        img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, counters=counters)
         img3 = fill(img3, valid3, coll3)
         # pair 0->2': concatenated flow (preprocess.py:400-411)
         flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01)

@@ -420,6 +420,42 @@ def test_frame_splat_vs_oracle_composition(pkg):
         assert eq(do[b], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v2)).numpy())
 
 
+def test_reproject_pair_equals_unfused_path(pkg):
+    """Flow computed inside the z-test == reproject_flow -> frame_splat."""
+    for (h, w, n) in ((480, 640, 3), (97, 131, 2)):
+        img, depth = _cfg1_inputs(pkg, n, h, w)
+        K, invK = pkg.synthesis.Plausible.K((h, w))
+        cams = []
+        for k in range(n):
+            torch.manual_seed(50 + k)
+            cams.append(pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]))
+        cam = torch.cat(cams).to(DEV)
+        vin = (torch.rand(n, 1, h, w, device=DEV) > 0.1).float()
+        for v in (None, vin):
+            flow = pkg.ops.reproject_flow(depth, cam)
+            a = pkg.ops.frame_splat(img, depth, flow, v, want_raw_valid=True)
+            b = pkg.ops.reproject_pair(img, depth, cam, v, want_raw_valid=True)
+            assert torch.equal(b[3], flow)
+            for x, y in zip(a, (b[0], b[1], b[2], b[4], b[5], b[6])):
+                assert torch.equal(x, y)
+
+
+def test_chunked_batches_match_single_frames(pkg, monkeypatch):
+    """The L2-sized chunk walk (every chunk reuses the same key region) gives the per-frame results."""
+    import os
+
+    img, depth = _cfg1_inputs(pkg, 5, 60, 84)
+    flow = torch.randn(5, 2, 60, 84, device=DEV) * 7
+    monkeypatch.setenv("OFD_SPLAT_CHUNK_FRAMES", "2")
+    whole = pkg.ops.splat_flow(img, flow, depth, want_winner=True)
+    monkeypatch.delenv("OFD_SPLAT_CHUNK_FRAMES")
+    for b in range(5):
+        one = pkg.ops.splat_flow(img[b:b + 1], flow[b:b + 1], depth[b:b + 1], want_winner=True)
+        for x, y in zip(whole, one):
+            assert torch.equal(x[b:b + 1], y)
+    assert os.environ.get("OFD_SPLAT_CHUNK_FRAMES") is None
+
+
 def test_augment_flow_geometric_branch_runs_and_is_consistent(pkg):
     img, depth = _cfg1_inputs(pkg, 1, 96, 128)
     res = pkg.synthesis.synthesize_pairs(img, depth, torch.tensor([47.0], device=DEV))

@@ -85,3 +85,32 @@ def test_product_never_imports_the_oracle():
         for f in (ROOT / base).rglob("*"):
             if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
                 assert not pat.search(f.read_text()), f"{f} references the oracle"
+
+
+def test_dropin_modules_expose_the_reference_names(monkeypatch):
+    """dropin/ provides the module names the reference imports (preprocess.py:14-17, alt_cuda/fw.py:7)."""
+    import importlib
+    import sys
+
+    monkeypatch.syspath_prepend(str(ROOT / "dropin"))
+    for name in ("fw_cuda", "alt_cuda", "alt_cuda.fw", "geometry", "bilateral_filter"):
+        sys.modules.pop(name, None)
+    fw_cuda = importlib.import_module("fw_cuda")
+    fw = importlib.import_module("alt_cuda.fw")
+    geo = importlib.import_module("geometry")
+    bil = importlib.import_module("bilateral_filter")
+    assert callable(fw_cuda.forward_warping)
+    m = fw.FW("cuda:0")
+    assert hasattr(m, "forward") and hasattr(m, "set_shape") and m.device == "cuda:0"
+    assert geo.__all__ == ["BackprojectDepth", "Project3D", "transformation_from_parameters"]
+    assert all(hasattr(geo, n) for n in geo.__all__)
+    assert bil.__all__ == ["sparse_bilateral_filtering"]
+    import inspect
+
+    sig = inspect.signature(bil.sparse_bilateral_filtering)
+    assert list(sig.parameters)[:12] == ["depth", "image", "filter_size", "sigma_r", "sigma_s", "depth_threshold", "HR",
+                                         "mask", "gsHR", "edge_id", "num_iter", "num_gs_iter"]
+    with pytest.raises(RuntimeError, match="obj must be a CUDA tensor"):
+        fw_cuda.forward_warping(torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2))
+    for name in ("fw_cuda", "alt_cuda", "alt_cuda.fw", "geometry", "bilateral_filter"):
+        sys.modules.pop(name, None)
