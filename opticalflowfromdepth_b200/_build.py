@@ -42,6 +42,18 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Tuning helper: build csrc/ with extra -D flags into build/variants/<name>.so (load it with OFD_LIB_PATH)."""
+    vdir = PKG / "build" / "variants"
+    vdir.mkdir(parents=True, exist_ok=True)
+    out = vdir / f"{name}.so"
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", str(out), *[str(CSRC / s) for s in SOURCES], "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu of csrc/ into libofd_b200.so (skipped when sources are unchanged)."""
     digest = _digest()

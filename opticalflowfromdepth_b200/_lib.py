@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libofd_b200.so"
+# OFD_LIB_PATH selects another build of the same ABI (kernel tuning variants); the default is the in-tree library
+LIB_PATH = Path(os.environ["OFD_LIB_PATH"]) if os.environ.get("OFD_LIB_PATH") else PKG / "libofd_b200.so"
 
 F32, F64 = 0, 1
 EPI_NONE, EPI_CONCAT, EPI_BACK = 0, 1, 2

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) pair_row_kernel(const float* __restrict__
                                                       float* __restrict__ flow, float* __restrict__ valid,
                                                       float* __restrict__ collision, uint64_t* __restrict__ counters,
                                                       int H, int W) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int j = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t hw = (size_t)H * W;

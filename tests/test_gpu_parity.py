@@ -456,6 +456,47 @@ def test_chunked_batches_match_single_frames(pkg, monkeypatch):
     assert os.environ.get("OFD_SPLAT_CHUNK_FRAMES") is None
 
 
+@pytest.mark.parametrize("lag", ["1", "2", "3"])
+def test_single_launch_pipeline_matches_two_launch_path(pkg, monkeypatch, lag):
+    """The persistent z-test/gather pipeline (ordered tiles, key ring in L2) == the two-launch path, bit for bit,
+    for every producer/epilogue it serves, and leaves the workspace armed."""
+    n, h, w = 9, 75, 132
+    img, depth = _cfg1_inputs(pkg, n, h, w)
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    cams = []
+    for k in range(n):
+        torch.manual_seed(70 + k)
+        cams.append(pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]))
+    cam = torch.cat(cams).to(DEV)
+    vin = (torch.rand(n, 1, h, w, device=DEV) > 0.1).float()
+    flow = pkg.ops.reproject_flow(depth, cam)
+    obj = torch.cat((img, depth, flow * -1.0), 1).contiguous()
+
+    def run_all():
+        cnt = pkg.ops.new_counters(DEV)
+        res = [pkg.ops.splat_flow(obj, flow, depth, want_winner=True, counters=cnt),
+               pkg.ops.splat_flow(flow, flow, depth, epilogue=pkg.ops.EPI_BACK),
+               pkg.ops.splat_flow(flow, flow * 0.5, depth, epilogue=pkg.ops.EPI_CONCAT, aux=flow),
+               pkg.ops.frame_splat(img, depth, flow, vin, want_raw_valid=True),
+               pkg.ops.frame_splat(img, depth, flow, None),
+               pkg.ops.reproject_pair(img, depth, cam, vin, want_raw_valid=True)]
+        return res, cnt.cpu()
+
+    monkeypatch.setenv("OFD_SPLAT_PIPELINE", "0")
+    want, cnt0 = run_all()
+    monkeypatch.setenv("OFD_SPLAT_PIPELINE", "1")
+    monkeypatch.setenv("OFD_SPLAT_PIPE_D", lag)
+    for _ in range(2):  # twice: the control words must have been re-armed
+        got, cnt1 = run_all()
+        for a, b in zip(want, got):
+            for x, y in zip(a, b):
+                assert (x is None and y is None) or torch.equal(x, y)
+        assert torch.equal(cnt0, cnt1)
+    ws = pkg.ops.workspace.get(torch.device(DEV), n, h, w)
+    torch.cuda.synchronize()
+    assert bool((ws.view(torch.int64) == -1).all()), "workspace not re-armed by the pipeline"
+
+
 def test_augment_flow_geometric_branch_runs_and_is_consistent(pkg):
     img, depth = _cfg1_inputs(pkg, 1, 96, 128)
     res = pkg.synthesis.synthesize_pairs(img, depth, torch.tensor([47.0], device=DEV))

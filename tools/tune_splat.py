@@ -39,14 +39,16 @@ def case(H, W, B, pool=4):
     vin = torch.ones(B, 1, H, W, device=dev)
     flow = ops.reproject_flow(depth, cam)
     px = B * H * W
-    for chunk in (1, 2, 4, 8, 13, 16, 32, 64, 128):
-        if chunk > B and chunk != 1:
-            continue
-        os.environ["OFD_SPLAT_CHUNK_FRAMES"] = str(chunk)
+    for mode in ("two-launch", "pipe D=auto", "pipe D=1", "pipe D=2", "pipe D=3", "pipe D=8"):
+        chunk = mode
+        os.environ["OFD_SPLAT_PIPELINE"] = "0" if mode == "two-launch" else "1"
+        os.environ.pop("OFD_SPLAT_PIPE_D", None)
+        if "D=" in mode and "auto" not in mode:
+            os.environ["OFD_SPLAT_PIPE_D"] = mode.split("=")[1]
         t_plane = timeit(lambda: ops.frame_splat(img, depth, flow, vin))
         t_fused = timeit(lambda: ops.reproject_pair(img, depth, cam, vin))
         t_c2 = timeit(lambda: ops.splat_flow(flow, flow, depth, epilogue=ops.EPI_BACK))
-        print(f"{H}x{W} B={B} chunk={chunk:3d}: frame_splat(flow plane, 72 B/px) {t_plane*1e6:8.1f} us {72*px/t_plane/1e9:6.0f} GB/s | "
+        print(f"{H}x{W} B={B} {chunk:12s}: frame_splat(flow plane, 72 B/px) {t_plane*1e6:8.1f} us {72*px/t_plane/1e9:6.0f} GB/s | "
               f"reproject_pair (64 B/px) {t_fused*1e6:8.1f} us {64*px/t_fused/1e9:6.0f} GB/s {B/t_fused:9.0f} fr/s | "
               f"backflow C=2 (36 B/px) {t_c2*1e6:8.1f} us {36*px/t_c2/1e9:6.0f} GB/s", flush=True)
 
