@@ -54,6 +54,9 @@ class ClockSampler:
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thr = None
+        if index < 0:
+            self.nv = None
+            return
         try:
             import pynvml
 
@@ -220,7 +223,7 @@ def run_ours(args):
         ops.disparity_pair(img, depth, sBf, out=outs)
 
     # ---- headline: K steps, device timed, max over ranks ---------------------------------------------------------------
-    with ClockSampler(local) as clk:
+    with ClockSampler(-1 if args.no_clock_sampler else local) as clk:
         elapsed = timed(step, K, Wm, sync, barrier)
     t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
     if world > 1:
@@ -245,7 +248,7 @@ def run_ours(args):
                    "frames_per_step_per_gpu": F, "H": H, "W": W, "parallelism": f"frames sharded by image index over {world} GPU(s), no collective on the hot path",
                    "l2": f"inputs {F * 4 * H * W * 4 / 1e6:.0f} MB + outputs {F * 10 * H * W * 4 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)"},
         "gpu_launches": K,
-        "roofline": {"bound": "hbm", "kernel": "pair_row_kernel<float,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pair_rows_persistent<float,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_px": PAIR_BYTES_PER_PX, "bytes_per_launch": PAIR_BYTES_PER_PX * H * W * F},
         "counters": totals,
@@ -301,6 +304,26 @@ def run_ours(args):
                 del big_img, big_depth, vin
             except Exception as e:  # secondary: never break the headline
                 extras["sixdof_1080p"] = {"error": repr(e)}
+        if "group" not in skip:
+            # (b2) the reference's whole 5-pair group per frame (preprocess.py:356-432 minus inpaint): 7 splats with
+            #      fused producers/epilogues = 13 launches per batch
+            try:
+                Fq = min(F, 32)
+                Kq, invKq = synthesis.Plausible.K((H, W))
+                camsq = []
+                for k in range(Fq):
+                    torch.manual_seed(12345 + k)
+                    camsq.append(geometry.camera_constants(Kq, invKq, synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]))
+                camq = torch.cat(camsq).to(dev)
+
+                def qstep():
+                    synthesis.synthesize_group(img[:Fq], depth[:Fq], sBf[:Fq], camq)
+
+                tq = timed(qstep, 10, 3, sync, barrier) / 10
+                extras["group_480x640"] = {"frames_per_s": Fq / tq, "pairs_per_s": 5 * Fq / tq, "ms_per_step": 1e3 * tq, "frames_per_step": Fq,
+                                           "launches_per_step": 13, "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats)"}
+            except Exception as e:
+                extras["group_480x640"] = {"error": repr(e)}
         if "ref" not in skip:
             # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
             try:
@@ -395,7 +418,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,ref,e2e (profiling runs)")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll NVML during the timed region (diagnostics)")
+    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,group,ref,e2e (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,6 +12,9 @@
 // with no global atomics and no key workspace.  The input row (depth + 3 colour planes) is brought in by the
 // TMA engine as 1-D bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers, so the colour planes land
 // while the z-test runs.  HBM traffic is the algorithmic minimum: 16 B/px in, 40 B/px out.
+#include <cstdio>
+#include <cstdlib>
+
 #include "ofd_common.cuh"
 
 namespace ofd {
@@ -207,13 +210,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// shared-memory plan of the persistent kernel, in floats after a 64-byte header (4 mbarriers)
+#ifndef OFD_PAIR_NITER
+#define OFD_PAIR_NITER 2
+#endif
+constexpr int kMaxInStages = 6;  // input ring depth is a launch parameter: rows are prefetched in_stages-1 ahead
+
+// shared-memory plan of the persistent kernel, in floats after a 64-byte header (mbarriers)
 template <typename DT>
 struct PairPlan {
     static constexpr int kIn = (int)(sizeof(DT) / 4) + 3;  // raw depth row (DT) + 3 colour rows, per input stage
     static constexpr int kOut = 8;                          // img1 x3, depth1, back_flow.x, flow.x, valid, collision
     static constexpr int kMisc = 4 + (sizeof(DT) == 8 ? 1 : 0);  // zero row, -0 row, ord, idx (+ float depth row)
-    static __host__ __device__ size_t bytes(int W) { return 64 + (size_t)W * 4 * (2 * kIn + 2 * kOut + kMisc); }
+    static __host__ __device__ size_t bytes(int W, int in_stages, int out_stages) {
+        return 128 + (size_t)W * 4 * (in_stages * kIn + out_stages * kOut + kMisc);
+    }
 };
 
 template <typename DT, int NITER>
@@ -222,17 +232,22 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                                                            float* __restrict__ depth1, float* __restrict__ back_flow,
                                                            float* __restrict__ flow, float* __restrict__ valid,
                                                            float* __restrict__ collision, uint64_t* __restrict__ counters,
-                                                           int B, int H, int W) {
+                                                           int B, int H, int W, int in_stages_rt, int out_stages_rt) {
+#ifdef OFD_PAIR_IN_STAGES
+    constexpr int kInStages = OFD_PAIR_IN_STAGES, kOutStages = OFD_PAIR_OUT_STAGES;  // tuning builds: compile-time rings
+#else
+    const int kInStages = in_stages_rt, kOutStages = out_stages_rt;
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t hw = (size_t)H * W;
     const int total_rows = B * H;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stage][0 depth, 1 colour]
-    float* base = reinterpret_cast<float*>(smem_raw + 64);
+    float* base = reinterpret_cast<float*>(smem_raw + 128);
     typedef PairPlan<DT> Plan;
     auto in_stage = [&](int s) { return base + (size_t)s * Plan::kIn * W; };
-    auto out_stage = [&](int s) { return base + (size_t)(2 * Plan::kIn + s * Plan::kOut) * W; };
-    float* misc = base + (size_t)(2 * Plan::kIn + 2 * Plan::kOut) * W;
+    auto out_stage = [&](int s) { return base + (size_t)(kInStages * Plan::kIn + s * Plan::kOut) * W; };
+    float* misc = base + (size_t)(kInStages * Plan::kIn + kOutStages * Plan::kOut) * W;
     float* zero_row = misc;
     float* negzero_row = misc + W;
     uint32_t* sord = reinterpret_cast<uint32_t*>(misc + 2 * (size_t)W);
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     float* sdepth32 = misc + 4 * (size_t)W;  // only when DT is double
 
     if (tid == 0) {
-        for (int k = 0; k < 4; ++k) mbar_init(&bars[k], 1);
+        for (int k = 0; k < 2 * kInStages; ++k) mbar_init(&bars[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < W; i += nt) {
@@ -250,7 +265,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     fence_async_smem();
     __syncthreads();
 
-    auto issue_loads = [&](int row, int s) {  // thread 0 only
+    auto issue_loads = [&](int row, int s) {  // one thread (the loader)
         const int b = row / H, j = row - b * H;
         DT* sraw = reinterpret_cast<DT*>(in_stage(s));
         float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
@@ -262,27 +277,41 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     };
 
     int row = blockIdx.x;
-    if (tid == 0 && row < total_rows) issue_loads(row, 0);
+    const int loader = nt > 32 ? 32 : 0;  // loads are issued by warp 1 so they do not queue behind warp 0's store bookkeeping
+    if (tid == loader)
+        for (int k = 0; k < kInStages - 1; ++k)
+            if (row + k * (int)gridDim.x < total_rows) issue_loads(row + k * (int)gridDim.x, k);
     unsigned n_hit = 0, n_col = 0, n_px = 0, n_drop = 0;
 
-    for (int n = 0; row < total_rows; ++n, row += gridDim.x) {
-        const int s = n & 1;
-        const unsigned ph = (unsigned)(n >> 1) & 1u;
+    // ring cursors advance incrementally (no runtime division in the per-row critical path)
+    int s = 0, so = 0, s_fill = kInStages - 1;
+    unsigned ph = 0;
+    for (; row < total_rows; row += gridDim.x, s = (s + 1 == kInStages ? 0 : s + 1), so = (so + 1 == kOutStages ? 0 : so + 1),
+                             s_fill = (s_fill + 1 == kInStages ? 0 : s_fill + 1), ph ^= (s == 0 ? 1u : 0u)) {
         const int b = row / H, j = row - b * H;
         const DT* sraw = reinterpret_cast<const DT*>(in_stage(s));
         const float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
         const float* sdep = sizeof(DT) == 4 ? reinterpret_cast<const float*>(sraw) : sdepth32;
-        float* o_img = out_stage(s);
+        float* o_img = out_stage(so);
         float* o_dep = o_img + 3 * (size_t)W;
         float* o_bfx = o_dep + W;
         float* o_flx = o_bfx + W;
         float* o_val = o_flx + W;
         float* o_col = o_val + W;
 
+        if (tid == loader) {
+            // the stage being refilled was released by the barrier that ended row n-1
+            const int next = row + (kInStages - 1) * (int)gridDim.x;
+            if (next < total_rows) issue_loads(next, s_fill);
+        }
         if (tid == 0) {
-            const int next = row + gridDim.x;
-            if (next < total_rows) issue_loads(next, s ^ 1);  // stage s^1 was released by the barrier ending row n-1
-            bulk_wait_read<1>();                              // the stores of row n-2 have finished reading out_stage(s)
+            // the stores that last used out_stage(so) have finished reading it
+            if (kOutStages >= 3)
+                bulk_wait_read<2>();
+            else if (kOutStages == 2)
+                bulk_wait_read<1>();
+            else
+                bulk_wait_read<0>();
         }
 #pragma unroll
         for (int k = 0; k < NITER; ++k) {
@@ -390,14 +419,31 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
                                   float* img1, float* depth1, float* back_flow, float* flow, float* valid, float* collision,
                                   uint64_t* counters, cudaStream_t st, bool* handled) {
     *handled = false;
-    const size_t smem = PairPlan<DT>::bytes(W);
-    if (smem > 227 * 1024 || (long long)B * H > 0x7FFFFFFFll) return OFD_OK;  // fall back to the one-row kernel
+    if ((long long)B * H > 0x7FFFFFFFll) return OFD_OK;
+    // ring depths, tuned on B200 (profiles/r1/tune_pair.txt): the deepest plan that still lets two CTAs share an SM
+#ifdef OFD_PAIR_IN_STAGES
+    static const int plans[][2] = {{OFD_PAIR_IN_STAGES, OFD_PAIR_OUT_STAGES}};
+#else
+    static const int plans[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}, {2, 1}};
+#endif
+    int in_stages = 0, out_stages = 0;
+    size_t smem = 0;
+    for (int pass = 0; pass < 2 && !in_stages; ++pass)
+        for (const auto& pl : plans) {
+            const size_t need = PairPlan<DT>::bytes(W, pl[0], pl[1]);
+            if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
+                in_stages = pl[0], out_stages = pl[1], smem = need;
+                break;
+            }
+        }
+    if (!in_stages) return OFD_OK;  // row too wide for shared memory: fall back to the one-row kernel
     // each thread owns NITER pixels of a row; threads = ceil(W / NITER) rounded up to a warp
-    int niter = 4;
+    int niter = OFD_PAIR_NITER;
     while ((W + niter - 1) / niter > 1024) niter *= 2;
-    if (niter > 16) return OFD_OK;
+    if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
     int threads = ((W + niter - 1) / niter + 31) / 32 * 32;
-    auto kern = niter == 4 ? pair_rows_persistent<DT, 4> : (niter == 8 ? pair_rows_persistent<DT, 8> : pair_rows_persistent<DT, 16>);
+    auto kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER>
+                                        : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER> : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     int dev = 0, sms = 0, per_sm = 0;
@@ -407,7 +453,11 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
     if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
     long long grid = (long long)sms * per_sm;
     if (grid > (long long)B * H) grid = (long long)B * H;
-    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W);
+    if (std::getenv("OFD_DEBUG"))
+        fprintf(stderr, "[ofd] %s: persistent pair kernel: in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM x %d SMs -> grid %lld\n",
+                fn, in_stages, out_stages, niter, threads, smem, per_sm, sms, grid);
+    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W,
+                                                in_stages, out_stages);
     *handled = true;
     return check_launch(fn);
 }
