@@ -56,7 +56,8 @@ typedef void* ofd_stream_t; /* cudaStream_t */
 #define OFD_CNT_HOLE 1      /* target pixels with valid == 0                                  */
 #define OFD_CNT_COLLISION 2 /* target pixels with collision == 1                              */
 #define OFD_CNT_DROPPED 3   /* sources dropped: NaN flow / out-of-range explicit target       */
-#define OFD_CNT_TIE_SRC 4   /* sources that tie the winning depth but lose on raster index    */
+#define OFD_CNT_TIE_SRC 4   /* sources that tie the winning depth but lose on raster index (deterministic in the
+                               reference's serial loop and here; counted for information by a census pass) */
 #define OFD_CNT_FRAMES 5
 #define OFD_CNT_PAIRS 6
 #define OFD_CNT_SLOTS 8
@@ -78,7 +79,8 @@ int ofd_workspace_reset(void* ws, size_t bytes, ofd_stream_t stream);
  *   Divergence (documented): a target outside [0,H)x[0,W) or NaN is undefined behaviour in the reference;
  *   here that source is dropped and counted in OFD_CNT_DROPPED.
  *   `winner` (optional, int32 [B,1,H,W]) receives the winning source raster id, -1 for holes, -2 for collisions.
- *   dtype: OFD_F32 only (OFD_F64 -> OFD_E_DTYPE; the Python shim handles double by the two-plane path).
+ *   dtype: OFD_F32, or OFD_F64 (all four tensors and the three outputs double, as AT_DISPATCH_FLOATING_TYPES at
+ *   fw_cuda_kernel.cu:70 allows; two key planes, so the workspace must hold 2 * ofd_workspace_bytes(B,H,W)).
  */
 int ofd_splat_targets(const void* obj, const void* safe_y, const void* safe_x, const void* depth, int dtype,
                       int B, int C, int H, int W, void* out, void* valid, void* collision, int32_t* winner,

@@ -184,10 +184,16 @@ __global__ void __launch_bounds__(256) pair_row_kernel(const float* __restrict__
         n_col += (hit && !win);
     }
     if (counters) {
+        unsigned n_tie = 0;
+        for (int i = tid; i < W; i += nt) {
+            const uint32_t tx = stgt[i], hi = depth_hi(sdepth[i]);
+            if (tx != T_DROPPED && hi < HI_NOWIN && sord[tx] == hi && sidx[tx] != (uint32_t)i) n_tie++;
+        }
         warp_count(counters, OFD_CNT_HIT, n_hit);
         warp_count(counters, OFD_CNT_HOLE, n_px - n_hit);
         warp_count(counters, OFD_CNT_COLLISION, n_col);
         warp_count(counters, OFD_CNT_DROPPED, dropped);
+        warp_count(counters, OFD_CNT_TIE_SRC, n_tie);
     }
 }
 
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     if (tid == loader)
         for (int k = 0; k < kInStages - 1; ++k)
             if (row + k * (int)gridDim.x < total_rows) issue_loads(row + k * (int)gridDim.x, k);
-    unsigned n_hit = 0, n_col = 0, n_px = 0, n_drop = 0;
+    unsigned n_hit = 0, n_col = 0, n_px = 0, n_drop = 0, n_tie = 0;
 
     // ring cursors advance incrementally (no runtime division in the per-row critical path)
     int s = 0, so = 0, s_fill = kInStages - 1;
@@ -384,6 +390,11 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                 n_col += (hit && !win);
             }
         }
+        if (counters) {  // tie census: sources that tie the winning depth of their target but lost on column order
+#pragma unroll
+            for (int k = 0; k < NITER; ++k)
+                if (tx[k] != T_DROPPED && hi[k] < HI_NOWIN && sord[tx[k]] == hi[k] && sidx[tx[k]] != (uint32_t)(tid + k * nt)) n_tie++;
+        }
         fence_async_smem();  // generic-proxy writes of the staging rows -> visible to the TMA engine
         __syncthreads();
         if (tid == 0) {
@@ -411,6 +422,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         warp_count(counters, OFD_CNT_HOLE, n_px - n_hit);
         warp_count(counters, OFD_CNT_COLLISION, n_col);
         warp_count(counters, OFD_CNT_DROPPED, n_drop);
+        warp_count(counters, OFD_CNT_TIE_SRC, n_tie);
     }
 }
 

@@ -1,7 +1,8 @@
 """Drop-in for the reference's torch extension module `fw_cuda` (alt_cuda/fw_cuda.cpp:15-30).
 
 `forward_warping(obj, safe_y, safe_x, depth) -> [output, valid, collision]` with the reference's input checks and
-error messages (fw_cuda.cpp:11-13,20-23); the work is done by ofd_splat_targets in libofd_b200.so.
+error messages (fw_cuda.cpp:11-13,20-23); float32 or float64 tensors, as AT_DISPATCH_FLOATING_TYPES allows
+(fw_cuda_kernel.cu:70).  The work is done by ofd_splat_targets in libofd_b200.so.
 """
 from __future__ import annotations
 
@@ -19,10 +20,6 @@ def forward_warping(obj, safe_y, safe_x, depth):
             raise RuntimeError(f"{name} must be a CUDA tensor")
         if not t.is_contiguous():
             raise RuntimeError(f"{name} must be contiguous")
-    if obj.dtype == torch.float64:
-        # AT_DISPATCH_FLOATING_TYPES also instantiates double (fw_cuda_kernel.cu:70); fw.py never uses it.
-        raise TypeError("fw_cuda.forward_warping: float64 tensors are not supported by the B200 path; "
-                        "cast to float32 as alt_cuda/fw.py does")
     with torch.cuda.device(obj.device):  # OptionalCUDAGuard(device_of(obj)), fw_cuda.cpp:24
         out, valid, collision = ops.splat_targets(obj, safe_y, safe_x, depth)
     return [out, valid, collision]

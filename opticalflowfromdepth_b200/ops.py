@@ -88,14 +88,15 @@ def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
     B, Cc, H, W = obj.shape
     for n, t in (("safe_y", safe_y), ("safe_x", safe_x), ("depth", depth)):
         _check(n, t, dtype=obj.dtype, shape=(B, 1, H, W))
-    if obj.dtype != torch.float32:
-        raise TypeError("the device path is float32; use fw_cuda.forward_warping for the float64 dispatch")
+    if obj.dtype not in _DT:
+        raise TypeError(f"obj must be float32 or float64, got {obj.dtype}")
+    planes = 2 if obj.dtype == torch.float64 else 1  # float64 keeps depth and source id in separate key planes
     out = torch.empty_like(obj)
     valid = torch.empty_like(depth)
     collision = torch.empty_like(depth)
     winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
-    ws = workspace.get(obj.device, B, H, W)
-    _run_splat("ofd_splat_targets", obj.device, _ptr(obj), _ptr(safe_y), _ptr(safe_x), _ptr(depth), F32, B, Cc, H, W,
+    ws = workspace.get(obj.device, planes * B, H, W)
+    _run_splat("ofd_splat_targets", obj.device, _ptr(obj), _ptr(safe_y), _ptr(safe_x), _ptr(depth), _DT[obj.dtype], B, Cc, H, W,
                _ptr(out), _ptr(valid), _ptr(collision), _ptr(winner), _ptr(counters), _ptr(ws),
                C.c_size_t(ws.numel()), _stream(obj.device))
     return (out, valid, collision, winner) if want_winner else (out, valid, collision)

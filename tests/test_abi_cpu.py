@@ -41,7 +41,8 @@ def test_version_and_workspace_bytes():
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 5, None, None, 1, 1 << 20, None), -4),   # epilogue
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 1, None, None, 1, 1 << 20, None), -1),   # concat w/o aux
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 0, None, None, 8, 16, None), -5),        # ws too small
-    ("ofd_splat_targets", (1, 1, 1, 1, 1, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 1 << 20, None), -3),      # float64
+    ("ofd_splat_targets", (1, 1, 1, 1, 5, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 1 << 20, None), -3),      # bad dtype
+    ("ofd_splat_targets", (1, 1, 1, 1, 1, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 200, None), -5),          # f64: 2 key planes
     ("ofd_splat_targets", (None, 1, 1, 1, 0, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 1 << 20, None), -1),   # NULL obj
     ("ofd_disparity_pair", (1, 1, 3, 1, 1, 4, 4, 1, 1, 1, 1, 1, 1, None, None), -3),
     ("ofd_bilateral_iter", (1, 1, 0, 8, 8, 4, 0.04, 1, None), -4),                                      # even window

@@ -43,6 +43,19 @@ def eq(t, a):
     return np.array_equal(t.cpu().numpy(), a, equal_nan=True)
 
 
+def expected_ties(flow, depth, winner):
+    """Sources that tie the winning depth of their target without being the winner (one frame, oracle side)."""
+    sx, sy = oracle.fw_targets(flow)
+    H, W = winner.shape
+    ok = (sx > -1) & (sx < W) & (sy > -1) & (sy < H)
+    t = (np.where(ok, sy, 0).astype(np.int64) * W + np.where(ok, sx, 0).astype(np.int64)).ravel()
+    d = depth.ravel().astype(np.float32)
+    w = winner.ravel()[t]
+    with np.errstate(invalid="ignore"):
+        tie = ok.ravel() & (w >= 0) & (d < 1000) & (d == d[np.maximum(w, 0)]) & (np.arange(t.size) != w)
+    return int(tie.sum())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # FW boundary: golden vectors from the reference's own fw.py + literal kernel loop
 # ---------------------------------------------------------------------------------------------------------------
@@ -76,6 +89,41 @@ def test_fw_cuda_forward_warping_contract(pkg, golden, tag):
             pkg.fw_cuda.forward_warping(obj, sy, sx_nc, depth)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_fw_cuda_float64_dispatch(pkg, seed):
+    """forward_warping on double tensors (fw_cuda_kernel.cu:70 dispatches double too): depth compared in float64."""
+    rng = np.random.default_rng(900 + seed)
+    B, C, H, W = 2, int(rng.integers(1, 8)), int(rng.integers(2, 60)), int(rng.integers(2, 80))
+    obj = rng.normal(0, 5, (B, C, H, W))
+    sx = rng.integers(0, W, (B, 1, H, W)).astype(np.float64) + rng.uniform(0, 0.9, (B, 1, H, W))
+    sy = rng.integers(0, H, (B, 1, H, W)).astype(np.float64) + rng.uniform(0, 0.9, (B, 1, H, W))
+    base = rng.integers(1, 4, (B, 1, H, W)).astype(np.float64)
+    depth = base + rng.choice([0.0, 1e-12, -1e-12], (B, 1, H, W))  # differences far below float32 resolution
+    depth[rng.random(depth.shape) < 0.03] = 1000.0
+    depth[rng.random(depth.shape) < 0.01] = np.nan
+    out, valid, coll = pkg.fw_cuda.forward_warping(cu(obj), cu(sy), cu(sx), cu(depth))
+    assert out.dtype == torch.float64 and valid.dtype == torch.float64
+    for b in range(B):  # serial loop of the reference in float64
+        dl = np.full(H * W, 1000.0)
+        o = np.zeros((C, H * W))
+        v = np.zeros(H * W)
+        c = np.zeros(H * W)
+        tt = (sy[b, 0].astype(np.int64) * W + sx[b, 0].astype(np.int64)).ravel()
+        dd = depth[b, 0].ravel()
+        src = obj[b].reshape(C, -1)
+        for p in range(H * W):
+            t = tt[p]
+            if dd[p] < dl[t]:
+                o[:, t] = src[:, p]
+                dl[t] = dd[p]
+            v[t] = 1
+            c[t] = 0.0 if dl[t] != 1000.0 else 1.0
+        assert np.array_equal(out[b].cpu().numpy().reshape(C, -1), o)
+        assert np.array_equal(valid[b, 0].cpu().numpy().ravel(), v) and np.array_equal(coll[b, 0].cpu().numpy().ravel(), c)
+    ws = pkg.ops.workspace.get(torch.device(DEV), 2 * B, H, W)
+    assert bool((ws.view(torch.int64)[: 2 * B * H * W] == -1).all())
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_splat_random_trials_vs_oracle(pkg, seed):
     rng = np.random.default_rng(100 + seed)
@@ -91,14 +139,16 @@ def test_splat_random_trials_vs_oracle(pkg, seed):
     flow[:, 0:1][nan_flow] = np.nan
     cnt = pkg.ops.new_counters(DEV)
     out, valid, coll, win = pkg.ops.splat_flow(cu(obj), cu(flow), cu(depth), want_winner=True, counters=cnt)
-    dropped = 0
+    dropped = ties = 0
     for b in range(B):
         o, v, c, w, d = oracle.fw_forward(obj[b], flow[b], depth[b])
         dropped += d
+        ties += expected_ties(flow[b], depth[b], w)
         assert eq(win[b, 0], w), f"winner map differs (seed {seed}, frame {b})"
         assert eq(valid[b], v) and eq(coll[b], c) and eq(out[b], o)
     cn = cnt.cpu().numpy()
     assert cn[3] == dropped == int(nan_flow.sum())
+    assert cn[4] == ties and ties > 0, "tie census differs from the oracle"
     assert cn[0] + cn[1] == B * H * W and cn[0] == int(valid.sum().item()) and cn[2] == int(coll.sum().item())
 
 
@@ -204,6 +254,12 @@ def test_disparity_pair_vs_oracle(pkg, h, w):
     assert np.all(np.signbit(got[3][:, 1].cpu().numpy()))  # flow.y == -0.0
     cn = cnt.cpu().numpy()
     assert cn[0] == int(want[4].sum()) and cn[0] + cn[1] == B * h * w and cn[2] == int(want[5].sum())
+    ties = 0
+    for b in range(B):
+        obj = np.concatenate([img[b], depth[b], want[3][b] * -1.0])
+        _, _, _, w_map, _ = oracle.fw_forward(obj, want[3][b], depth[b])
+        ties += expected_ties(want[3][b], depth[b], w_map)
+    assert cn[4] == ties, "tie census of the fused pair kernel differs from the oracle"
 
 
 def test_disparity_pair_float64_depth(pkg):
