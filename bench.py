@@ -277,11 +277,11 @@ def run_ours(args):
                                        "achieved_GBps": (PAIR_BYTES_PER_PX + 16) * H * W * Fg / per / 1e9,
                                        "note": "algorithmic bytes 72 B/px: the flow plane is written by one kernel and re-read by z-test and gather"}
         if "sixdof" not in skip:
-            # (b) cfg3-style: 6-DoF reprojection + C=7 splat + hole mask at 1080p
+            # (b) cfg3: random 6-DoF reprojection + C=7 z-buffered splat + hole mask, 1080p batch 32 (fused: 2 launches)
             try:
-                Hb, Wb, Fb = 1080, 1920, 8
-                big_img = torch.rand(Fb, 3, Hb, Wb, device=dev) * 255
+                Hb, Wb, Fb = 1080, 1920, 32
                 from opticalflowfromdepth_b200 import synthetic
+                big_img = torch.rand(Fb, 3, Hb, Wb, device=dev) * 255
                 raw = np.stack([synthetic.diml_frame(100 + k, Hb, Wb)[1] for k in range(2)])
                 big_depth = ops.normalize_depth(torch.from_numpy(raw).to(dev))[torch.arange(Fb, device=dev) % 2].contiguous()
                 Kc, invK = synthesis.Plausible.K((Hb, Wb))
@@ -294,16 +294,44 @@ def run_ours(args):
                 vin = torch.ones(Fb, 1, Hb, Wb, device=dev)
 
                 def bstep():
-                    fl = ops.reproject_flow(big_depth, cam)
-                    ops.frame_splat(big_img, big_depth, fl, vin)
+                    ops.reproject_pair(big_img, big_depth, cam, vin)
 
                 tb = timed(bstep, 10, 3, sync, barrier) / 10
-                extras["sixdof_1080p"] = {"frames_per_s": Fb / tb, "ms_per_step": 1e3 * tb, "frames_per_step": Fb, "launches_per_step": 3,
-                                          "achieved_GBps": (64 + 16) * Hb * Wb * Fb / tb / 1e9,
-                                          "note": "64 B/px fused-pair algorithmic bytes (SURVEY 8d) + 16 B/px for the materialised flow plane"}
+                extras["cfg3_sixdof_1080p_b32"] = {"frames_per_s": Fb / tb, "ms_per_step": 1e3 * tb, "frames_per_step": Fb, "launches_per_step": 2,
+                                                   "achieved_GBps": 64 * Hb * Wb * Fb / tb / 1e9, "frac_of_measured_peak": 64 * Hb * Wb * Fb / tb / 1e9 / peak,
+                                                   "note": "64 B/px algorithmic (SURVEY 8d fused 6-DoF pair with valid_in); the flow plane re-read (8) and key traffic (32) are overhead"}
                 del big_img, big_depth, vin
             except Exception as e:  # secondary: never break the headline
-                extras["sixdof_1080p"] = {"error": repr(e)}
+                extras["cfg3_sixdof_1080p_b32"] = {"error": repr(e)}
+        if "bilateral" not in skip:
+            # (b1) cfg2 stage: 5-iteration gated-median bilateral at 480x640 (reference numpy: 5.2 s/frame)
+            try:
+                from opticalflowfromdepth_b200 import bilateral_filter as bfm
+                d2 = depth[0, 0].contiguous()
+                tbil = timed(lambda: bfm.sparse_bilateral_filtering(d2, None, [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5), 10, 3, sync, barrier) / 10
+                extras["cfg2_bilateral_480x640_5iter"] = {"ms_per_frame": 1e3 * tbil, "frames_per_s": 1.0 / tbil, "launches": 5}
+            except Exception as e:
+                extras["cfg2_bilateral_480x640_5iter"] = {"error": repr(e)}
+        if "augment" not in skip:
+            # (b3) cfg4: in-loop geometric augmentation of one image of the pair at 368x496, batch 8 (6 splats per sample)
+            try:
+                from opticalflowfromdepth_b200 import synthetic
+                Ha, Wa, Fa = 368, 496, 8
+                fr = [synthetic.diml_frame(200 + k, Ha, Wa) for k in range(Fa)]
+                a_img = torch.from_numpy(np.stack([f[0] for f in fr])).to(dev)
+                a_dep = ops.normalize_depth(torch.from_numpy(np.stack([f[1] for f in fr])).to(dev))
+                pa = synthesis.synthesize_pairs(a_img, a_dep, torch.full((Fa,), 47.0, device=dev))
+
+                kinds = [5 + k % 3 for k in range(Fa)]
+
+                def astep():
+                    synthesis.augment_flow_batch(a_img, a_dep, pa["img1"], pa["depth1"], pa["flow"], pa["back_flow"], kinds)
+
+                ta = timed(astep, 10, 3, sync, barrier) / 10
+                extras["cfg4_augment_368x496_b8"] = {"pairs_per_s": Fa / ta, "ms_per_step": 1e3 * ta, "pairs_per_step": Fa,
+                                                     "what": "augment_flow_batch: geometric branch (flip/rotate/shear per sample), 6 batched splats + 8 special-flow launches"}
+            except Exception as e:
+                extras["cfg4_augment_368x496_b8"] = {"error": repr(e)}
         if "group" not in skip:
             # (b2) the reference's whole 5-pair group per frame (preprocess.py:356-432 minus inpaint): 7 splats with
             #      fused producers/epilogues = 13 launches per batch
@@ -419,7 +447,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll NVML during the timed region (diagnostics)")
-    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,group,ref,e2e (profiling runs)")
+    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,bilateral,augment,group,ref,e2e (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

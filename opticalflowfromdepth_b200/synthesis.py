@@ -18,8 +18,8 @@ from torch import nn
 from . import geometry, ops
 from .fw import FW
 
-__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "normalize_depth",
-           "fix_warped_depth", "get_random", "set_seed", "synthesize_pairs", "synthesize_group"]
+__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch",
+           "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "synthesize_pairs", "synthesize_group"]
 
 
 # ---- utils.py helpers ------------------------------------------------------------------------------------------
@@ -249,6 +249,43 @@ def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device
     return ((aug_img0, aug_img0_depth, aug0_flow, back_aug0_flow, img1, img1_depth),
             (img0, img0_depth, aug1_flow, back_aug1_flow, aug_img1, aug_img1_depth),
             int(augment_flow_type), (special_flow, back_special_flow))
+
+
+@torch.no_grad()
+def augment_flow_batch(img0, depth0, img1, depth1, flow01, back_flow01, kinds, inpaint=None):
+    """Batched in-loop geometric augmentation (BASELINE config 4): the geometric branch of augment_flow
+    (preprocess.py:116-147) for B pairs at once, one special flow per sample (kinds[b] in {5 flip, 6 rotate, 7 shear}).
+
+    All tensors are [B,C,H,W] float32 CUDA.  The six splats of the branch run as six batched z-test/gather launch pairs
+    instead of 6*B; random parameters are drawn per sample in batch order with the reference's draw order.
+    Returns (set1, set2, (special_flow, back_special_flow)) with the same members as augment_flow, batched."""
+    B, _, h, w = img0.shape
+    dev = img0.device
+    sf = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
+    bsf = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
+    gen = SpecialFlow(dev)
+    for b in range(B):
+        gen.horizontal_flip = gen.horizontal_shear = True  # a fresh instance per call in the reference (preprocess.py:115)
+        f, bf_ = gen((h, w), float(kinds[b]))
+        sf[b], bsf[b] = f, bf_
+    with torch.cuda.device(dev):
+        aug0_flow, _, _ = ops.splat_flow(flow01, sf, depth0, epilogue=ops.EPI_CONCAT, aux=bsf)
+        aug1_flow, _, _ = ops.splat_flow(sf, back_flow01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01)
+
+        def warp(img, depth):
+            allc, valid, collision = ops.splat_flow(torch.cat((img, depth), 1), sf, depth)
+            a_img = allc[:, 0:3].contiguous()
+            a_depth = ops.fix_warped_depth_(allc[:, 3:4].contiguous())
+            if inpaint is not None:
+                a_img = inpaint(a_img, valid, collision)
+            return a_img, a_depth
+
+        aug_img0, aug_depth0 = warp(img0, depth0)
+        aug_img1, aug_depth1 = warp(img1, depth1)
+        back_aug0, _, _ = ops.splat_flow(aug0_flow, aug0_flow, aug_depth0, epilogue=ops.EPI_BACK)
+        back_aug1, _, _ = ops.splat_flow(aug1_flow, aug1_flow, depth0, epilogue=ops.EPI_BACK)
+    return ((aug_img0, aug_depth0, aug0_flow, back_aug0, img1, depth1),
+            (img0, depth0, aug1_flow, back_aug1, aug_img1, aug_depth1), (sf, bsf))
 
 
 # ---- batched frame-level entry points ----------------------------------------------------------------------------

@@ -567,3 +567,80 @@ def test_augment_flow_geometric_branch_runs_and_is_consistent(pkg):
         o, v, c, _, _ = oracle.fw_forward(res["flow"][0].cpu().numpy(), sf.cpu().numpy(), depth[0].cpu().numpy())
         want = (o + bsf.cpu().numpy()) * v
         assert eq(s1[2], want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 2 and 4 as parity cases
+# ---------------------------------------------------------------------------------------------------------------
+def test_cfg2_redweb_ragged_batch_bilateral_then_pair(pkg):
+    """cfg2: mixed-resolution ReDWeb-shaped frames: smooth_closer -> normalize_depth -> 5-iteration gated-median
+    bilateral -> virtual-disparity pair, every stage against the oracle (bit-exact)."""
+    sizes = [(150, 212), (98, 170), (201, 133)]  # ragged: every frame its own H x W (incl. widths not divisible by 4)
+    fs = [7, 7, 5, 5, 5]
+    for k, (h, w) in enumerate(sizes):
+        img, depth = pkg.synthetic.redweb_frame(k, h, w)
+        d_ref = oflow.normalize_depth(torch.from_numpy(depth.copy())).numpy()
+        d_gpu = pkg.ops.normalize_depth(cu(depth)[None])
+        assert eq(d_gpu[0], d_ref)
+        f_ref = obil.sparse_bilateral_filtering(d_ref[0].copy(), fs, 0.04, 5)
+        f_gpu = pkg.bilateral_filter.sparse_bilateral_filtering(d_gpu[0, 0], None, fs, depth_threshold=0.04, num_iter=5)
+        assert eq(f_gpu, f_ref) and (f_ref != d_ref[0]).any()
+        sBf = np.array([46.5 + k], np.float32)
+        got = pkg.ops.disparity_pair(cu(img)[None], f_gpu[None, None].contiguous(), cu(sBf))
+        want = oracle.disparity_pair(img[None], f_ref[None, None], sBf)
+        for g, wnt in zip(got, want):
+            assert eq(g, wnt)
+
+
+@pytest.mark.parametrize("kind", [5, 6, 7])
+def test_cfg4_inloop_geometric_augmentation_368x496(pkg, kind):
+    """cfg4: the 6-splat geometric branch of augment_flow (preprocess.py:116-147 minus inpaint) at RAFT's crop size;
+    every splat result against the oracle fed with the same special flow."""
+    h, w = 368, 496
+    img, depth = _cfg1_inputs(pkg, 1, h, w, seed0=40 + kind)
+    p01 = pkg.synthesis.synthesize_pairs(img, depth, torch.tensor([48.0], device=DEV))
+    img0, d0, img1, d1 = img[0], depth[0], p01["img1"][0], p01["depth1"][0]
+    f01, b01 = p01["flow"][0], p01["back_flow"][0]
+    pkg.synthesis.set_seed(300 + kind)
+    s1, s2, t, (sf, bsf) = pkg.synthesis.augment_flow(img0, d0, img1, d1, f01, b01, device=DEV, augment_flow_type=float(kind))
+    n = lambda x: x.cpu().numpy()  # noqa: E731
+
+    def fw(obj, flow, dep):
+        o, v, c, _, _ = oracle.fw_forward(n(obj), n(flow), n(dep))
+        return o, v
+
+    # ConcatFlow(back_special, special, flow01, depth0) and ConcatFlow(flow01, back_flow01, special, depth1)
+    o, v = fw(f01, sf, d0)
+    a0_flow = (o + n(bsf)) * v
+    o, v = fw(sf, b01, d1)
+    a1_flow = (o + n(f01)) * v
+    assert eq(s1[2], a0_flow) and eq(s2[2], a1_flow)
+    # warped image + depth of both views
+    for (im, dp, got_img, got_dep) in ((img0, d0, s1[0], s1[1]), (img1, d1, s2[4], s2[5])):
+        o, v = fw(torch.cat((im, dp)), sf, dp)
+        assert eq(got_img, o[0:3])
+        assert eq(got_dep, oflow.fix_warped_depth(torch.from_numpy(o[3:4])).numpy())
+    # BackFlow(aug0_flow, aug_depth0) and BackFlow(aug1_flow, depth0)
+    o, v = fw(s1[2], s1[2], s1[1])
+    assert eq(s1[3], (o * -1.0) * v)
+    o, v = fw(s2[2], s2[2], d0)
+    assert eq(s2[3], (o * -1.0) * v)
+    assert t == kind
+
+
+def test_cfg4_batched_augmentation_equals_per_sample(pkg):
+    """augment_flow_batch (6 batched splats) == augment_flow per sample with the same random draws."""
+    h, w, B = 368, 496, 4
+    img, depth = _cfg1_inputs(pkg, B, h, w, seed0=60)
+    p01 = pkg.synthesis.synthesize_pairs(img, depth, torch.full((B,), 47.5, device=DEV))
+    kinds = [5, 6, 7, 6]
+    pkg.synthesis.set_seed(77)
+    s1, s2, (sf, bsf) = pkg.synthesis.augment_flow_batch(img, depth, p01["img1"], p01["depth1"], p01["flow"], p01["back_flow"], kinds)
+    pkg.synthesis.set_seed(77)
+    for b in range(B):
+        r1, r2, t, (f, bf_) = pkg.synthesis.augment_flow(img[b], depth[b], p01["img1"][b], p01["depth1"][b], p01["flow"][b],
+                                                        p01["back_flow"][b], device=DEV, augment_flow_type=float(kinds[b]))
+        assert torch.equal(sf[b], f) and torch.equal(bsf[b], bf_)
+        for k in range(6):
+            assert torch.equal(s1[k][b], r1[k]), (b, "set1", k)
+            assert torch.equal(s2[k][b], r2[k]), (b, "set2", k)
