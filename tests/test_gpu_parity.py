@@ -644,3 +644,48 @@ def test_cfg4_batched_augmentation_equals_per_sample(pkg):
         for k in range(6):
             assert torch.equal(s1[k][b], r1[k]), (b, "set1", k)
             assert torch.equal(s2[k][b], r2[k]), (b, "set2", k)
+
+
+def test_no_out_of_bounds_writes_guard_bands(pkg):
+    """compute-sanitizer is closed on this GPU pool, so the kernels are checked with guard bands instead: every
+    output lives inside a larger poisoned buffer and the bytes around it must be untouched (odd sizes, all paths)."""
+    from opticalflowfromdepth_b200 import _lib
+    import ctypes as C
+
+    def guarded(shape, dtype=torch.float32, pad=4096):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * pad,), 12345.0 if dtype == torch.float32 else 77, dtype=dtype, device=DEV)
+        return buf, buf[pad:pad + n].view(shape)
+
+    def check(buf, n, pad=4096):
+        assert bool((buf[:pad] == 12345.0).all()) and bool((buf[pad + n:] == 12345.0).all()), "guard band overwritten"
+
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, H, W) in ((2, 33, 52), (1, 19, 37), (3, 8, 640)):
+        img, depth = _cfg1_inputs(pkg, B, max(H, 16), max(W, 16))
+        img, depth = img[:, :, :H, :W].contiguous(), depth[:, :, :H, :W].contiguous()
+        sBf = torch.full((B,), 49.0, device=DEV)
+        outs = [guarded((B, c, H, W)) for c in (3, 1, 2, 2, 1, 1)]
+        _lib.call("ofd_disparity_pair", p(img), p(depth), 0, p(sBf), B, H, W, *[p(v) for _, v in outs], None, st)
+        torch.cuda.synchronize()
+        for (buf, v), c in zip(outs, (3, 1, 2, 2, 1, 1)):
+            check(buf, B * c * H * W)
+        ref = pkg.ops.disparity_pair(img, depth, sBf)
+        for (_, v), r in zip(outs, ref):
+            assert torch.equal(v, r)
+        # general splat, C = 7 frame epilogue with in-kernel flow
+        K, invK = pkg.synthesis.Plausible.K((H, W))
+        torch.manual_seed(B)
+        cam = pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]).repeat(B, 1).to(DEV)
+        vin = torch.ones(B, 1, H, W, device=DEV)
+        gouts = [guarded((B, c, H, W)) for c in (3, 1, 2, 2, 1, 1, 1)]
+        ws_buf, ws = guarded((pkg.ops.workspace.get(torch.device(DEV), B, H, W).numel(),), dtype=torch.uint8)
+        ws.fill_(255)
+        _lib.call("ofd_reproject_pair", p(img), p(depth), p(cam), C.c_float(1e-7), p(vin), B, H, W, *[p(v) for _, v in gouts], None,
+                  p(ws), C.c_size_t(ws.numel()), st)
+        torch.cuda.synchronize()
+        for (buf, v), c in zip(gouts, (3, 1, 2, 2, 1, 1, 1)):
+            check(buf, B * c * H * W)
+        assert bool((ws_buf[:4096] == 77).all()) and bool((ws_buf[4096 + ws.numel():] == 77).all())
+        assert bool((ws == 255).all()), "workspace not re-armed"
