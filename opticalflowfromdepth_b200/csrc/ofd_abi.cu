@@ -23,13 +23,6 @@ int check_launch(const char* what) {
     return OFD_OK;
 }
 
-__global__ void fill_keys_kernel(ulonglong2* __restrict__ p, size_t n2) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    const ulonglong2 v = make_ulonglong2(KEY_UNTOUCHED, KEY_UNTOUCHED);
-    for (; i < n2; i += stride) p[i] = v;
-}
-
 }  // namespace ofd
 
 extern "C" {
