@@ -689,3 +689,62 @@ def test_no_out_of_bounds_writes_guard_bands(pkg):
             check(buf, B * c * H * W)
         assert bool((ws_buf[:4096] == 77).all()) and bool((ws_buf[4096 + ws.numel():] == 77).all())
         assert bool((ws == 255).all()), "workspace not re-armed"
+
+
+def test_extreme_contention_and_1080p_border_pileup(pkg):
+    """Every source on one target (307 200 atomics on one key) and a 1080p 6-DoF frame whose clamped corner collects
+    tens of thousands of sources: the warp run-aggregation + 64-bit atomicMin must still give the serial loop's winner."""
+    img, depth = _cfg1_inputs(pkg, 1)
+    flow = torch.full((1, 2, 480, 640), -1e6, device=DEV)
+    out, valid, coll, win = pkg.ops.splat_flow(img, flow, depth, want_winner=True)
+    d = depth[0, 0].cpu().numpy().ravel()
+    w_expect = int(np.flatnonzero(d == d.min())[0])
+    assert int(win[0, 0, 0, 0]) == w_expect and int(valid.sum()) == 1 and int((win >= 0).sum()) == 1
+    assert torch.equal(out[0, :, 0, 0], img[0].reshape(3, -1)[:, w_expect])
+    # 1080p 6-DoF frame against the oracle
+    big_img, big_depth = _cfg1_inputs(pkg, 1, 1080, 1920, seed0=100)
+    f6, _ = _six_dof_flow(pkg, big_depth, 5)
+    obj = torch.cat((big_img, big_depth, f6 * -1.0), 1).contiguous()
+    out, valid, coll, win = pkg.ops.splat_flow(obj, f6, big_depth, want_winner=True)
+    o, v, c, w, _ = oracle.fw_forward(obj[0].cpu().numpy(), f6[0].cpu().numpy(), big_depth[0].cpu().numpy())
+    assert eq(win[0, 0], w) and eq(valid[0], v) and eq(coll[0], c) and eq(out[0], o)
+    sx, sy = oracle.fw_targets(f6[0].cpu().numpy())
+    fan_in = np.bincount((sy.astype(np.int64) * 1920 + sx.astype(np.int64)).ravel()).max()
+    print(f"[1080p] max sources on one target: {fan_in}")
+    assert fan_in > 1000
+
+
+def test_cuda_graph_capture_and_replay(pkg):
+    """Every ABI call is a pure stream operation (no allocation, no synchronisation): a whole multi-kernel synthesis
+    step can be captured into a CUDA graph and replayed, with the key workspace armed across replays."""
+    B, h, w = 4, 96, 128
+    img, depth = _cfg1_inputs(pkg, B, h, w)
+    sBf = torch.full((B,), 46.0, device=DEV)
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    torch.manual_seed(9)
+    cam = pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]).repeat(B, 1).to(DEV)
+
+    def step():
+        img1, d1, back, flow, valid, coll = pkg.ops.disparity_pair(img, depth, sBf)
+        return pkg.ops.reproject_pair(img1, d1, cam, valid) + (img1, d1, back, flow)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eager = [t.clone() for t in step() if t is not None]  # also arms this stream's workspace
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            outs = step()
+        for _ in range(3):
+            img.add_(0)  # inputs are read at replay time
+            g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(eager, [t for t in outs if t is not None]):
+            assert torch.equal(a, b)
+        # new input values flow through the captured graph
+        img.mul_(0.5)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(outs[7], pkg.ops.disparity_pair(img, depth, sBf)[0])
+    torch.cuda.current_stream().wait_stream(s)
