@@ -426,6 +426,30 @@ def run_ours(args):
                        "frames_per_step": Fe, "steps": Ke,
                        "api": "ofd_pair_pipeline_run (C ABI, pinned host buffers in and out, 3-slot H2D/kernel/D2H pipeline)"}
 
+    if "e2e" not in skip and "compact" not in skip:
+        # same pipeline with the compact transport (uint8 colour + masks, constant planes not transferred): extra information,
+        # the judged `e2e` above stays on float32 host buffers
+        try:
+            c_img = torch.from_numpy(img_pool.astype(np.uint8))[torch.arange(Fe) % POOL].contiguous().pin_memory()
+            c_out = [torch.empty((Fe, 3, H, W), dtype=torch.uint8).pin_memory()] + [torch.empty((Fe, 1, H, W)).pin_memory() for _ in range(3)] + \
+                    [torch.empty((Fe, 1, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            pipe = ops.PairPipeline(local, H, W, chunk_frames=args.e2e_chunk)
+            for _ in range(2):
+                pipe.run_u8(c_img, h_depth, h_s, *c_out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                pipe.run_u8(c_img, h_depth, h_s, *c_out)
+            tc = time.perf_counter() - t0
+            pipe.close()
+            tc_t = torch.tensor([tc], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tc_t, op=dist.ReduceOp.MAX)
+            line["e2e_compact"] = {"value": world * Fe * Ke / float(tc_t.item()), "unit": "pairs/s", "h2d_bytes_per_step": Fe * (7 * H * W + 4),
+                                   "d2h_bytes_per_step": Fe * 17 * H * W, "api": "ofd_pair_pipeline_run_u8 (uint8 colour/masks, x planes only; lossless for uint8-valued images)"}
+        except Exception as e:
+            line["e2e_compact"] = {"error": repr(e)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle

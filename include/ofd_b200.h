@@ -207,6 +207,14 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
 int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host,
                           const float* sBf_host, int B, float* img1_host, float* depth1_host, float* back_flow_host,
                           float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/);
+/* Compact transport of the same pipeline: colour planes and the valid / collision masks cross PCIe as uint8 and the
+ * two constant planes (flow.y == -0.0, back_flow.y == +0.0) are not transferred: 7 B/px up, 16-17 B/px down instead
+ * of 16 and 40.  Lossless when img0 holds integers 0..255 - what the reference's loader delivers (cv2.imread then
+ * .type(float32), utils.py:17-25).  back_flow_x / flow_x are [B,1,H,W]. */
+int ofd_pair_pipeline_run_u8(ofd_pair_pipeline* p, const uint8_t* img0_u8_host, const float* depth0_host,
+                             const float* sBf_host, int B, uint8_t* img1_u8_host, float* depth1_host,
+                             float* back_flow_x_host, float* flow_x_host /*nullable*/, uint8_t* valid_u8_host,
+                             uint8_t* collision_u8_host /*nullable*/);
 void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p);
 
 #ifdef __cplusplus

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ofd_bilateral_iter": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "ofd_pair_pipeline_run_u8": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "ofd_pair_pipeline_destroy": (None, [_p]),
 }
 

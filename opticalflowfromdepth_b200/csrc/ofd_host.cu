@@ -13,7 +13,19 @@ struct ofd_pair_pipeline {
     float* d_in[NSLOT];   // img0 (3) | depth0 (1) per frame, frames contiguous per plane group
     float* d_out[NSLOT];  // img1 (3) | depth1 (1) | back_flow (2) | flow (2) | valid (1) | collision (1)
     float* d_s[NSLOT];
+    unsigned char* d_u8[NSLOT];  // compact transport staging: img0 u8 (3) in | img1 u8 (3) + valid (1) + collision (1) out
 };
+
+namespace ofd {
+// compact host transport (ofd_pair_pipeline_run_u8): colour planes and masks cross PCIe as bytes
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+__global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (unsigned char)__float2uint_rn(fminf(fmaxf(in[i], 0.0f), 255.0f));
+}
+}  // namespace ofd
 
 using namespace ofd;
 
@@ -34,12 +46,13 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     if (!p) return fail(OFD_E_ARG, "ofd_pair_pipeline_create: out of host memory");
     p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) p->st[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr;
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) p->st[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
         cudaError_t e = cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&p->d_in[s], n * 4 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_out[s], n * 10 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_s[s], n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_u8[s], n * 8 * hw);
         if (e != cudaSuccess) {
             int rc = fail((int)e, "ofd_pair_pipeline_create: %s", cudaGetErrorString(e));
             void ofd_pair_pipeline_destroy(ofd_pair_pipeline*);
@@ -59,6 +72,7 @@ void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
         cudaFree(p->d_in[s]);
         cudaFree(p->d_out[s]);
         cudaFree(p->d_s[s]);
+        cudaFree(p->d_u8[s]);
     }
     delete p;
 }
@@ -104,6 +118,64 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
         if (collision_host)
             OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
+    return OFD_OK;
+}
+
+// Compact transport of the same pipeline: colour and masks as uint8, the two constant planes (flow.y == -0.0,
+// back_flow.y == +0.0) not transferred at all.  Lossless when img0 holds integers 0..255, which is what the reference's
+// loader delivers (cv2.imread -> .type(float32), utils.py:17-25); 7 B/px up and 16-17 B/px down instead of 16 and 40.
+int ofd_pair_pipeline_run_u8(ofd_pair_pipeline* p, const unsigned char* img0_u8_host, const float* depth0_host,
+                             const float* sBf_host, int B, unsigned char* img1_u8_host, float* depth1_host,
+                             float* back_flow_x_host, float* flow_x_host, unsigned char* valid_u8_host,
+                             unsigned char* collision_u8_host) {
+    const char* fn = "ofd_pair_pipeline_run_u8";
+    if (!p) return fail(OFD_E_NULL, "%s: pipeline is NULL", fn);
+    if (B < 0) return fail(OFD_E_SHAPE, "%s: negative B", fn);
+    if (B == 0) return OFD_OK;
+    if (!img0_u8_host || !depth0_host || !sBf_host || !img1_u8_host || !depth1_host || !back_flow_x_host || !valid_u8_host)
+        return fail(OFD_E_NULL, "%s: NULL host pointer", fn);
+    OFD_CUDA(cudaSetDevice(p->device));
+    const size_t hw = (size_t)p->H * p->W, F = sizeof(float);
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += p->chunk, ++k) {
+        const int s = k % ofd_pair_pipeline::NSLOT;
+        const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
+        cudaStream_t st = p->st[s];
+        float* dimg = p->d_in[s];
+        float* ddep = dimg + n * 3 * hw;
+        float* o_img = p->d_out[s];
+        float* o_dep = o_img + n * 3 * hw;
+        float* o_bf = o_dep + n * hw;
+        float* o_fl = o_bf + n * 2 * hw;
+        float* o_val = o_fl + n * 2 * hw;
+        float* o_col = o_val + n * hw;
+        unsigned char* u_in = p->d_u8[s];
+        unsigned char* u_img = u_in + n * 3 * hw;
+        unsigned char* u_val = u_img + n * 3 * hw;
+        unsigned char* u_col = u_val + n * hw;
+        OFD_CUDA(cudaMemcpyAsync(u_in, img0_u8_host + (size_t)b0 * 3 * hw, n * 3 * hw, cudaMemcpyHostToDevice, st));
+        OFD_CUDA(cudaMemcpyAsync(ddep, depth0_host + (size_t)b0 * hw, n * hw * F, cudaMemcpyHostToDevice, st));
+        OFD_CUDA(cudaMemcpyAsync(p->d_s[s], sBf_host + b0, n * F, cudaMemcpyHostToDevice, st));
+        u8_to_f32_kernel<<<592, 256, 0, st>>>(u_in, dimg, n * 3 * hw);
+        int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[s], (int)n, p->H, p->W, o_img, o_dep, o_bf, o_fl, o_val,
+                                    collision_u8_host ? o_col : nullptr, nullptr, st);
+        if (rc) return rc;
+        f32_to_u8_kernel<<<592, 256, 0, st>>>(o_img, u_img, n * 3 * hw);
+        f32_to_u8_kernel<<<296, 256, 0, st>>>(o_val, u_val, n * hw);
+        if (collision_u8_host) f32_to_u8_kernel<<<296, 256, 0, st>>>(o_col, u_col, n * hw);
+        rc = check_launch(fn);
+        if (rc) return rc;
+        OFD_CUDA(cudaMemcpyAsync(img1_u8_host + (size_t)b0 * 3 * hw, u_img, n * 3 * hw, cudaMemcpyDeviceToHost, st));
+        OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
+        // x planes only: plane 0 of every [2,H,W] frame (pitch 2*hw floats)
+        OFD_CUDA(cudaMemcpy2DAsync(back_flow_x_host + (size_t)b0 * hw, hw * F, o_bf, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
+        if (flow_x_host)
+            OFD_CUDA(cudaMemcpy2DAsync(flow_x_host + (size_t)b0 * hw, hw * F, o_fl, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
+        OFD_CUDA(cudaMemcpyAsync(valid_u8_host + (size_t)b0 * hw, u_val, n * hw, cudaMemcpyDeviceToHost, st));
+        if (collision_u8_host)
+            OFD_CUDA(cudaMemcpyAsync(collision_u8_host + (size_t)b0 * hw, u_col, n * hw, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
     return OFD_OK;

@@ -285,6 +285,20 @@ class PairPipeline:
         _lib.call("ofd_pair_pipeline_run", self._h, _ptr(img0), _ptr(depth0), _ptr(sBf), B, _ptr(img1), _ptr(depth1),
                   _ptr(back_flow), _ptr(flow), _ptr(valid), _ptr(collision))
 
+    def run_u8(self, img0_u8, depth0, sBf, img1_u8, depth1, back_flow_x, flow_x, valid_u8, collision_u8):
+        """Compact transport (ofd_pair_pipeline_run_u8): uint8 colour / masks, x planes only.  CPU tensors, contiguous."""
+        B = img0_u8.shape[0]
+        for n, t, dt in (("img0_u8", img0_u8, torch.uint8), ("depth0", depth0, torch.float32), ("sBf", sBf, torch.float32),
+                         ("img1_u8", img1_u8, torch.uint8), ("depth1", depth1, torch.float32),
+                         ("back_flow_x", back_flow_x, torch.float32), ("flow_x", flow_x, torch.float32),
+                         ("valid_u8", valid_u8, torch.uint8), ("collision_u8", collision_u8, torch.uint8)):
+            if t is None:
+                continue
+            if t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous {dt} CPU tensor")
+        _lib.call("ofd_pair_pipeline_run_u8", self._h, _ptr(img0_u8), _ptr(depth0), _ptr(sBf), B, _ptr(img1_u8), _ptr(depth1),
+                  _ptr(back_flow_x), _ptr(flow_x), _ptr(valid_u8), _ptr(collision_u8))
+
     def close(self):
         if self._h:
             _lib.load().ofd_pair_pipeline_destroy(self._h)

@@ -308,6 +308,27 @@ def test_pair_pipeline_host_front_end(pkg):
         assert np.array_equal(o.numpy(), wnt)
 
 
+def test_pair_pipeline_compact_u8_transport(pkg):
+    """uint8 colour/mask transport == the float32 pipeline on uint8-valued images (what cv2.imread delivers)."""
+    B, h, w = 7, 48, 64
+    rng = np.random.default_rng(5)
+    img_u8 = torch.from_numpy(rng.integers(0, 256, (B, 3, h, w)).astype(np.uint8)).pin_memory()
+    depth = torch.from_numpy(rng.integers(1, 60, (B, 1, h, w)).astype(np.float32)).pin_memory()
+    depth[0, 0, 0, 0] = 1000.0
+    sBf = torch.from_numpy(rng.uniform(40, 55, B).astype(np.float32))
+    o_img = torch.empty((B, 3, h, w), dtype=torch.uint8).pin_memory()
+    o_dep, o_bfx, o_flx = (torch.empty((B, 1, h, w)).pin_memory() for _ in range(3))
+    o_val, o_col = (torch.empty((B, 1, h, w), dtype=torch.uint8).pin_memory() for _ in range(2))
+    pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=3)
+    pipe.run_u8(img_u8, depth, sBf, o_img, o_dep, o_bfx, o_flx, o_val, o_col)
+    pipe.close()
+    want = oracle.disparity_pair(img_u8.numpy().astype(np.float32), depth.numpy(), sBf.numpy())
+    assert np.array_equal(o_img.numpy().astype(np.float32), want[0]) and np.array_equal(o_dep.numpy(), want[1])
+    assert np.array_equal(o_bfx.numpy(), want[2][:, 0:1]) and not want[2][:, 1].any()
+    assert np.array_equal(o_flx.numpy(), want[3][:, 0:1]) and np.all(np.signbit(want[3][:, 1]))
+    assert np.array_equal(o_val.numpy().astype(np.float32), want[4]) and np.array_equal(o_col.numpy().astype(np.float32), want[5])
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # depth helpers, disparity flow, 6-DoF flow, geometry classes, special flows
 # ---------------------------------------------------------------------------------------------------------------
