@@ -177,6 +177,14 @@ int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void*
 int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream);
 
 /*
+ * ofd_inpaint_mask — the hole-mask logic of utils.inpaint (utils.py:137-149; SURVEY 8f-1, the step after every image
+ * splat): M = (valid != collision); M' = 3x3 dilate(M); H' = valid * (M' == M); mask = 1 - H' as uint8 [B,1,H,W],
+ * i.e. the mask the reference hands to cv2.inpaint (the Telea fill itself stays a host-side hook).
+ */
+int ofd_inpaint_mask(const float* valid, const float* collision, int B, int H, int W, uint8_t* mask,
+                     ofd_stream_t stream);
+
+/*
  * ofd_special_flow — SpecialFlow.forward (preprocess.py:24-105): analytic augmentation flows.
  *   kind 5 flip (vertical, :47-60; no params), 6 rotate (:62-79), 7 shear (:81-99).
  *   params_host (HOST, 10 floats, kinds 6/7): cx, cy, M row-major (4), Mrev row-major (4) with

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ofd_reproject_pair": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ofd_fix_warped_depth": (_i, [_p, _sz, _p]),
+    "ofd_inpaint_mask": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofd_special_flow": (_i, [_i, _p, _i, _i, _p, _p, _p]),
     "ofd_bilateral_iter": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),

@@ -227,6 +227,31 @@ __global__ void __launch_bounds__(256) fix_depth_kernel(float* __restrict__ d, s
         d[p] = fix_depth(d[p]);
 }
 
+// ---- utils.inpaint hole-mask logic (utils.py:137-149) ----------------------------------------------
+// M = (valid != collision); M' = 3x3 dilation of M (cv2.dilate, out-of-image taps ignored); P = (M' == M);
+// H' = valid * P; mask = 1 - H'  (uint8: the mask handed to cv2.inpaint)
+__global__ void __launch_bounds__(256) inpaint_mask_kernel(const float* __restrict__ valid, const float* __restrict__ collision,
+                                                          int H, int W, unsigned char* __restrict__ mask) {
+    const int b = blockIdx.z, j = blockIdx.y * 8 + threadIdx.y, i = blockIdx.x * 32 + threadIdx.x;
+    if (j >= H || i >= W) return;
+    const size_t base = (size_t)b * H * W;
+    const float* v = valid + base;
+    const float* c = collision + base;
+    const size_t p = (size_t)j * W + i;
+    const unsigned char m = (v[p] != c[p]) ? 1 : 0;
+    unsigned char md = 0;
+    for (int dj = -1; dj <= 1; ++dj)
+        for (int di = -1; di <= 1; ++di) {
+            const int jj = j + dj, ii = i + di;
+            if (jj >= 0 && jj < H && ii >= 0 && ii < W) {
+                const size_t q = (size_t)jj * W + ii;
+                md |= (v[q] != c[q]) ? 1 : 0;
+            }
+        }
+    const unsigned char hp = (unsigned char)(v[p] * (float)(md == m ? 1 : 0));  // (H * P).astype(uint8)
+    mask[base + p] = (unsigned char)(1 - hp);
+}
+
 static unsigned blocks_for(size_t n, unsigned per_block, unsigned cap) {
     size_t g = (n + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -328,6 +353,16 @@ int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream) {
     if (!depth) return fail(OFD_E_NULL, "ofd_fix_warped_depth: NULL pointer");
     fix_depth_kernel<<<blocks_for(n, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(depth, n);
     return check_launch("ofd_fix_warped_depth");
+}
+
+int ofd_inpaint_mask(const float* valid, const float* collision, int B, int H, int W, uint8_t* mask, ofd_stream_t stream) {
+    const char* fn = "ofd_inpaint_mask";
+    if (B < 0 || H < 0 || W < 0 || B > 65535 || (H + 7) / 8 > 65535) return fail(OFD_E_SHAPE, "%s: bad dimension", fn);
+    if (B == 0 || H == 0 || W == 0) return OFD_OK;
+    if (!valid || !collision || !mask) return fail(OFD_E_NULL, "%s: NULL tensor pointer", fn);
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B), block(32, 8);
+    inpaint_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(valid, collision, H, W, mask);
+    return check_launch(fn);
 }
 
 }  // extern "C"

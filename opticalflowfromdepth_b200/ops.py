@@ -242,6 +242,16 @@ def fix_warped_depth_(depth):
     return depth
 
 
+def inpaint_mask(valid, collision):
+    """The mask utils.inpaint hands to cv2.inpaint (utils.py:137-149): uint8 [B,1,H,W], 1 = pixel to fill."""
+    _check("valid", valid, dtype=torch.float32)
+    _check("collision", collision, dtype=torch.float32, shape=valid.shape)
+    B, _, H, W = valid.shape
+    mask = torch.empty((B, 1, H, W), dtype=torch.uint8, device=valid.device)
+    _lib.call("ofd_inpaint_mask", _ptr(valid), _ptr(collision), B, H, W, _ptr(mask), _stream(valid.device))
+    return mask
+
+
 def special_flow(kind: int, params, H: int, W: int, device):
     """SpecialFlow (preprocess.py:24-105): returns (flow[2,H,W], back_flow[2,H,W]); params = 10 host floats or None."""
     flow = torch.empty((2, H, W), dtype=torch.float32, device=device)

@@ -19,7 +19,7 @@ from . import geometry, ops
 from .fw import FW
 
 __all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch",
-           "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "synthesize_pairs", "synthesize_group"]
+           "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
 
 
 # ---- utils.py helpers ------------------------------------------------------------------------------------------
@@ -54,6 +54,24 @@ def fix_warped_depth(depth):
     fixed = ops.fix_warped_depth_(depth.float().contiguous())
     depth.copy_(fixed)
     return depth
+
+
+def inpaint(img, valid, collision):
+    """utils.inpaint (utils.py:136-151) as a HOST-SIDE HOOK, outside the hot path: the hole mask is computed on the
+    GPU (ofd_inpaint_mask); the Telea fill is OpenCV on the CPU exactly as in the reference (cv2.inpaint radius 3), with
+    the image crossing as uint8.  Accepts [3,H,W] + [1,H,W] or batched [B,3,H,W] + [B,1,H,W]; returns float32 on img's device."""
+    import cv2  # only needed when this hook is used
+
+    single = img.dim() == 3
+    im = img.unsqueeze(0) if single else img
+    v = (valid.unsqueeze(0) if single else valid).float().contiguous()
+    c = (collision.unsqueeze(0) if single else collision).float().contiguous()
+    with torch.cuda.device(im.device):
+        mask = ops.inpaint_mask(v, c).cpu().numpy()
+    im_u8 = im.permute(0, 2, 3, 1).to(torch.uint8).cpu().numpy()  # .astype(np.uint8): truncation, utils.py:147
+    out = np.stack([cv2.inpaint(np.ascontiguousarray(im_u8[b]), mask[b, 0], 3, cv2.INPAINT_TELEA) for b in range(im_u8.shape[0])])
+    res = torch.from_numpy(out.astype(np.float32)).permute(0, 3, 1, 2).contiguous().to(im.device)
+    return res[0] if single else res
 
 
 # ---- preprocess.py:184-235 -------------------------------------------------------------------------------------

@@ -152,3 +152,20 @@ def special_flow(h, w, kind):
     else:
         raise ValueError(kind)
     return (p1 - p0).permute(2, 0, 1), (pp - p0).permute(2, 0, 1), params
+
+
+def inpaint_mask(valid, collision):
+    """utils.py:137-149 up to the cv2.inpaint call, numpy only: valid, collision [H,W] float -> uint8 mask [H,W].
+    (3x3 dilation with out-of-image taps ignored, as cv2.dilate's default border does.)"""
+    import numpy as np
+
+    H = np.asarray(valid)
+    M = (1 - (H == np.asarray(collision))).astype(np.uint8)
+    pad = np.pad(M, 1, "constant")
+    Mp = np.zeros_like(M)
+    for dj in range(3):
+        for di in range(3):
+            Mp = np.maximum(Mp, pad[dj:dj + M.shape[0], di:di + M.shape[1]])
+    P = (Mp == M).astype(np.uint8)
+    Hp = (H * P).astype(np.uint8)
+    return (1 - Hp).astype(np.uint8)

@@ -55,6 +55,7 @@ def install_reference():
     import utils as ref_utils
 
     sys.modules["dataloader"].COCO = None
+    ref_utils._real_inpaint = ref_utils.inpaint
     ref_utils.inpaint = lambda img, valid, collision: img
     src = (REF / "preprocess.py").read_text().splitlines()
     assert src[462].rstrip().endswith("axis=0"), src[462]
@@ -262,6 +263,71 @@ def pipeline_case(pp, ref_utils):
     return dict(img0=img0, raw_depth=raw, group=group.astype(np.float32), sBf=np.float32(sBf.item()), T1=T1.numpy())
 
 
+def inpaint_case(pp, ref_utils):
+    """The same pipeline with the reference's REAL utils.inpaint (utils.py:136-151; OpenCV Telea on the CPU).  Records
+    the group tensor and, for each of the 5 inpaint calls, (valid, collision) and the mask handed to cv2.inpaint."""
+    import cv2
+
+    rng = np.random.default_rng(2024)
+    h, w = 40, 56
+    img0 = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+    raw = diml_depth(rng, h, w).astype(np.float32)
+    calls, grabbed = [], {}
+
+    class Stop(Exception):
+        pass
+
+    real_cv_inpaint = cv2.inpaint
+
+    def rec_cv_inpaint(src, mask, radius, flags):
+        calls[-1]["mask"] = mask.copy()
+        return real_cv_inpaint(src, mask, radius, flags)
+
+    def rec_inpaint(img, valid, collision):
+        calls.append({"valid": valid.numpy().copy(), "collision": collision.numpy().copy()})
+        return ref_utils._real_inpaint(img, valid, collision)
+
+    def fake_savez(path, **kw):
+        grabbed.update(kw)
+        raise Stop()
+
+    saved = (ref_utils.inpaint, cv2.inpaint, np.savez_compressed, torch.Tensor.get_device)
+    ref_utils.inpaint, cv2.inpaint, np.savez_compressed = rec_inpaint, rec_cv_inpaint, fake_savez
+    torch.Tensor.get_device = lambda self: "cpu"  # utils.py:150 `.to(img.get_device())` fails for CPU tensors (Appendix B)
+    pp.os.makedirs = lambda *a, **k: None
+    ppa = pp.PreprocessPlusAugment(device="cpu")
+    ref_utils.set_seed(12345 + 11)
+    try:
+        with redirect_stdout(io.StringIO()):
+            ppa((torch.from_numpy(img0), torch.from_numpy(raw.copy())[None]), "/tmp/ofd_golden/0", is_stereo=False)
+    except Stop:
+        pass
+    finally:
+        ref_utils.inpaint, cv2.inpaint, np.savez_compressed, torch.Tensor.get_device = saved
+    assert len(calls) == 5 and grabbed["img_depth_flow"].shape == (44, h, w)
+    out = dict(img0=img0, raw_depth=raw, group=grabbed["img_depth_flow"].astype(np.float32))
+    for k, c in enumerate(calls):
+        out[f"valid{k}"], out[f"collision{k}"], out[f"mask{k}"] = c["valid"], c["collision"], c["mask"]
+        assert np.array_equal(oflow.inpaint_mask(c["valid"][0], c["collision"][0]), c["mask"]), k
+    # synthetic collision cases for the mask logic (collision is identically 0 in the pipeline)
+    v = (rng.random((6, 1, 21, 29)) > 0.3).astype(np.float32)
+    c = ((rng.random((6, 1, 21, 29)) > 0.8) * v).astype(np.float32)
+    out["mask_valid"], out["mask_collision"] = v, c
+    ms = []
+    for b in range(6):
+        rec = {}
+        cv2.inpaint = lambda src, mask, radius, flags, rec=rec: rec.setdefault("m", mask.copy()) is None or src
+        torch.Tensor.get_device = lambda self: "cpu"
+        try:
+            ref_utils._real_inpaint(torch.zeros(3, 21, 29), torch.from_numpy(v[b]), torch.from_numpy(c[b]))
+        finally:
+            cv2.inpaint, torch.Tensor.get_device = saved[1], saved[3]
+        ms.append(rec["m"])
+        assert np.array_equal(oflow.inpaint_mask(v[b, 0], c[b, 0]), rec["m"])
+    out["mask_out"] = np.stack(ms)[:, None]
+    return out
+
+
 def concat_back_cases(pp):
     out = {}
     rng = np.random.default_rng(31)
@@ -288,6 +354,7 @@ def main():
         "bilateral_cases": lambda: bilateral_cases(ref_bil),
         "concat_back_cases": lambda: concat_back_cases(pp),
         "pipeline_case": lambda: pipeline_case(pp, ref_utils),
+        "inpaint_case": lambda: inpaint_case(pp, ref_utils),
     }
     for name, job in jobs.items():
         data = job()

@@ -769,3 +769,37 @@ def test_cuda_graph_capture_and_replay(pkg):
         torch.cuda.synchronize()
         assert torch.equal(outs[7], pkg.ops.disparity_pair(img, depth, sBf)[0])
     torch.cuda.current_stream().wait_stream(s)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8f-1 ("next" row): utils.inpaint — hole mask on the GPU, Telea fill as the reference's host-side OpenCV call
+# ---------------------------------------------------------------------------------------------------------------
+def test_inpaint_mask_vs_reference_golden(pkg, golden):
+    g = golden("inpaint_case")
+    m = pkg.ops.inpaint_mask(cu(g["mask_valid"]), cu(g["mask_collision"]))
+    assert m.dtype == torch.uint8 and eq(m, g["mask_out"])
+    for k in range(5):
+        m = pkg.ops.inpaint_mask(cu(g[f"valid{k}"])[None], cu(g[f"collision{k}"])[None])
+        assert eq(m[0, 0], g[f"mask{k}"])
+
+
+def test_group_with_inpaint_hook_vs_reference_pipeline(pkg, golden):
+    """The reference's group tensor WITH its real utils.inpaint (preprocess.py:341-447) vs synthesize_group with the
+    inpaint hook: pair 0->1 (exact arithmetic) bit-exact including the inpainted image; later pairs as in the
+    inpaint-free test (6-DoF tolerance can move a few targets)."""
+    pytest.importorskip("cv2")
+    g, gp = golden("inpaint_case"), golden("pipeline_case")
+    grp = g["group"]
+    h, w = grp.shape[1:]
+    img0 = cu(g["img0"])[None]
+    depth0 = pkg.ops.normalize_depth(cu(g["raw_depth"])[None, None])
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    cam = pkg.geometry.camera_constants(K, invK, torch.from_numpy(gp["T1"])).to(DEV)
+    res = pkg.synthesis.synthesize_group(img0, depth0, torch.tensor([float(gp["sBf"])], device=DEV), cam, inpaint=pkg.synthesis.inpaint)
+    assert eq(res["img1"][0], grp[4:7]) and eq(res["depth1"][0], grp[7:8])
+    assert eq(res["flow01"][0], grp[24:26]) and eq(res["back_flow01"][0], grp[26:28])
+    assert (grp[4:7] != gp["group"][4:7]).any()  # the inpaint really changed the image
+    for name, (a, b) in dict(img2=(8, 11), img3=(12, 15), img2_prime=(16, 19), img3_prime=(20, 23)).items():
+        diff = float((res[name][0].cpu().numpy() != grp[a:b]).mean())
+        print(f"[group+inpaint] {name}: differing fraction {diff:.2e}")
+        assert diff <= 0.03, name

@@ -143,3 +143,13 @@ def test_pipeline_golden_is_consistent_with_oracle(golden):
     img1, d1, back, flow, valid, _ = oracle.disparity_pair(g["img0"][None], depth0[None], np.array([g["sBf"]], np.float32))
     assert np.array_equal(img1[0], grp[4:7]) and np.array_equal(d1[0], grp[7:8])
     assert np.array_equal(flow[0], grp[24:26]) and np.array_equal(back[0], grp[26:28])
+
+
+def test_inpaint_mask_oracle_matches_reference(golden):
+    """utils.inpaint's hole-mask logic (utils.py:137-149): masks captured at the reference's cv2.inpaint call."""
+    g = golden("inpaint_case")
+    for k in range(5):
+        assert np.array_equal(oflow.inpaint_mask(g[f"valid{k}"][0], g[f"collision{k}"][0]), g[f"mask{k}"])
+    for b in range(g["mask_valid"].shape[0]):
+        assert np.array_equal(oflow.inpaint_mask(g["mask_valid"][b, 0], g["mask_collision"][b, 0]), g["mask_out"][b, 0])
+    assert g["mask_out"].any() and not g["mask_out"].all()
