@@ -6,8 +6,9 @@ each runs its index range through the fused kernels; at the end of the run the r
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Sequence
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -52,3 +53,43 @@ def reduce_counters(counters: torch.Tensor, group=None) -> Dict[str, int]:
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     host = total.cpu().tolist()
     return {name: int(host[slot]) for name, slot in COUNTER_NAMES.items()}
+
+
+def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device, batch: int = 32, epoch: int = 0,
+              dataset_len: int = 0, inpaint: Optional[Callable] = None, sink: Optional[Callable] = None,
+              counters: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's per-frame driver loop (preprocess.py:551-561 + the group part of PreprocessPlusAugment.forward,
+    :341-447) over this rank's `indices`, `batch` frames at a time on `device`.
+
+    load_frame(idx) -> (img[3,H,W] float32, raw_depth[1,H,W] float32) numpy arrays (all frames of a sweep share H x W).
+    For every frame the generator is reseeded with frame_seed(idx, epoch, dataset_len) and the disparity scale and the
+    camera pose are drawn in the reference's order, so a frame's result does not depend on batch size, shard or rank.
+    sink(idx_list, results_dict) receives each batch's device tensors (e.g. to stage them to pinned host memory).
+    Returns the counter block (frames, pairs, hit/hole/collision/dropped/tie pixel counts) of this rank."""
+    from . import geometry, ops, synthesis
+
+    dev = torch.device(device)
+    if counters is None:
+        counters = ops.new_counters(dev)
+    for idx_list in batches(indices, batch):
+        frames = [load_frame(i) for i in idx_list]
+        img = torch.from_numpy(np.stack([f[0] for f in frames])).to(dev)
+        raw = torch.from_numpy(np.stack([f[1] for f in frames])).to(dev)
+        h, w = img.shape[-2:]
+        K, inv_K = synthesis.Plausible.K((h, w))
+        s_vals, cams = [], []
+        for i in idx_list:
+            synthesis.set_seed(frame_seed(i, epoch, dataset_len))
+            s_vals.append(float(synthesis.Convert.disparity_scale()))          # preprocess.py:356 (first draw)
+            T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)  # :372 -> :277
+            cams.append(geometry.camera_constants(K, inv_K, T1))
+        sBf = torch.tensor(s_vals, dtype=torch.float32, device=dev)
+        cam = torch.cat(cams).to(dev)
+        with torch.cuda.device(dev):
+            depth = ops.normalize_depth(raw)                                    # :355
+        res = synthesis.synthesize_group(img, depth, sBf, cam, inpaint=inpaint, counters=counters)
+        counters[_lib.CNT_FRAMES] += len(idx_list)
+        counters[_lib.CNT_PAIRS] += 5 * len(idx_list)
+        if sink is not None:
+            sink(idx_list, res)
+    return counters

@@ -803,3 +803,37 @@ def test_group_with_inpaint_hook_vs_reference_pipeline(pkg, golden):
         diff = float((res[name][0].cpu().numpy() != grp[a:b]).mean())
         print(f"[group+inpaint] {name}: differing fraction {diff:.2e}")
         assert diff <= 0.03, name
+
+
+def test_sweep_results_do_not_depend_on_the_partition(pkg, golden):
+    """cfg5 driver: per-image reseeding makes a frame's 5-pair group independent of batch size / shard / rank
+    (preprocess.py:543-547,555), and the sweep reproduces the reference pipeline's golden frame."""
+    from opticalflowfromdepth_b200 import sweep
+
+    h, w, n = 64, 96, 6
+    load = lambda i: pkg.synthetic.diml_frame(i, h, w)  # noqa: E731
+    keep = {}
+
+    def sink_into(store):
+        def sink(idx_list, res):
+            for k, i in enumerate(idx_list):
+                store[i] = {name: t[k].clone() for name, t in res.items()}
+        return sink
+
+    whole = {}
+    c_all = sweep.run_sweep(range(n), load, DEV, batch=4, dataset_len=n, sink=sink_into(whole))
+    parts, c_parts = {}, None
+    for rank in range(2):
+        c = sweep.run_sweep(sweep.shard_strided(n, 2, rank), load, DEV, batch=2, dataset_len=n, sink=sink_into(parts))
+        c_parts = c.clone() if c_parts is None else c_parts + c
+    assert sorted(whole) == sorted(parts) == list(range(n))
+    for i in range(n):
+        for name in whole[i]:
+            assert torch.equal(whole[i][name], parts[i][name]), (i, name)
+    assert torch.equal(c_all, c_parts) and int(c_all[5]) == n and int(c_all[6]) == 5 * n
+    # the reference's own frame (seed 12345 + 11): the sweep draws the same scale and pose
+    g = golden("pipeline_case")
+    one = {}
+    sweep.run_sweep([11], lambda i: (g["img0"], g["raw_depth"][None]), DEV, batch=1, dataset_len=0, sink=sink_into(one))
+    assert eq(one[11]["img1"], g["group"][4:7]) and eq(one[11]["flow01"], g["group"][24:26])
+    _flow_tolerance_check(one[11]["flow12"], g["group"][28:30], *g["group"].shape[1:], "sweep flow12")
