@@ -37,6 +37,19 @@ using namespace ofd;
 
 extern "C" {
 
+void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
+        if (p->st[s]) cudaStreamSynchronize(p->st[s]), cudaStreamDestroy(p->st[s]);
+        cudaFree(p->d_in[s]);
+        cudaFree(p->d_out[s]);
+        cudaFree(p->d_s[s]);
+        cudaFree(p->d_u8[s]);
+    }
+    delete p;
+}
+
 int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out) {
     if (!out) return fail(OFD_E_NULL, "ofd_pair_pipeline_create: out is NULL");
     if (H <= 0 || W <= 0 || chunk_frames <= 0 || chunk_frames > 65535)
@@ -55,26 +68,12 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
         if (e == cudaSuccess) e = cudaMalloc(&p->d_u8[s], n * 8 * hw);
         if (e != cudaSuccess) {
             int rc = fail((int)e, "ofd_pair_pipeline_create: %s", cudaGetErrorString(e));
-            void ofd_pair_pipeline_destroy(ofd_pair_pipeline*);
             ofd_pair_pipeline_destroy(p);
             return rc;
         }
     }
     *out = p;
     return OFD_OK;
-}
-
-void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
-    if (!p) return;
-    cudaSetDevice(p->device);
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
-        if (p->st[s]) cudaStreamSynchronize(p->st[s]), cudaStreamDestroy(p->st[s]);
-        cudaFree(p->d_in[s]);
-        cudaFree(p->d_out[s]);
-        cudaFree(p->d_s[s]);
-        cudaFree(p->d_u8[s]);
-    }
-    delete p;
 }
 
 // All *_host pointers are HOST memory (page-locked for overlap), dense [B,C,H,W]; flow/collision may be NULL.
