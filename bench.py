@@ -340,12 +340,22 @@ def run_ours(args):
 
                 kinds = [5 + k % 3 for k in range(Fa)]
 
+                gen = torch.Generator().manual_seed(4)
+
                 def astep():
+                    synthesis.augment_flow_batch(a_img, a_dep, pa["img1"], pa["depth1"], pa["flow"], pa["back_flow"], kinds,
+                                                 reference_draws=False, generator=gen)
+
+                def astep_ref():
                     synthesis.augment_flow_batch(a_img, a_dep, pa["img1"], pa["depth1"], pa["flow"], pa["back_flow"], kinds)
 
-                ta = timed(astep, 10, 3, sync, barrier) / 10
-                extras["cfg4_augment_368x496_b8"] = {"pairs_per_s": Fa / ta, "ms_per_step": 1e3 * ta, "pairs_per_step": Fa,
-                                                     "what": "augment_flow_batch: geometric branch (flip/rotate/shear per sample), 6 batched splats + 8 special-flow launches"}
+                ta = timed(astep, 50, 5, sync, barrier) / 50
+                tr = timed(astep_ref, 10, 3, sync, barrier) / 10
+                extras["cfg4_augment_368x496_b8"] = {"pairs_per_s": Fa / ta, "ms_per_step": 1e3 * ta, "pairs_per_step": Fa, "launches_per_step": 13,
+                                                     "pairs_per_s_reference_draw_order": Fa / tr,
+                                                     "what": "augment_flow_batch -> ofd_augment_pairs: geometric branch (flip/rotate/shear per sample), one native call = "
+                                                             "1 batched special-flow launch + 6 batched splats; parameters from sample_special_params (2 generator calls "
+                                                             "per batch); *_reference_draw_order draws per sample in the reference's get_random order (host-bound)"}
             except Exception as e:
                 extras["cfg4_augment_368x496_b8"] = {"error": repr(e)}
         if "group" not in skip:

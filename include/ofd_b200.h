@@ -195,6 +195,36 @@ int ofd_special_flow(int kind, const float* params_host, int H, int W, float* fl
                      ofd_stream_t stream);
 
 /*
+ * ofd_special_flow_batch — one special flow per sample of a batch in one launch (per 48 samples): kinds_host[B] (HOST
+ * ints, 5/6/7) and params_host[B,10] (HOST floats, layout as ofd_special_flow; ignored for kind 5)
+ * -> flow[B,2,H,W], back_flow[B,2,H,W].
+ */
+int ofd_special_flow_batch(const int* kinds_host, const float* params_host, int B, int H, int W, float* flow,
+                           float* back_flow, ofd_stream_t stream);
+
+/*
+ * ofd_augment_pairs — the geometric branch of augment_flow (preprocess.py:116-147, inpaint excluded) for a batch of B
+ * pairs (img0, depth0, img1, depth1, flow01, back_flow01), one special flow per sample (BASELINE config 4: in-loop
+ * augmentation for RAFT training).  13 launches issued back to back from this one call:
+ *   special/back_special   = SpecialFlow(kind_b, params_b)                                   (:118)
+ *   aug0_flow              = ConcatFlow(back_special, special, flow01, depth0)               (:121)
+ *   aug1_flow              = ConcatFlow(flow01, back_flow01, special, depth1)                (:122)
+ *   aug_img0 | aug_depth0  = FW(img0 | depth0, special, depth0), fix_warped_depth on depth   (:124-129)
+ *   aug_img1 | aug_depth1  = FW(img1 | depth1, special, depth1), fix_warped_depth on depth   (:130-135)
+ *   back_aug0_flow         = BackFlow(aug0_flow, aug_depth0)                                 (:137)
+ *   back_aug1_flow         = BackFlow(aug1_flow, depth0)                                     (:138)
+ * valid_img* / collision_img* [B,1,H,W] are the masks of the two image warps (what utils.inpaint is handed, :127,133;
+ * collision nullable); scratch_valid [B,1,H,W] receives the (unused) masks of the four flow splats.
+ */
+int ofd_augment_pairs(const float* img0, const float* depth0, const float* img1, const float* depth1,
+                      const float* flow01, const float* back_flow01, const int* kinds_host, const float* params_host,
+                      int B, int H, int W, float* special_flow, float* back_special_flow, float* aug_img0,
+                      float* aug_depth0, float* aug0_flow, float* back_aug0_flow, float* aug_img1, float* aug_depth1,
+                      float* aug1_flow, float* back_aug1_flow, float* valid_img0, float* collision_img0,
+                      float* valid_img1, float* collision_img1, float* scratch_valid, uint64_t* counters, void* ws,
+                      size_t ws_bytes, ofd_stream_t stream);
+
+/*
  * ofd_bilateral_iter — one iteration of sparse_bilateral_filtering (bilateral_filter.py:33-58):
  *   discontinuity map from `depth_in` (|1/d - 1/d'| > thr on 4-neighbours of the interior, :63-116), forced to 1
  *   where depth_orig == 0 (:46), border ring edge-replicated (:141-147), then the gated median of window x window

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ofd_fix_warped_depth": (_i, [_p, _sz, _p]),
     "ofd_inpaint_mask": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofd_special_flow": (_i, [_i, _p, _i, _i, _p, _p, _p]),
+    "ofd_special_flow_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "ofd_augment_pairs": (_i, [_p] * 8 + [_i, _i, _i] + [_p] * 17 + [_sz, _p]),
     "ofd_bilateral_iter": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),

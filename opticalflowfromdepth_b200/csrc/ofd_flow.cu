@@ -96,11 +96,8 @@ struct SpecialParams {
     int use_center;
 };
 
-__global__ void __launch_bounds__(256) special_flow_kernel(int kind, SpecialParams sp, int H, int W,
-                                                          float* __restrict__ flow, float* __restrict__ back) {
-    const int j = blockIdx.y * 8 + threadIdx.y;
-    const int i = blockIdx.x * 32 + threadIdx.x;
-    if (j >= H || i >= W) return;
+__device__ __forceinline__ void special_flow_px(int kind, const SpecialParams& sp, int H, int W, int i, int j,
+                                                float* __restrict__ flow, float* __restrict__ back) {
     const size_t hw = (size_t)H * W, p = (size_t)j * W + i;
     const float x = (float)i, y = (float)j;
     if (kind == 5) {
@@ -128,6 +125,32 @@ __global__ void __launch_bounds__(256) special_flow_kernel(int kind, SpecialPara
     flow[hw + p] = __fsub_rn(y1, y);
     back[p] = __fsub_rn(x0, x);
     back[hw + p] = __fsub_rn(y0, y);
+}
+
+__global__ void __launch_bounds__(256) special_flow_kernel(int kind, SpecialParams sp, int H, int W,
+                                                          float* __restrict__ flow, float* __restrict__ back) {
+    const int j = blockIdx.y * 8 + threadIdx.y;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (j >= H || i >= W) return;
+    special_flow_px(kind, sp, H, W, i, j, flow, back);
+}
+
+// One special flow per sample of a batch (in-loop augmentation, BASELINE config 4): the per-sample kind and parameters
+// travel in the kernel parameter block, SPECIAL_BATCH samples per launch.
+constexpr int SPECIAL_BATCH = 48;
+struct SpecialBatch {
+    SpecialParams sp[SPECIAL_BATCH];
+    int kind[SPECIAL_BATCH];
+};
+
+__global__ void __launch_bounds__(256) special_flow_batch_kernel(const __grid_constant__ SpecialBatch sb, int H, int W,
+                                                                float* __restrict__ flow, float* __restrict__ back) {
+    const int b = blockIdx.z;
+    const int j = blockIdx.y * 8 + threadIdx.y;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (j >= H || i >= W) return;
+    const size_t off = (size_t)b * 2 * H * W;
+    special_flow_px(sb.kind[b], sb.sp[b], H, W, i, j, flow + off, back + off);
 }
 
 // ---- normalize_depth ---------------------------------------------------------------------------------------
@@ -323,6 +346,37 @@ int ofd_special_flow(int kind, const float* params_host, int H, int W, float* fl
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
     special_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(kind, sp, H, W, flow, back_flow);
     return check_launch(fn);
+}
+
+int ofd_special_flow_batch(const int* kinds_host, const float* params_host, int B, int H, int W, float* flow,
+                           float* back_flow, ofd_stream_t stream) {
+    const char* fn = "ofd_special_flow_batch";
+    if (B < 0 || H < 0 || W < 0 || (H + 7) / 8 > 65535) return fail(OFD_E_SHAPE, "%s: bad dimension", fn);
+    if (B == 0 || H == 0 || W == 0) return OFD_OK;
+    if (!kinds_host || !params_host || !flow || !back_flow) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    for (int b = 0; b < B; ++b)
+        if (kinds_host[b] < 5 || kinds_host[b] > 7)
+            return fail(OFD_E_ARG, "%s: kinds[%d] = %d, must be 5 (flip), 6 (rotate) or 7 (shear)", fn, b, kinds_host[b]);
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += SPECIAL_BATCH) {
+        const int n = (B - b0) < SPECIAL_BATCH ? (B - b0) : SPECIAL_BATCH;
+        SpecialBatch sb = {};
+        for (int k = 0; k < n; ++k) {
+            const float* q = params_host + (size_t)(b0 + k) * 10;
+            sb.kind[k] = kinds_host[b0 + k];
+            if (sb.kind[k] == 5) continue;
+            sb.sp[k].cx = q[0];
+            sb.sp[k].cy = q[1];
+            for (int m = 0; m < 4; ++m) sb.sp[k].m[m] = q[2 + m], sb.sp[k].mrev[m] = q[6 + m];
+            sb.sp[k].use_center = (sb.kind[k] == 6);
+        }
+        dim3 grid((W + 31) / 32, (H + 7) / 8, n), block(32, 8);
+        special_flow_batch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sb, H, W, flow + (size_t)b0 * 2 * hw,
+                                                                           back_flow + (size_t)b0 * 2 * hw);
+        int rc = check_launch(fn);
+        if (rc) return rc;
+    }
+    return OFD_OK;
 }
 
 int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void* out, void* scratch,

@@ -263,6 +263,55 @@ def special_flow(kind: int, params, H: int, W: int, device):
     return flow, back
 
 
+def _host_params(kinds, params, B):
+    kinds_arr = (C.c_int * B)(*[int(k) for k in kinds])
+    flat = (C.c_float * (10 * B))()
+    for b in range(B):
+        if params[b] is not None:
+            for k in range(10):
+                flat[10 * b + k] = float(params[b][k])
+    return kinds_arr, flat
+
+
+def special_flow_batch(kinds, params, H: int, W: int, device):
+    """One SpecialFlow per sample in one launch: kinds[B] in {5,6,7}, params[B] = 10 host floats or None (kind 5)."""
+    B = len(kinds)
+    flow = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
+    back = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
+    kinds_arr, flat = _host_params(kinds, params, B)
+    _lib.call("ofd_special_flow_batch", kinds_arr, flat, B, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
+    return flow, back
+
+
+def augment_pairs(img0, depth0, img1, depth1, flow01, back_flow01, kinds, params, want_collision=True, counters=None):
+    """ofd_augment_pairs: the geometric branch of augment_flow (preprocess.py:116-147 minus inpaint) for B pairs, ONE call.
+    Returns a dict of the ten result tensors plus the masks of the two image warps."""
+    _check("img0", img0, dtype=torch.float32)
+    B, c3, H, W = img0.shape
+    if c3 != 3:
+        raise ValueError("img0 must be [B,3,H,W]")
+    _check("img1", img1, dtype=torch.float32, shape=(B, 3, H, W))
+    _check("depth0", depth0, dtype=torch.float32, shape=(B, 1, H, W))
+    _check("depth1", depth1, dtype=torch.float32, shape=(B, 1, H, W))
+    _check("flow01", flow01, dtype=torch.float32, shape=(B, 2, H, W))
+    _check("back_flow01", back_flow01, dtype=torch.float32, shape=(B, 2, H, W))
+    if len(kinds) != B or len(params) != B:
+        raise ValueError("kinds and params must have one entry per sample")
+    dev = img0.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    names = (("special_flow", 2), ("back_special_flow", 2), ("aug_img0", 3), ("aug_depth0", 1), ("aug0_flow", 2),
+             ("back_aug0_flow", 2), ("aug_img1", 3), ("aug_depth1", 1), ("aug1_flow", 2), ("back_aug1_flow", 2),
+             ("valid_img0", 1), ("collision_img0", 1), ("valid_img1", 1), ("collision_img1", 1), ("scratch_valid", 1))
+    r = {n: torch.empty((B, c, H, W), **f32) for n, c in names if want_collision or not n.startswith("collision")}
+    kinds_arr, flat = _host_params(kinds, params, B)
+    ws = workspace.get(dev, B, H, W)
+    _run_splat("ofd_augment_pairs", dev, _ptr(img0), _ptr(depth0), _ptr(img1), _ptr(depth1), _ptr(flow01), _ptr(back_flow01),
+               kinds_arr, flat, B, H, W, *[_ptr(r.get(n)) for n, _ in names], _ptr(counters), _ptr(ws),
+               C.c_size_t(ws.numel()), _stream(dev))
+    r.pop("scratch_valid")
+    return r
+
+
 def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
     """One iteration of sparse_bilateral_filtering (bilateral_filter.py:33-58) on [H,W] f32|f64 CUDA tensors."""
     _check("depth_in", depth_in, dtype=(torch.float32, torch.float64))

@@ -18,7 +18,7 @@ from torch import nn
 from . import geometry, ops
 from .fw import FW
 
-__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch",
+__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "sample_special_params",
            "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
 
 
@@ -208,9 +208,10 @@ class SpecialFlow(nn.Module):
         self.horizontal_flip = True
         self.horizontal_shear = True
 
-    def forward(self, size, augment_flow_type):
+    def params(self, size, augment_flow_type):
+        """The host half of forward(): draws the random parameters in the reference's order (utils.py:96-100) and returns
+        (kind, params) with params = [cx, cy, M(4), Mrev(4)] or None for the flip."""
         h, w = size
-        dev = self.device if self.device is not None else "cuda"
         if augment_flow_type >= 7.:
             self.horizontal_shear = not self.horizontal_shear
             s = get_random(0.15, 0.2)
@@ -218,25 +219,58 @@ class SpecialFlow(nn.Module):
                 m, mrev = [1, 0, s, 1], [1, 0, -s, 1]
             else:
                 m, mrev = [1, s, 0, 1], [1, -s, 0, 1]
-            params = [0.0, 0.0] + [float(v) for v in m + mrev]
-            kind = 7
-        elif augment_flow_type >= 6.:
+            return 7, [0.0, 0.0] + [float(v) for v in m + mrev]
+        if augment_flow_type >= 6.:
             c0 = (get_random(w / 4, w / 2) + w / 2, get_random(h / 4, h / 2) + h / 2)
             c0 = torch.tensor(c0)
             theta = torch.deg2rad(get_random(2, 8))
             rot = torch.tensor([[torch.cos(theta), -torch.sin(theta)], [torch.sin(theta), torch.cos(theta)]]).type(torch.float32)
             rev = torch.tensor([[torch.cos(-theta), -torch.sin(-theta)], [torch.sin(-theta), torch.cos(-theta)]]).type(torch.float32)
-            params = [float(c0[0]), float(c0[1])] + [float(v) for v in rot.reshape(-1)] + [float(v) for v in rev.reshape(-1)]
-            kind = 6
-        elif augment_flow_type >= 5.:
+            return 6, [float(c0[0]), float(c0[1])] + [float(v) for v in rot.reshape(-1)] + [float(v) for v in rev.reshape(-1)]
+        if augment_flow_type >= 5.:
             self.horizontal_flip = not self.horizontal_flip
             if self.horizontal_flip:
                 raise NotImplementedError("horizontal flip is unreachable in the reference (fresh instance per call)")
-            params, kind = None, 5
-        else:
-            raise ValueError("augment_flow_type must be >= 5 for a special flow")
+            return 5, None
+        raise ValueError("augment_flow_type must be >= 5 for a special flow")
+
+    def forward(self, size, augment_flow_type):
+        h, w = size
+        dev = self.device if self.device is not None else "cuda"
+        kind, params = self.params(size, augment_flow_type)
         with torch.cuda.device(dev):
             return ops.special_flow(kind, params, h, w, dev)
+
+
+def sample_special_params(kinds, size, generator=None):
+    """Vectorised parameter draw for a batch of special flows: the same distributions as SpecialFlow.params
+    (preprocess.py:62-99: theta = +-[8,10) deg, centre = +-[w/2,3w/4)+w/2, +-[h/2,3h/4)+h/2, shear = +-[0.2,0.35)) from
+    TWO generator calls per batch instead of up to six per sample.  The draw ORDER therefore differs from the reference's
+    per-call sequence (in-loop augmentation needs the distribution, not the sequence); augment_flow_batch(...,
+    reference_draws=True) keeps the reference's sequence."""
+    h, w = size
+    B = len(kinds)
+    sign = (torch.randint(0, 2, (B, 3), generator=generator) * 2 - 1).to(torch.float32)
+    u = torch.rand((B, 3), generator=generator)
+    cx = sign[:, 0] * (u[:, 0] * (w / 4) + (w / 2)) + w / 2
+    cy = sign[:, 1] * (u[:, 1] * (h / 4) + (h / 2)) + h / 2
+    theta = torch.deg2rad(sign[:, 2] * (u[:, 2] * 2 + 8))
+    shear = sign[:, 2] * (u[:, 2] * 0.15 + 0.2)
+    cos, sin, ncos, nsin = torch.cos(theta), torch.sin(theta), torch.cos(-theta), torch.sin(-theta)
+    cols = torch.stack((cx, cy, cos, -sin, sin, cos, ncos, -nsin, nsin, ncos, shear), 1).tolist()
+    out = []
+    for b in range(B):
+        k = int(kinds[b])
+        c = cols[b]
+        if k == 5:
+            out.append(None)
+        elif k == 6:
+            out.append(c[:10])
+        elif k == 7:
+            out.append([0.0, 0.0, 1.0, c[10], 0.0, 1.0, 1.0, -c[10], 0.0, 1.0])
+        else:
+            raise ValueError("kinds must be 5 (flip), 6 (rotate) or 7 (shear)")
+    return out
 
 
 def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device=None, augment_flow_type=None,
@@ -270,40 +304,34 @@ def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device
 
 
 @torch.no_grad()
-def augment_flow_batch(img0, depth0, img1, depth1, flow01, back_flow01, kinds, inpaint=None):
+def augment_flow_batch(img0, depth0, img1, depth1, flow01, back_flow01, kinds, inpaint=None, params=None,
+                       reference_draws=True, generator=None):
     """Batched in-loop geometric augmentation (BASELINE config 4): the geometric branch of augment_flow
     (preprocess.py:116-147) for B pairs at once, one special flow per sample (kinds[b] in {5 flip, 6 rotate, 7 shear}).
 
-    All tensors are [B,C,H,W] float32 CUDA.  The six splats of the branch run as six batched z-test/gather launch pairs
-    instead of 6*B; random parameters are drawn per sample in batch order with the reference's draw order.
+    All tensors are [B,C,H,W] float32 CUDA.  One native call (ofd_augment_pairs) issues the special-flow kernel and the six
+    batched splats back to back.  Random parameters: `params` (list of 10 floats / None per sample) if given; else drawn
+    per sample in batch order with the reference's draw order (reference_draws=True, reproduces augment_flow sample by
+    sample) or with sample_special_params (two generator calls per batch).
     Returns (set1, set2, (special_flow, back_special_flow)) with the same members as augment_flow, batched."""
     B, _, h, w = img0.shape
-    dev = img0.device
-    sf = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
-    bsf = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
-    gen = SpecialFlow(dev)
-    for b in range(B):
-        gen.horizontal_flip = gen.horizontal_shear = True  # a fresh instance per call in the reference (preprocess.py:115)
-        f, bf_ = gen((h, w), float(kinds[b]))
-        sf[b], bsf[b] = f, bf_
-    with torch.cuda.device(dev):
-        aug0_flow, _, _ = ops.splat_flow(flow01, sf, depth0, epilogue=ops.EPI_CONCAT, aux=bsf)
-        aug1_flow, _, _ = ops.splat_flow(sf, back_flow01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01)
-
-        def warp(img, depth):
-            allc, valid, collision = ops.splat_flow(torch.cat((img, depth), 1), sf, depth)
-            a_img = allc[:, 0:3].contiguous()
-            a_depth = ops.fix_warped_depth_(allc[:, 3:4].contiguous())
-            if inpaint is not None:
-                a_img = inpaint(a_img, valid, collision)
-            return a_img, a_depth
-
-        aug_img0, aug_depth0 = warp(img0, depth0)
-        aug_img1, aug_depth1 = warp(img1, depth1)
-        back_aug0, _, _ = ops.splat_flow(aug0_flow, aug0_flow, aug_depth0, epilogue=ops.EPI_BACK)
-        back_aug1, _, _ = ops.splat_flow(aug1_flow, aug1_flow, depth0, epilogue=ops.EPI_BACK)
-    return ((aug_img0, aug_depth0, aug0_flow, back_aug0, img1, depth1),
-            (img0, depth0, aug1_flow, back_aug1, aug_img1, aug_depth1), (sf, bsf))
+    if params is None:
+        if reference_draws:
+            params = []
+            for b in range(B):
+                gen = SpecialFlow(None)  # a fresh instance per call in the reference (preprocess.py:114)
+                params.append(gen.params((h, w), float(kinds[b]))[1])
+        else:
+            params = sample_special_params(kinds, (h, w), generator)
+    with torch.cuda.device(img0.device):
+        r = ops.augment_pairs(img0, depth0, img1, depth1, flow01, back_flow01, [int(k) for k in kinds], params)
+        aug_img0, aug_img1 = r["aug_img0"], r["aug_img1"]
+        if inpaint is not None:
+            aug_img0 = inpaint(aug_img0, r["valid_img0"], r["collision_img0"])
+            aug_img1 = inpaint(aug_img1, r["valid_img1"], r["collision_img1"])
+    return ((aug_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"], img1, depth1),
+            (img0, depth0, r["aug1_flow"], r["back_aug1_flow"], aug_img1, r["aug_depth1"]),
+            (r["special_flow"], r["back_special_flow"]))
 
 
 # ---- batched frame-level entry points ----------------------------------------------------------------------------

@@ -667,6 +667,34 @@ def test_cfg4_batched_augmentation_equals_per_sample(pkg):
             assert torch.equal(s2[k][b], r2[k]), (b, "set2", k)
 
 
+def test_cfg4_native_batch_with_given_params_and_masks(pkg):
+    """ofd_augment_pairs with caller-supplied parameters (the fast sampler): special_flow_batch == per-sample
+    special_flow, the six splats == the per-sample operators, and the returned image-warp masks == FW's."""
+    h, w, B = 121, 203, 5  # odd sizes
+    img, depth = _cfg1_inputs(pkg, B, h, w, seed0=80)
+    p01 = pkg.synthesis.synthesize_pairs(img, depth, torch.full((B,), 45.0, device=DEV))
+    kinds = [7, 5, 6, 6, 7]
+    torch.manual_seed(5)
+    params = pkg.synthesis.sample_special_params(kinds, (h, w))
+    r = pkg.ops.augment_pairs(img, depth, p01["img1"], p01["depth1"], p01["flow"], p01["back_flow"], kinds, params)
+    sfb, bsfb = pkg.ops.special_flow_batch(kinds, params, h, w, torch.device(DEV))
+    assert torch.equal(sfb, r["special_flow"]) and torch.equal(bsfb, r["back_special_flow"])
+    fw = pkg.m.fw.FW(DEV)
+    for b in range(B):
+        f, bf_ = pkg.ops.special_flow(kinds[b], params[b], h, w, torch.device(DEV))
+        assert torch.equal(f, sfb[b]) and torch.equal(bf_, bsfb[b])
+        for v, (im, dp) in enumerate(((img[b], depth[b]), (p01["img1"][b], p01["depth1"][b]))):
+            allc, valid, coll = fw(torch.cat((im, dp)), f, dp)
+            assert torch.equal(r[f"aug_img{v}"][b], allc[0:3])
+            assert torch.equal(r[f"aug_depth{v}"][b], pkg.synthesis.fix_warped_depth(allc[3:4].contiguous()))
+            assert torch.equal(r[f"valid_img{v}"][b], valid) and torch.equal(r[f"collision_img{v}"][b], coll)
+        o, v_, _, _, _ = oracle.fw_forward(p01["flow"][b].cpu().numpy(), f.cpu().numpy(), depth[b].cpu().numpy())
+        assert eq(r["aug0_flow"][b], (o + bf_.cpu().numpy()) * v_)
+    ws = pkg.ops.workspace.get(torch.device(DEV), B, h, w)
+    torch.cuda.synchronize()
+    assert bool((ws.view(torch.int64) == -1).all()), "workspace not re-armed by ofd_augment_pairs"
+
+
 def test_no_out_of_bounds_writes_guard_bands(pkg):
     """compute-sanitizer is closed on this GPU pool, so the kernels are checked with guard bands instead: every
     output lives inside a larger poisoned buffer and the bytes around it must be untouched (odd sizes, all paths)."""

@@ -114,3 +114,54 @@ def test_dropin_modules_expose_the_reference_names(monkeypatch):
         fw_cuda.forward_warping(torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2))
     for name in ("fw_cuda", "alt_cuda", "alt_cuda.fw", "geometry", "bilateral_filter"):
         sys.modules.pop(name, None)
+
+
+def test_sample_special_params_ranges_and_layout():
+    """The vectorised sampler draws from the reference's ranges (preprocess.py:62-99) and emits the ofd_special_flow
+    parameter layout [cx, cy, M(4), Mrev(4)]; M @ Mrev == I for rotations."""
+    import math
+
+    import torch
+
+    from opticalflowfromdepth_b200 import synthesis
+
+    h, w = 368, 496
+    kinds = [5, 6, 7] * 200
+    g = torch.Generator().manual_seed(3)
+    ps = synthesis.sample_special_params(kinds, (h, w), g)
+    assert len(ps) == len(kinds)
+    for k, p in zip(kinds, ps):
+        if k == 5:
+            assert p is None
+            continue
+        assert len(p) == 10
+        if k == 6:
+            cx, cy, m00, m01, m10, m11 = p[:6]
+            assert w / 2 <= abs(cx - w / 2) < 3 * w / 4 + 1e-3 and h / 2 <= abs(cy - h / 2) < 3 * h / 4 + 1e-3
+            th = math.degrees(math.atan2(m10, m00))
+            assert 8 - 1e-3 <= abs(th) < 10 + 1e-3
+            assert m01 == -m10 and m00 == m11
+            assert p[6:] == [m00, -m01, -m10, m11]  # the inverse rotation
+        else:
+            assert p[:3] == [0.0, 0.0, 1.0] and p[4:7] == [0.0, 1.0, 1.0] and p[8:] == [0.0, 1.0]
+            assert 0.2 <= abs(p[3]) < 0.35 + 1e-6 and p[7] == -p[3]
+    # same generator state -> same draws
+    again = synthesis.sample_special_params(kinds, (h, w), torch.Generator().manual_seed(3))
+    assert again == ps
+
+
+def test_special_flow_params_follow_the_reference_draw_order():
+    """SpecialFlow.params consumes the generator exactly like the reference's SpecialFlow.forward: rotate = 3 get_random
+    calls (centre x, centre y, angle), shear = 1, flip = 0 (preprocess.py:62-99, utils.py:96-100)."""
+    import torch
+
+    from opticalflowfromdepth_b200 import synthesis
+
+    for kind, n_calls in ((5.0, 0), (6.0, 3), (7.0, 1)):
+        torch.manual_seed(11)
+        synthesis.SpecialFlow(None).params((100, 120), kind)
+        after = torch.rand(1)
+        torch.manual_seed(11)
+        for _ in range(n_calls):
+            synthesis.get_random(1, 0)
+        assert torch.equal(after, torch.rand(1))
