@@ -491,7 +491,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--e2e-frames", type=int, default=128)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")

@@ -45,11 +45,18 @@ __device__ __forceinline__ uint32_t fw_target(int i, int j, T fx, T fy, int H, i
 // Lanes hold consecutive raster sources.  Consecutive lanes that hit the same target (clamped borders,
 // compressed regions) are merged to one key before the L2 atomic: a segmented min over runs.
 // Returns true when this lane must issue the atomic with `key`.
+#ifndef OFD_RUNMIN_MAX_HEADS
+#define OFD_RUNMIN_MAX_HEADS 32
+#endif
 __device__ __forceinline__ bool warp_run_min(uint32_t t, u64& key, int lane) {
     const unsigned full = 0xFFFFFFFFu;
     uint32_t t_prev = __shfl_up_sync(full, t, 1);
     bool head = (lane == 0) || (t != t_prev);
     unsigned heads = __ballot_sync(full, head);
+    // Experiment knob (default off): skip the pre-reduction when the warp has more than OFD_RUNMIN_MAX_HEADS distinct runs
+    // and let every lane issue its own atomic.  MEASURED slower on B200 (profiles/r1/tune_runmin.txt: FW C=6 600 -> 626 us
+    // at 16, 670 us at 8): duplicate same-address atomics cost more in L2 than the 42 shuffle/select instructions here.
+    if (OFD_RUNMIN_MAX_HEADS < 32 && __popc(heads) > OFD_RUNMIN_MAX_HEADS) return t != T_DROPPED;
     if (heads != full) {  // warp-uniform
         unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
         int run_end = above ? (__ffs(above) - 2) : 31;
@@ -63,6 +70,57 @@ __device__ __forceinline__ bool warp_run_min(uint32_t t, u64& key, int lane) {
 }
 
 __device__ __forceinline__ void key_min(u64* addr, u64 key) { atomicMin(addr, key); }
+
+// ---- the z-buffer plane as stored in the workspace -------------------------------------------------------------------
+// OFD_KEY32 = 0: one packed 64-bit key per target, one fire-and-forget REDG.MIN.64 per source.
+// OFD_KEY32 = 1: only the 32-bit source id is stored (4 B per target: half the key traffic of z-test RMW, gather read and
+//                re-arm); the ordering key (ordered depth, id) of the current holder is re-derived from the read-only
+//                depth plane, and the minimum is taken by a compare-and-swap loop.  Same winner: the loop only ever
+//                replaces a holder by a source with a strictly smaller (depth, id) key, so the final holder is the
+//                minimum, whatever the order the SMs run in.
+// MEASURED (B200, profiles/r1/tune_key32.txt; 128 x 480x640): bit-identical (all GPU parity tests pass with either), but
+// the returning CAS costs more than the 16 B/px it saves: FW C=6 752 us vs 600 us, reproject pair 1071 vs 732 us.  The
+// packed 64-bit key with a fire-and-forget RED stays the default; -DOFD_KEY32=1 rebuilds the experiment.
+#ifndef OFD_KEY32
+#define OFD_KEY32 0
+#endif
+#if OFD_KEY32
+typedef uint32_t zkey_t;
+constexpr zkey_t ZKEY_EMPTY = 0xFFFFFFFFu;  // no source reached this target (the 0xFF workspace pattern)
+constexpr zkey_t ZKEY_NOWIN = 0xFFFFFFFEu;  // reached only by sources with !(depth < 1000)
+
+__device__ __forceinline__ void zkey_min(zkey_t* __restrict__ kp, const float* __restrict__ dp, uint32_t t, u64 key) {
+    const uint32_t src = (uint32_t)key;
+    if ((uint32_t)(key >> 32) >= HI_NOWIN) {
+        atomicCAS(kp + t, ZKEY_EMPTY, ZKEY_NOWIN);  // marks "hit"; any real source overrides it
+        return;
+    }
+    zkey_t old = atomicCAS(kp + t, ZKEY_EMPTY, src);
+    while (old != ZKEY_EMPTY) {
+        if (old != ZKEY_NOWIN && make_key(depth_hi(__ldg(dp + old)), old) < key) break;  // the holder wins
+        const zkey_t seen = atomicCAS(kp + t, old, src);
+        if (seen == old) break;
+        old = seen;
+    }
+}
+__device__ __forceinline__ bool zkey_hit(zkey_t k) { return k != ZKEY_EMPTY; }
+__device__ __forceinline__ bool zkey_win(zkey_t k) { return k < ZKEY_NOWIN; }
+__device__ __forceinline__ uint32_t zkey_src(zkey_t k) { return k; }
+// ordered depth of the winner (tie census)
+__device__ __forceinline__ uint32_t zkey_winner_hi(zkey_t k, const float* __restrict__ dp) {
+    return zkey_win(k) ? depth_hi(__ldg(dp + k)) : HI_NOWIN;
+}
+#else
+typedef u64 zkey_t;
+constexpr zkey_t ZKEY_EMPTY = KEY_UNTOUCHED;
+__device__ __forceinline__ void zkey_min(zkey_t* __restrict__ kp, const float* __restrict__, uint32_t t, u64 key) {
+    atomicMin(kp + t, key);
+}
+__device__ __forceinline__ bool zkey_hit(zkey_t k) { return k != KEY_UNTOUCHED; }
+__device__ __forceinline__ bool zkey_win(zkey_t k) { return (uint32_t)(k >> 32) < HI_NOWIN; }
+__device__ __forceinline__ uint32_t zkey_src(zkey_t k) { return (uint32_t)k; }
+__device__ __forceinline__ uint32_t zkey_winner_hi(zkey_t k, const float* __restrict__) { return (uint32_t)(k >> 32); }
+#endif
 
 // utils.fix_warped_depth (utils.py:123-126)
 __device__ __forceinline__ float fix_depth(float d) {
