@@ -1,0 +1,291 @@
+"""Drop-in for the driver side of the reference's preprocess.py (the caller of the hot path and the
+`.npz` format on its other side): `PreprocessPlusAugment.forward(datas, output_dir, is_stereo)` writes the same 121 files
+per frame — `group.npz` (44 channels, preprocess.py:437-447) and `{group}_{k}_{1,2}.npz` for the 12 augmentations of each
+of the 5 pairs (preprocess.py:453-476) — with the same keys, shapes and values.
+
+What differs from the reference is how it gets there:
+  * the group's 7 splats run as the fused kernels of `synthesis.synthesize_group` (13 launches);
+  * the 45 geometric augmentations of a frame run as FIVE `ofd_augment_pairs` calls (one per pair, batch of 9), their
+    random parameters pre-drawn on the host in the reference's exact order (utils.py:96-100), so the files are the same;
+  * results cross PCIe once per batch into host memory and are compressed / written by a pool of writer threads
+    (zlib releases the GIL) while the GPU goes on with the next frame;
+  * `utils.inpaint` (OpenCV Telea on the CPU) is a pluggable hook: "reference" reproduces it, None skips it.
+Float64 dataset inputs (cv2.imread(...).astype(float), utils.py:44-72): the 0->1 pair is evaluated from the float64 depth
+exactly as the reference does (float64 disparity, float64 target); the other pairs and the flow composition take the
+float32 rounding of depth0 / flow01 (the reference keeps float64 there; difference <= 1.2e-7 relative).
+Saved arrays are float32 unless save_dtype says otherwise.
+"""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+import time
+from argparse import ArgumentParser
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import geometry, ops, sweep, synthesis
+
+AUGMENT_TYPES = [0, 5, 6, 7, 1, 5, 6, 7, 2, 5, 6, 7]  # preprocess.py:455
+GROUP_CHANNELS = ("img0", "depth0", "img1", "depth1", "img2", "depth2", "img3", "depth3", "img2_prime", "depth2_prime",
+                  "img3_prime", "depth3_prime", "flow01", "back_flow01", "flow12", "back_flow12", "flow02",
+                  "back_flow02_prime", "flow03", "back_flow03", "flow13", "back_flow13_prime")  # preprocess.py:437-441
+# the 5 pairs of a group (preprocess.py:427-432): (imgA, depthA, imgB, depthB, flowAB, back_flowAB)
+GROUP_PAIRS = (("img0", "depth0", "img1", "depth1", "flow01", "back_flow01"),
+               ("img1", "depth1", "img2", "depth2", "flow12", "back_flow12"),
+               ("img0", "depth0", "img2_prime", "depth2_prime", "flow02", "back_flow02_prime"),
+               ("img0", "depth0", "img3", "depth3", "flow03", "back_flow03"),
+               ("img1", "depth1", "img3_prime", "depth3_prime", "flow13", "back_flow13_prime"))
+
+
+class NpzWriter:
+    """Asynchronous `.npz` writer: `submit(path, **arrays)` returns at once, a pool of threads compresses and writes.
+    `close()` waits for everything and re-raises the first error."""
+
+    def __init__(self, threads: int = 4, compress: bool = True, max_pending: int = 256):
+        self._q: "queue.Queue" = queue.Queue(max_pending)
+        self._save = np.savez_compressed if compress else np.savez
+        self._err: List[BaseException] = []
+        self.files = 0
+        self.bytes = 0
+        self._lock = threading.Lock()
+        self._threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(1, threads))]
+        for t in self._threads:
+            t.start()
+
+    def _run(self):
+        while True:
+            job = self._q.get()
+            if job is None:
+                self._q.task_done()
+                return
+            path, arrays = job
+            try:
+                self._save(path, **arrays)
+                with self._lock:
+                    self.files += 1
+                    self.bytes += sum(int(np.asarray(a).nbytes) for a in arrays.values())
+            except BaseException as e:  # noqa: BLE001 - reported by close()
+                self._err.append(e)
+            finally:
+                self._q.task_done()
+
+    def submit(self, path: str, **arrays):
+        if self._err:
+            raise self._err[0]
+        self._q.put((path, arrays))
+
+    def drain(self):
+        self._q.join()
+        if self._err:
+            raise self._err[0]
+
+    def close(self):
+        self.drain()
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()
+
+
+def photometric_draws(augment_flow_type: float):
+    """Host random draws of the photometric branch of augment_flow in the reference's order (preprocess.py:150-163)."""
+    if augment_flow_type >= 2.:
+        return None
+    if augment_flow_type >= 1.:
+        channel = int(synthesis.get_random(3, 0, False))
+        shift = synthesis.get_random(10, 15)
+        return channel, shift
+    return synthesis.get_random(1, 0, False)
+
+
+def photometric_apply(img: torch.Tensor, augment_flow_type: float, draws) -> torch.Tensor:
+    """augment_img_func of preprocess.py:150-163 on img[...,3,H,W]: 0 brightness scale, 1 one-channel shift, 2 grayscale."""
+    if augment_flow_type >= 2.:
+        # (img.permute(1,2,0) @ gray).permute(2,0,1) with gray[k, :] = (0.2989, 0.5870, 0.1140)[k]: every output channel is the
+        # same K=3 dot product, evaluated here as an ascending-k chain (the reference's order is a BLAS detail)
+        r, g, b = img.select(-3, 0), img.select(-3, 1), img.select(-3, 2)
+        gray = (r * 0.2989 + g * 0.5870) + b * 0.1140
+        return gray.unsqueeze(-3).expand_as(img).contiguous()
+    if augment_flow_type >= 1.:
+        channel, shift = draws
+        out = img.clone()
+        out.select(-3, channel).add_(shift.to(img.device))
+        return out
+    return img * draws.to(img.device)
+
+
+class PreprocessPlusAugment(nn.Module):
+    """preprocess.PreprocessPlusAugment (preprocess.py:328-505): same constructor / forward signature and output files."""
+
+    def __init__(self, device, inpaint="reference", writer: Optional[NpzWriter] = None, compress: bool = True,
+                 save_dtype=np.float32, quiet: bool = False):
+        super().__init__()
+        self.device = torch.device(device)
+        self.inpaint: Optional[Callable] = synthesis.inpaint if inpaint == "reference" else inpaint
+        self._own_writer = writer is None
+        self.writer = writer if writer is not None else NpzWriter(compress=compress)
+        self.save_dtype = save_dtype
+        self.quiet = quiet
+        self.counters = None
+
+    # ---- the group (preprocess.py:341-447) -------------------------------------------------------------------------
+    def synthesize(self, datas, is_stereo=False) -> Dict[str, torch.Tensor]:
+        dev = self.device
+        if not is_stereo:
+            img0, depth = datas
+        else:
+            img0, _img1_unused, disp0 = datas  # the real right view is ignored and overwritten (preprocess.py:352,361)
+            depth = synthesis.Convert.disparity_to_depth(disp0)
+        img0 = img0.to(dev).float().contiguous()[None]
+        depth = depth.to(dev)
+        if depth.dtype not in (torch.float32, torch.float64):
+            depth = depth.float()
+        with torch.cuda.device(dev):
+            depth0 = ops.normalize_depth(depth.contiguous()[None])
+        h, w = img0.shape[-2:]
+        sBf = torch.as_tensor(synthesis.Convert.disparity_scale(), dtype=torch.float32).reshape(1).to(dev)  # :356
+        T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)                      # :372 -> :277
+        K, inv_K = synthesis.Plausible.K((h, w))
+        cam = geometry.camera_constants(K, inv_K, T1).to(dev)
+        if self.counters is None:
+            self.counters = ops.new_counters(dev)
+        res = synthesis.synthesize_group(img0, depth0, sBf, cam, inpaint=self.inpaint, counters=self.counters)
+        return res
+
+    # ---- the 60 augmentations (preprocess.py:453-476) ------------------------------------------------------------------
+    def augment(self, group: Dict[str, torch.Tensor]):
+        """Yields (group_idx, augment_idx, augment_flow_type, data1[8,H,W], data2[8,H,W]) in the reference's file order."""
+        h, w = group["img0"].shape[-2:]
+        # host draws first, in the reference's order: pair by pair, type by type
+        plan = []
+        for _ in GROUP_PAIRS:
+            row = []
+            for t in AUGMENT_TYPES:
+                if t >= 5:
+                    row.append(synthesis.SpecialFlow(None).params((h, w), float(t))[1])  # fresh instance per call (:114)
+                else:
+                    row.append(photometric_draws(float(t)))
+            plan.append(row)
+        geo = [k for k, t in enumerate(AUGMENT_TYPES) if t >= 5]
+        for gi, names in enumerate(GROUP_PAIRS):
+            imgA, depA, imgB, depB, fAB, bAB = (group[n].float() for n in names)
+            n = len(geo)
+            rep = lambda x: x.expand(n, -1, -1, -1).contiguous()  # noqa: E731
+            with torch.cuda.device(self.device):
+                r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
+                                      [AUGMENT_TYPES[k] for k in geo], [plan[gi][k] for k in geo])
+                a_img0, a_img1 = r["aug_img0"], r["aug_img1"]
+                if self.inpaint is not None:
+                    a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
+                    a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
+                geo1 = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)   # set1[0:4]
+                geo2 = torch.cat((r["aug1_flow"], r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)   # set2[2:6]
+            for k, t in enumerate(AUGMENT_TYPES):
+                if t >= 5:
+                    j = geo.index(k)
+                    yield gi, k, t, geo1[j], geo2[j]
+                else:
+                    pa = photometric_apply(imgA[0], float(t), plan[gi][k])
+                    pb = photometric_apply(imgB[0], float(t), plan[gi][k])
+                    yield (gi, k, t, torch.cat((pa, depA[0], fAB[0], bAB[0]), 0), torch.cat((fAB[0], bAB[0], pb, depB[0]), 0))
+
+    def forward(self, datas, output_dir, is_stereo=False, n_continuous=4):
+        t0 = time.time()
+        group = self.synthesize(datas, is_stereo)
+        os.makedirs(output_dir, exist_ok=True)
+        dt = self.save_dtype
+        stack = torch.cat([group[n][0].float() for n in GROUP_CHANNELS], 0)
+        self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=stack.cpu().numpy().astype(dt, copy=False))
+        t1 = time.time()
+        for gi, k, t, d1, d2 in self.augment(group):
+            both = torch.stack((d1, d2)).cpu().numpy().astype(dt, copy=False)
+            self.writer.submit(f"{output_dir}/{gi}_{k}_1.npz", img_depth_flow=both[0], augment_flow_type=t)
+            self.writer.submit(f"{output_dir}/{gi}_{k}_2.npz", img_depth_flow=both[1], augment_flow_type=t)
+        if self._own_writer:
+            self.writer.drain()
+        if not self.quiet:
+            print(f"{output_dir = }: preprocessing time = {t1 - t0:.3f}, augmenting time = {time.time() - t1:.3f}")
+
+    def close(self):
+        if self._own_writer:
+            self.writer.close()
+
+
+def read_args(argv=None):
+    """preprocess.read_args (preprocess.py:507-517) plus the knobs this driver adds."""
+    parser = ArgumentParser()
+    parser.add_argument('--dataset')
+    parser.add_argument('--gpu', default=0, type=int)
+    parser.add_argument('--split', default=1, type=int)
+    parser.add_argument('--split_id', default=0, type=int)
+    parser.add_argument('--specific_epoch_idx', default=-1, type=int)
+    parser.add_argument('--no_inpaint', action='store_true', help='skip utils.inpaint (OpenCV Telea on the CPU)')
+    parser.add_argument('--writer_threads', default=8, type=int)
+    parser.add_argument('--output_root', default='datasets/AugmentedDatasets')
+    parser.add_argument('--epochs', default=2, type=int, help='the reference always runs 2 (preprocess.py:552)')
+    return parser.parse_args(argv)
+
+
+def run(dataset, output_dir: str, is_stereo: bool, args, epochs=2) -> Dict[str, int]:
+    """The reference's driver loop (preprocess.py:540-561): contiguous shard [start, end) of the dataset, two epochs,
+    per-image reseeding (12345 + img_idx + epoch_idx * len(dataset))."""
+    device = f"cuda:{args.gpu}"
+    writer = NpzWriter(threads=args.writer_threads)
+    ppa = PreprocessPlusAugment(device=device, inpaint=None if args.no_inpaint else "reference", writer=writer)
+    rng = sweep.shard_range(len(dataset), args.split, args.split_id)
+    epochs = getattr(args, "epochs", epochs)
+    for epoch_idx in range(epochs):
+        for img_idx in rng:
+            synthesis.set_seed(sweep.frame_seed(img_idx, epoch_idx, len(dataset)))
+            datas = dataset[img_idx]
+            ppa(datas, f"{output_dir}/{img_idx + epoch_idx * len(dataset)}", is_stereo)
+    writer.close()
+    return sweep.reduce_counters(ppa.counters) if ppa.counters is not None else {}
+
+
+class SyntheticDataset:
+    """`--dataset synthetic:N[:HxW]`: N DIML-shaped synthetic RGB-D frames (BASELINE config 5), float64 depth like the
+    reference's loaders deliver."""
+
+    def __init__(self, n: int, h: int = 480, w: int = 640):
+        self.n, self.h, self.w = n, h, w
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        from . import synthetic
+
+        img, raw = synthetic.diml_frame(idx, self.h, self.w)
+        return torch.from_numpy(img), torch.from_numpy(raw.astype(np.float64))
+
+
+def main(argv=None):
+    """`python -m opticalflowfromdepth_b200.preprocess --dataset DIML|ReDWeb|synthetic:N --gpu 0 --split S --split_id K`
+    (README.md:53 of the reference).  DIML / ReDWeb use the reference's own dataset classes (its `dataloader.py` must be
+    importable, i.e. run from / with PYTHONPATH at the reference checkout)."""
+    args = read_args(argv)
+    if args.dataset and args.dataset.startswith("synthetic"):
+        parts = args.dataset.split(":")
+        n = int(parts[1]) if len(parts) > 1 else 8
+        h, w = (int(v) for v in parts[2].split("x")) if len(parts) > 2 else (480, 640)
+        dataset, is_stereo, name = SyntheticDataset(n, h, w), False, "synthetic"
+    elif args.dataset in ("DIML", "ReDWeb"):
+        import dataloader  # the reference's module (datasets + file lists)
+
+        dataset = dataloader.DIML() if args.dataset == "DIML" else dataloader.ReDWeb()
+        is_stereo, name = args.dataset == "DIML", args.dataset
+    else:
+        raise SystemExit(f"unknown --dataset {args.dataset!r}")
+    t0 = time.time()
+    totals = run(dataset, f"{args.output_root}/{name}", is_stereo, args)
+    print(f"done in {time.time() - t0:.1f} s: {totals}")
+
+
+if __name__ == "__main__":
+    main()

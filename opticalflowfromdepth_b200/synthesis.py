@@ -353,12 +353,16 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
     (1 fused stereo pair, 6 x (z-test + gather)).
 
     img0[B,3,H,W], depth0[B,1,H,W] f32 (normalised), sBf[B], cam1/cam0 built from the same pose: cam[B,21] float32.
-    Returns a dict of tensors named as in preprocess.py."""
+    depth0 may be float64 (dataset path, utils.py:44-72): pair 0->1 is then evaluated from the float64 depth as the
+    reference does (float64 disparity and target); everything after it uses depth0's float32 rounding.
+    Returns a dict of tensors named as in preprocess.py (all float32)."""
     dev = img0.device
     fill = (lambda im, v, c: im) if inpaint is None else inpaint
     with torch.cuda.device(dev):
         # pair 0->1: virtual stereo (preprocess.py:356-366)
         img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, True, counters)
+        if depth0.dtype != torch.float32:
+            depth0 = depth0.float()
         img1 = fill(img1, valid1, coll1)
         # pair 1->2: random camera motion from view 1 (preprocess.py:372-382); flow computed inside the z-test
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)

@@ -343,6 +343,45 @@ def concat_back_cases(pp):
     return out
 
 
+def preprocess_case(pp, ref_utils):
+    """The reference's WHOLE PreprocessPlusAugment.forward (preprocess.py:341-476): group.npz and the 5 x 12 x 2 augmented
+    files, inpaint = identity, float32 inputs, small frame.  Every np.savez_compressed call is captured."""
+    rng = np.random.default_rng(77)
+    h, w = 30, 44
+    img0 = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+    raw = diml_depth(rng, h, w).astype(np.float32)
+    files = {}
+
+    def fake_savez(path, **kw):
+        files[Path(path).name] = {k: np.asarray(v) for k, v in kw.items()}
+
+    ppa = pp.PreprocessPlusAugment(device="cpu")
+    ref_utils.set_seed(12345 + 3)
+    real = np.savez_compressed
+    np.savez_compressed = fake_savez
+    pp.os.makedirs = lambda *a, **k: None
+    try:
+        with redirect_stdout(io.StringIO()):
+            try:
+                ppa((torch.from_numpy(img0), torch.from_numpy(raw.copy())[None]), "/tmp/ofd_golden/7", is_stereo=False)
+            except (NameError, UnboundLocalError) as e:  # the `del` block after the last file is written (Appendix B)
+                files["__tail_error__"] = {"msg": np.array(str(e))}
+    finally:
+        np.savez_compressed = real
+    assert "group.npz" in files and len([k for k in files if k.endswith(".npz")]) == 121, sorted(files)[:5]
+    out = dict(img0=img0, raw_depth=raw)
+    for name, kw in files.items():
+        if not name.endswith(".npz"):
+            continue
+        stem = name[:-4]
+        arr = kw["img_depth_flow"]
+        assert arr.dtype == np.float32, (name, arr.dtype)
+        out[f"{stem}__data"] = arr
+        if "augment_flow_type" in kw:
+            out[f"{stem}__type"] = np.asarray(kw["augment_flow_type"])
+    return out
+
+
 def main():
     torch.set_num_threads(1)
     pp, ref_utils, ref_geo, ref_bil, RefFW = install_reference()
@@ -355,8 +394,12 @@ def main():
         "concat_back_cases": lambda: concat_back_cases(pp),
         "pipeline_case": lambda: pipeline_case(pp, ref_utils),
         "inpaint_case": lambda: inpaint_case(pp, ref_utils),
+        "preprocess_case": lambda: preprocess_case(pp, ref_utils),
     }
+    only = set(sys.argv[1:])
     for name, job in jobs.items():
+        if only and name not in only:
+            continue
         data = job()
         np.savez_compressed(HERE / f"{name}.npz", **data)
         print(f"{name}: {len(data)} arrays, {(HERE / (name + '.npz')).stat().st_size / 1024:.0f} KiB")

@@ -695,6 +695,77 @@ def test_cfg4_native_batch_with_given_params_and_masks(pkg):
     assert bool((ws.view(torch.int64) == -1).all()), "workspace not re-armed by ofd_augment_pairs"
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# the driver around the path - PreprocessPlusAugment writes the reference's 121 files
+# ---------------------------------------------------------------------------------------------------------------
+def test_preprocess_plus_augment_writes_the_reference_files(pkg, golden, tmp_path):
+    """preprocess.PreprocessPlusAugment.forward vs the reference's own forward run on the CPU (golden preprocess_case,
+    inpaint = identity): same 121 files, keys, shapes, dtypes; pair 0 (exact arithmetic end to end) bit-exact in all 24
+    of its files bar the grayscale one (K=3 dot product, 1e-5 relative); files that depend on the 6-DoF flow within the
+    path's tolerance (a flow difference of 1e-5 px can move a truncated target, so a small fraction of pixels may differ)."""
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    g = golden("preprocess_case")
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    pkg.synthesis.set_seed(12345 + 3)
+    out = tmp_path / "7"
+    ppa((torch.from_numpy(g["img0"]), torch.from_numpy(g["raw_depth"].copy())[None]), str(out), is_stereo=False)
+    ppa.close()
+    want_files = sorted(k[:-6] for k in g if k.endswith("__data"))
+    got_files = sorted(p.name[:-4] for p in out.glob("*.npz"))
+    assert got_files == want_files and len(got_files) == 121
+    worst = 0.0
+    for stem in want_files:
+        z = np.load(out / f"{stem}.npz")
+        want = g[f"{stem}__data"]
+        got = z["img_depth_flow"]
+        assert got.shape == want.shape and got.dtype == want.dtype == np.float32, stem
+        if stem == "group":
+            assert sorted(z.files) == ["img_depth_flow"]
+            assert np.array_equal(got[0:8], want[0:8]) and np.array_equal(got[24:28], want[24:28])  # pair 0->1
+            frac = float((np.abs(got - want) > 1e-3).mean())
+        else:
+            assert sorted(z.files) == ["augment_flow_type", "img_depth_flow"]
+            assert int(z["augment_flow_type"]) == int(g[f"{stem}__type"]), stem
+            gi, k, _ = (int(v) for v in stem.split("_"))
+            t = pp.AUGMENT_TYPES[k]
+            if gi == 0 and t != 2:
+                assert np.array_equal(got, want), stem
+                frac = 0.0
+            elif gi == 0:
+                assert np.allclose(got, want, rtol=1e-5, atol=1e-4), stem
+                frac = 0.0
+            else:
+                frac = float((np.abs(got - want) > 1e-3).mean())
+        worst = max(worst, frac)
+        assert frac <= 0.03, f"{stem}: {frac:.4f} of the values differ"
+    print(f"[preprocess] 121 files, worst differing fraction {worst:.2e}")
+
+
+def test_preprocess_float64_dataset_depth_and_stereo_input(pkg, tmp_path):
+    """Dataset-shaped inputs: float64 depth (cv2.imread(...).astype(float)) and the stereo triple (img0, img1, disp0) of
+    DIML (preprocess.py:350-355).  Pair 0->1 equals the oracle fed with the float64 depth."""
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    h, w = 36, 52
+    img, raw = pkg.synthetic.diml_frame(5, h, w)
+    disp = (np.random.default_rng(1).integers(1, 255, (1, h, w)).astype(float)) * 63 / 255  # utils.get_disparity
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    pkg.synthesis.set_seed(99)
+    grp = ppa.synthesize((torch.from_numpy(img), torch.from_numpy(img), torch.from_numpy(disp)), is_stereo=True)
+    d64 = oflow.normalize_depth(50.0 / (torch.from_numpy(disp) + 0.005)).numpy()
+    pkg.synthesis.set_seed(99)
+    sBf = torch.as_tensor(pkg.synthesis.Convert.disparity_scale(), dtype=torch.float32)
+    flow64 = oflow.disparity_flow(torch.from_numpy(d64), sBf).numpy()  # float64 flow, float64 target (fw.py:31)
+    obj = np.concatenate([img, d64, flow64 * -1.0]).astype(np.float32)
+    o, v, c, _, _ = oracle.fw_forward(obj, flow64, d64.astype(np.float32))
+    assert eq(grp["valid1"][0], v) and eq(grp["img1"][0], o[0:3] * v) and eq(grp["back_flow01"][0], o[4:6] * v)
+    assert eq(grp["depth1"][0], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v)).numpy())
+    assert eq(grp["flow01"][0], flow64.astype(np.float32))
+    assert grp["depth0"].dtype == torch.float32 and eq(grp["depth0"][0], d64.astype(np.float32))
+    ppa.close()
+
+
 def test_no_out_of_bounds_writes_guard_bands(pkg):
     """compute-sanitizer is closed on this GPU pool, so the kernels are checked with guard bands instead: every
     output lives inside a larger poisoned buffer and the bytes around it must be untouched (odd sizes, all paths)."""
