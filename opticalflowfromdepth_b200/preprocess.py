@@ -158,10 +158,36 @@ class PreprocessPlusAugment(nn.Module):
         return res
 
     # ---- the 60 augmentations (preprocess.py:453-476) ------------------------------------------------------------------
-    def augment(self, group: Dict[str, torch.Tensor]):
-        """Yields (group_idx, augment_idx, augment_flow_type, data1[8,H,W], data2[8,H,W]) in the reference's file order."""
-        h, w = group["img0"].shape[-2:]
-        # host draws first, in the reference's order: pair by pair, type by type
+    def augment_pair_block(self, group: Dict[str, torch.Tensor], gi: int, draws) -> torch.Tensor:
+        """All 12 augmentations of group pair `gi` as ONE device tensor [12, 2, 8, H, W]: [k, 0] is file {gi}_{k}_1
+        (set1[0:4] = aug_img0, aug_depth0, aug0_flow, back_aug0_flow) and [k, 1] is file {gi}_{k}_2 (set2[2:6] = aug1_flow,
+        back_aug1_flow, aug_img1, aug_depth1), preprocess.py:459-476.  `draws[k]` are the pre-drawn host parameters."""
+        imgA, depA, imgB, depB, fAB, bAB = (group[n].float() for n in GROUP_PAIRS[gi])
+        h, w = imgA.shape[-2:]
+        geo = [k for k, t in enumerate(AUGMENT_TYPES) if t >= 5]
+        n = len(geo)
+        rep = lambda x: x.expand(n, -1, -1, -1).contiguous()  # noqa: E731
+        block = torch.empty((len(AUGMENT_TYPES), 2, 8, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
+                                  [AUGMENT_TYPES[k] for k in geo], [draws[k] for k in geo])
+            a_img0, a_img1 = r["aug_img0"], r["aug_img1"]
+            if self.inpaint is not None:
+                a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
+                a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
+            block[geo, 0] = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)
+            block[geo, 1] = torch.cat((r["aug1_flow"], r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)
+            for k, t in enumerate(AUGMENT_TYPES):
+                if t < 5:
+                    pa = photometric_apply(imgA[0], float(t), draws[k])
+                    pb = photometric_apply(imgB[0], float(t), draws[k])
+                    block[k, 0] = torch.cat((pa, depA[0], fAB[0], bAB[0]), 0)
+                    block[k, 1] = torch.cat((fAB[0], bAB[0], pb, depB[0]), 0)
+        return block
+
+    @staticmethod
+    def draw_augmentations(h: int, w: int):
+        """Host draws of a frame's 60 augmentations in the reference's order: pair by pair, type by type (:454-455)."""
         plan = []
         for _ in GROUP_PAIRS:
             row = []
@@ -171,41 +197,31 @@ class PreprocessPlusAugment(nn.Module):
                 else:
                     row.append(photometric_draws(float(t)))
             plan.append(row)
-        geo = [k for k, t in enumerate(AUGMENT_TYPES) if t >= 5]
-        for gi, names in enumerate(GROUP_PAIRS):
-            imgA, depA, imgB, depB, fAB, bAB = (group[n].float() for n in names)
-            n = len(geo)
-            rep = lambda x: x.expand(n, -1, -1, -1).contiguous()  # noqa: E731
-            with torch.cuda.device(self.device):
-                r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
-                                      [AUGMENT_TYPES[k] for k in geo], [plan[gi][k] for k in geo])
-                a_img0, a_img1 = r["aug_img0"], r["aug_img1"]
-                if self.inpaint is not None:
-                    a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
-                    a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
-                geo1 = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)   # set1[0:4]
-                geo2 = torch.cat((r["aug1_flow"], r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)   # set2[2:6]
-            for k, t in enumerate(AUGMENT_TYPES):
-                if t >= 5:
-                    j = geo.index(k)
-                    yield gi, k, t, geo1[j], geo2[j]
-                else:
-                    pa = photometric_apply(imgA[0], float(t), plan[gi][k])
-                    pb = photometric_apply(imgB[0], float(t), plan[gi][k])
-                    yield (gi, k, t, torch.cat((pa, depA[0], fAB[0], bAB[0]), 0), torch.cat((fAB[0], bAB[0], pb, depB[0]), 0))
+        return plan
+
+    def _to_host(self, t: torch.Tensor) -> np.ndarray:
+        """One D2H copy into page-locked memory (torch's caching host allocator recycles the block once the writer
+        threads drop their views)."""
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy().astype(self.save_dtype, copy=False)
 
     def forward(self, datas, output_dir, is_stereo=False, n_continuous=4):
         t0 = time.time()
         group = self.synthesize(datas, is_stereo)
         os.makedirs(output_dir, exist_ok=True)
-        dt = self.save_dtype
-        stack = torch.cat([group[n][0].float() for n in GROUP_CHANNELS], 0)
-        self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=stack.cpu().numpy().astype(dt, copy=False))
-        t1 = time.time()
-        for gi, k, t, d1, d2 in self.augment(group):
-            both = torch.stack((d1, d2)).cpu().numpy().astype(dt, copy=False)
-            self.writer.submit(f"{output_dir}/{gi}_{k}_1.npz", img_depth_flow=both[0], augment_flow_type=t)
-            self.writer.submit(f"{output_dir}/{gi}_{k}_2.npz", img_depth_flow=both[1], augment_flow_type=t)
+        with torch.cuda.device(self.device):
+            stack = torch.cat([group[n][0].float() for n in GROUP_CHANNELS], 0)
+            self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=self._to_host(stack))
+            t1 = time.time()
+            h, w = stack.shape[-2:]
+            plan = self.draw_augmentations(h, w)
+            for gi in range(len(GROUP_PAIRS)):
+                block = self._to_host(self.augment_pair_block(group, gi, plan[gi]))
+                for k, t in enumerate(AUGMENT_TYPES):
+                    self.writer.submit(f"{output_dir}/{gi}_{k}_1.npz", img_depth_flow=block[k, 0], augment_flow_type=t)
+                    self.writer.submit(f"{output_dir}/{gi}_{k}_2.npz", img_depth_flow=block[k, 1], augment_flow_type=t)
         if self._own_writer:
             self.writer.drain()
         if not self.quiet:
