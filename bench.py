@@ -320,14 +320,42 @@ def run_ours(args):
             except Exception as e:  # secondary: never break the headline
                 extras["cfg3_sixdof_1080p_b32"] = {"error": repr(e)}
         if "bilateral" not in skip:
-            # (b1) cfg2 stage: 5-iteration gated-median bilateral at 480x640 (reference numpy: 5.2 s/frame)
+            # (b1) cfg2: ReDWeb-shaped ragged batch (16 frames, 0.3-2 MP): normalize_depth -> 5-iteration gated-median
+            #      bilateral (one launch per iteration over the whole ragged batch) -> virtual-disparity pair per frame
             try:
                 from opticalflowfromdepth_b200 import bilateral_filter as bfm
+                from opticalflowfromdepth_b200 import synthetic
+                sizes = synthetic.redweb_sizes(16, seed=1)
+                r_img, r_dep = [], []
+                for k, (hh, ww) in enumerate(sizes):
+                    im, dp = synthetic.redweb_frame(k, hh, ww)
+                    r_img.append(torch.from_numpy(im).to(dev)[None])
+                    r_dep.append(torch.from_numpy(dp).to(dev)[None])
+                r_s = [torch.tensor([47.0], device=dev) for _ in sizes]
+                mpx = sum(hh * ww for hh, ww in sizes) / 1e6
+
+                def cfg2_filter():
+                    nd = [ops.normalize_depth(d)[0, 0] for d in r_dep]
+                    return bfm.sparse_bilateral_filtering_batch(nd, [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5)
+
+                def cfg2_step():
+                    fd = cfg2_filter()
+                    for im, d, sv in zip(r_img, fd, r_s):
+                        ops.disparity_pair(im, d[None, None], sv)
+
+                t_f = timed(cfg2_filter, 10, 3, sync, barrier) / 10
+                t_all = timed(cfg2_step, 10, 3, sync, barrier) / 10
                 d2 = depth[0, 0].contiguous()
                 tbil = timed(lambda: bfm.sparse_bilateral_filtering(d2, None, [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5), 10, 3, sync, barrier) / 10
+                extras["cfg2_redweb_ragged_b16"] = {"frames_per_s": len(sizes) / t_all, "ms_per_step": 1e3 * t_all, "frames_per_step": len(sizes),
+                                                    "megapixels_per_step": mpx, "Mpx_per_s": mpx / t_all,
+                                                    "bilateral_5iter_ms": 1e3 * t_f, "bilateral_Mpx_per_s_per_iter": 5 * mpx / t_f,
+                                                    "launches_per_step": 5 + 4 * len(sizes),
+                                                    "what": "16 mixed-resolution frames (0.3-2 MP): normalize_depth (3 launches/frame), 5 bilateral iterations "
+                                                            "(ofd_bilateral_iter_batch: 1 launch/iteration for the whole ragged batch), fused disparity pair (1 launch/frame)"}
                 extras["cfg2_bilateral_480x640_5iter"] = {"ms_per_frame": 1e3 * tbil, "frames_per_s": 1.0 / tbil, "launches": 5}
             except Exception as e:
-                extras["cfg2_bilateral_480x640_5iter"] = {"error": repr(e)}
+                extras["cfg2_redweb_ragged_b16"] = {"error": repr(e)}
         if "augment" not in skip:
             # (b3) cfg4: in-loop geometric augmentation of one image of the pair at 368x496, batch 8 (6 splats per sample)
             try:

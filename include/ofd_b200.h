@@ -234,6 +234,16 @@ int ofd_bilateral_iter(const void* depth_in, const void* depth_orig, int dtype, 
                        double threshold, void* depth_out, ofd_stream_t stream);
 
 /*
+ * ofd_bilateral_iter_batch — the same iteration over a RAGGED batch (BASELINE config 2: mixed-resolution frames, each
+ * filtered independently exactly as ofd_bilateral_iter would): image i is H_host[i] x W_host[i], stored densely at element
+ * offset offset_host[i] of depth_in / depth_orig / depth_out (the three buffers share one layout).  One launch per 64
+ * images; H_host / W_host / offset_host are HOST arrays.
+ */
+int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int dtype, int n_images, const int* H_host,
+                             const int* W_host, const size_t* offset_host, int window, double threshold,
+                             void* depth_out, ofd_stream_t stream);
+
+/*
  * Host-buffer front end of the flow-pair path (what a reference-side caller holding numpy arrays or pinned CPU
  * tensors binds; the reference crosses host<->device around every FW call, preprocess.py:350-366,437-447).
  * A pipeline owns three device staging slots with one stream each: chunk k does host->device copies, the pair

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 
-__all__ = ["sparse_bilateral_filtering"]
+__all__ = ["sparse_bilateral_filtering", "sparse_bilateral_filtering_batch"]
 
 
 def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4.0, depth_threshold=0.04, HR=False,
@@ -39,3 +39,30 @@ def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4
     if num_iter == 0:
         cur = d0.clone()
     return cur.cpu().numpy() if is_numpy else cur
+
+
+def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, num_iter=None):
+    """sparse_bilateral_filtering for a RAGGED batch of CUDA depth maps (BASELINE config 2: mixed-resolution frames): every
+    depths[i] is an [H_i, W_i] tensor of one dtype and device, filtered independently exactly as the single-image call
+    would, but each iteration is ONE launch over all images (ofd_bilateral_iter_batch).  Returns a list of tensors that are
+    views into one packed buffer."""
+    if num_iter is None:
+        raise TypeError("'NoneType' object cannot be interpreted as an integer")
+    if not depths:
+        return []
+    dev, dt = depths[0].device, depths[0].dtype
+    shapes = [tuple(d.shape) for d in depths]
+    if any(len(s_) != 2 for s_ in shapes) or any(d.device != dev or d.dtype != dt for d in depths):
+        raise ValueError("depths must be [H,W] tensors of one dtype on one device")
+    sizes = [h * w for h, w in shapes]
+    offsets = [0]
+    for n in sizes[:-1]:
+        offsets.append(offsets[-1] + n)
+    packed0 = torch.cat([d.reshape(-1) for d in depths])
+    cur = packed0
+    with torch.cuda.device(dev):
+        for i in range(num_iter):
+            cur = ops.bilateral_iter_batch(cur, packed0, shapes, offsets, int(filter_size[i]), float(depth_threshold))
+    if num_iter == 0:
+        cur = packed0.clone()
+    return [cur[o:o + n].view(h, w) for (h, w), o, n in zip(shapes, offsets, sizes)]

@@ -14,9 +14,10 @@
 //   2. the discontinuity flag of every interior cell comes from its four shared-memory neighbours;
 //   3. a replication pass applies the reference's border rule (every tap reads row clamp(r,1,H-2), column
 //      clamp(c,1,W-2)) so the window taps are plain offsets;
-//   4. pixels whose window holds a discontinuity pull their window into REGISTERS (discontinuity taps -> +inf) and
-//      sort it with a fully unrolled bitonic network (window 3/5/7: 16/32/64 keys, 80/240/672 compare-exchanges -
-//      against ~2400 x 2 shared-memory compares of a rank count); other window sizes use the rank count.
+//   4. pixels whose window holds a discontinuity are COMPACTED into a per-tile list (so the selection runs in full
+//      warps), pull their window into REGISTERS (discontinuity taps -> +inf) and sort it with a fully unrolled odd-even
+//      merge-sort network over exactly 9/25/49 keys (28/140/394 compare-exchanges of 2 FMNMX each; the half of the
+//      outputs that can never be selected is dead code); other window sizes use a rank count in shared memory.
 // A TMA 2-D tiled load was considered for step 1 (the north star suggests it); a 40x16 float tile is 2.5 loads per
 // thread, so plain coalesced loads are as fast and need no tensor map per call - the time goes into step 4.
 #include "ofd_common.cuh"
@@ -36,32 +37,91 @@ __device__ __forceinline__ double pos_inf<double>() {
     return __longlong_as_double(0x7ff0000000000000ll);
 }
 
-// fully unrolled bitonic sort (ascending) of N = 2^k register values
-template <typename DT, int N>
-__device__ __forceinline__ void bitonic_sort(DT (&v)[N]) {
-#pragma unroll
-    for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int l = i ^ stride;
-                if (l > i) {
-                    const bool up = ((i & size) == 0);
-                    const DT a = v[i], b = v[l];
-                    const DT lo = a < b ? a : b, hi = a < b ? b : a;
-                    v[i] = up ? lo : hi;
-                    v[l] = up ? hi : lo;
-                }
+// Batcher's odd-even merge sort as a compile-time comparator list for ANY n (not only powers of two): 28 / 140 / 394
+// compare-exchanges for 9 / 25 / 49 keys (a bitonic network over the padded 16 / 32 / 64 keys needs 80 / 240 / 672).
+// Only ranks 0 .. (n-1)/2 are ever selected, so the compiler also drops the comparators that feed higher outputs only
+// (25 / 124 / 352 remain).  Each compare-exchange is two FMNMX (min / max) instead of FSETP + 2 FSEL.
+struct CePair {
+    int a, b;
+};
+// the idx-th comparator of the network over n keys ({-1,-1} past the end); evaluated at compile time only
+constexpr CePair oems_pair(int n, int idx) {
+    int count = 0;
+    for (int p = 1; p < n; p *= 2)
+        for (int k = p; k >= 1; k /= 2)
+            for (int j = k % p; j <= n - 1 - k; j += 2 * k) {
+                const int imax = (k - 1 < n - j - k - 1) ? k - 1 : n - j - k - 1;
+                for (int i = 0; i <= imax; ++i)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        if (count == idx) return CePair{i + j, i + j + k};
+                        ++count;
+                    }
             }
-        }
+    return CePair{-1, -1};
+}
+constexpr int oems_count(int n) {
+    int count = 0;
+    while (oems_pair(n, count).a >= 0) ++count;
+    return count;
+}
+
+template <typename DT>
+__device__ __forceinline__ void compare_exchange(DT& x, DT& y);
+template <>
+__device__ __forceinline__ void compare_exchange<float>(float& x, float& y) {
+    const float lo = fminf(x, y), hi = fmaxf(x, y);
+    x = lo, y = hi;
+}
+template <>
+__device__ __forceinline__ void compare_exchange<double>(double& x, double& y) {
+    const double lo = fmin(x, y), hi = fmax(x, y);
+    x = lo, y = hi;
+}
+
+// comparators [LO, HI) of the network, unrolled by halving (keeps the template recursion depth at log2 of the count)
+template <typename DT, int N, int LO, int HI>
+__device__ __forceinline__ void oems_range(DT (&v)[N]) {
+    if constexpr (HI - LO == 1) {
+        constexpr CePair ce = oems_pair(N, LO);
+        compare_exchange<DT>(v[ce.a], v[ce.b]);
+    } else if constexpr (HI - LO > 1) {
+        oems_range<DT, N, LO, (LO + HI) / 2>(v);
+        oems_range<DT, N, (LO + HI) / 2, HI>(v);
     }
+}
+
+// ascending sort of N register values (N compile-time, any value)
+template <typename DT, int N>
+__device__ __forceinline__ void network_sort(DT (&v)[N]) {
+    oems_range<DT, N, 0, oems_count(N)>(v);
+}
+
+// rank table k(n) = #{ m in 1..n : float32 running sum of m copies of float32(1/n) <= 0.5 } (numpy cumsum + digitize,
+// bilateral_filter.py:194-197), n <= 15 x 15.  Filled on the host once per call and passed in the parameter block.
+struct KRank {
+    unsigned char k[MAX_WIN * MAX_WIN + 3];
+};
+
+static KRank make_krank(int window) {
+    KRank kr = {};
+    for (int n = 1; n <= window * window; ++n) {
+        const float w = 1.0f / (float)n;
+        volatile float cum = 0.0f;  // volatile: every partial sum is rounded to float32
+        int k = 0;
+        for (int q = 0; q < n; ++q) {
+            cum = cum + w;
+            k += (cum <= 0.5f);
+        }
+        kr.k[n] = (unsigned char)k;
+    }
+    return kr;
 }
 
 // WS > 0: compile-time window (register sort); WS == 0: run-time window (rank count in shared memory)
 template <typename DT, int WS>
-__global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
-                                                                   int H, int W, int win_rt, DT thr, DT* __restrict__ dout) {
+__device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const DT* __restrict__ dorig, int H, int W,
+                                               int win_rt, DT thr, DT* __restrict__ dout, int tile_x, int tile_y,
+                                               const KRank& kr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int win = WS > 0 ? WS : win_rt;
     const int m = win / 2;
@@ -69,39 +129,61 @@ __global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __
     const int TW = BT_W + 2 * m, TH = BT_H + 2 * m;          // window tile
     DT* sraw = reinterpret_cast<DT*>(smem_raw);               // raw depth
     DT* sinv = sraw + RW * RH;                                // 1 / depth, formed once per cell
-    DT* sdep = sinv + RW * RH;                                // replicated depth at window coordinates
+    DT* sdep = sinv + RW * RH;                                // replicated depth at window coordinates (border tiles only)
     unsigned char* sflag = reinterpret_cast<unsigned char*>(sdep + TW * TH);  // raw-tile discontinuity flags
-    unsigned char* sdisc = sflag + RW * RH;                                   // replicated flags at window coordinates
-    __shared__ int krank[MAX_WIN * MAX_WIN + 1];
+    unsigned char* sdisc = sflag + RW * RH;                                   // replicated flags (border tiles only)
+    __shared__ unsigned char s_k[MAX_WIN * MAX_WIN + 3];
+    __shared__ unsigned long long s_rowmask[BT_H + MAX_WIN - 1];  // discontinuity bits of every window-tile row (TW <= 46 columns)
+    __shared__ unsigned char s_list[BT_W * BT_H];                 // tile pixels that need the median (thread ids, BT_W * BT_H == 256)
+    __shared__ int s_count;
     const int tid = threadIdx.y * BT_W + threadIdx.x;
-    const int nthr = BT_W * BT_H;
-    const int r0 = blockIdx.y * BT_H - m - 2, c0 = blockIdx.x * BT_W - m - 2;  // raw coordinate of raw-tile cell (0,0)
+    constexpr int nthr = BT_W * BT_H;
+    if (tid == 0) s_count = 0;
+    if (tid <= MAX_WIN * MAX_WIN) s_k[tid] = kr.k[tid];
+    const int r0 = tile_y * BT_H - m - 2, c0 = tile_x * BT_W - m - 2;  // raw coordinate of raw-tile cell (0,0)
 
-    // rank table k(n), numpy float32 semantics (bilateral_filter.py:194-197)
-    for (int n = 1 + tid; n <= win * win; n += nthr) {
-        const float w = __fdiv_rn(1.0f, (float)n);
-        float cum = 0.0f;
-        int k = 0;
-        for (int q = 0; q < n; ++q) {
-            cum = __fadd_rn(cum, w);
-            k += (cum <= 0.5f);
+    // 1. raw tile: depth, 1/depth, depth_orig == 0 (zero outside the image; those cells are never consumed).  For a
+    //    compile-time window all global loads of a thread are issued before the first use.
+    if constexpr (WS > 0) {
+        constexpr int CELLS = (BT_W + 2 * (WS / 2) + 4) * (BT_H + 2 * (WS / 2) + 4);
+        constexpr int NL = (CELLS + nthr - 1) / nthr;
+        DT dv[NL], ov[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const int e = tid + k * nthr;
+            const int tr = e / RW, tc = e - tr * RW;
+            const int r = r0 + tr, c = c0 + tc;
+            dv[k] = (DT)0, ov[k] = (DT)1;
+            if (e < CELLS && r >= 0 && r < H && c >= 0 && c < W) {
+                const size_t p = (size_t)r * W + c;
+                dv[k] = din[p];
+                ov[k] = dorig[p];
+            }
         }
-        krank[n] = k;
-    }
-    // 1. raw tile: depth, 1/depth, depth_orig == 0 (zero outside the image; those cells are never consumed)
-    for (int e = tid; e < RW * RH; e += nthr) {
-        const int tr = e / RW, tc = e - tr * RW;
-        const int r = r0 + tr, c = c0 + tc;
-        DT d = (DT)0;
-        unsigned char z = 0;
-        if (r >= 0 && r < H && c >= 0 && c < W) {
-            const size_t p = (size_t)r * W + c;
-            d = din[p];
-            z = (dorig[p] == (DT)0) ? 2 : 0;  // bit 1: forced discontinuity (:46)
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const int e = tid + k * nthr;
+            if (e < CELLS) {
+                sraw[e] = dv[k];
+                sinv[e] = (DT)1.0 / dv[k];
+                sflag[e] = (ov[k] == (DT)0) ? 2 : 0;  // bit 1: forced discontinuity (:46)
+            }
         }
-        sraw[e] = d;
-        sinv[e] = (DT)1.0 / d;
-        sflag[e] = z;
+    } else {
+        for (int e = tid; e < RW * RH; e += nthr) {
+            const int tr = e / RW, tc = e - tr * RW;
+            const int r = r0 + tr, c = c0 + tc;
+            DT d = (DT)0;
+            unsigned char z = 0;
+            if (r >= 0 && r < H && c >= 0 && c < W) {
+                const size_t p = (size_t)r * W + c;
+                d = din[p];
+                z = (dorig[p] == (DT)0) ? 2 : 0;
+            }
+            sraw[e] = d;
+            sinv[e] = (DT)1.0 / d;
+            sflag[e] = z;
+        }
     }
     __syncthreads();
     // 2. discontinuity of interior image pixels from their four shared-memory neighbours (:63-116)
@@ -116,58 +198,99 @@ __global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __
         }
     }
     __syncthreads();
-    // 3. replication pass: window cell (tr,tc) <- raw cell of the clamped coordinate (border ring rule, :141-147)
-    for (int e = tid; e < TW * TH; e += nthr) {
-        const int tr = e / TW, tc = e - tr * TW;
-        int r = r0 + 2 + tr, c = c0 + 2 + tc;
-        r = r < 1 ? 1 : (r > H - 2 ? H - 2 : r);
-        c = c < 1 ? 1 : (c > W - 2 ? W - 2 : c);
-        const int src = (r - r0) * RW + (c - c0);
-        sdep[e] = sraw[src];
-        sdisc[e] = sflag[src] ? 1 : 0;
+    // 3. the reference's border rule (:141-147): every tap reads row clamp(r,1,H-2), column clamp(c,1,W-2).  A tile whose
+    //    window tile lies inside [1,H-2] x [1,W-2] needs no clamping: its taps read the raw tile in place.  Only tiles
+    //    on the image border run the replication pass.
+    const bool interior = (r0 + 2 >= 1) && (r0 + 2 + TH - 1 <= H - 2) && (c0 + 2 >= 1) && (c0 + 2 + TW - 1 <= W - 2);
+    const DT* wdep = sraw + 2 * RW + 2;             // window-tile cell (tr,tc) -> wdep[tr * wstride + tc]
+    const unsigned char* wdisc = sflag + 2 * RW + 2;  // non-zero = discontinuity
+    int wstride = RW;
+    if (!interior) {  // block-uniform
+        for (int e = tid; e < TW * TH; e += nthr) {
+            const int tr = e / TW, tc = e - tr * TW;
+            int r = r0 + 2 + tr, c = c0 + 2 + tc;
+            r = r < 1 ? 1 : (r > H - 2 ? H - 2 : r);
+            c = c < 1 ? 1 : (c > W - 2 ? W - 2 : c);
+            const int src = (r - r0) * RW + (c - c0);
+            sdep[e] = sraw[src];
+            sdisc[e] = sflag[src];
+        }
+        wdep = sdep, wdisc = sdisc, wstride = TW;
+        __syncthreads();
+    }
+    // 4a. one 64-bit discontinuity mask per window-tile row (ballots), so a pixel tests its whole window with `win` loads
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int tr = warp; tr < TH; tr += nthr / 32) {
+            const unsigned lo = __ballot_sync(0xFFFFFFFFu, wdisc[tr * wstride + lane] != 0);
+            const unsigned hi = __ballot_sync(0xFFFFFFFFu, (32 + lane < TW) && wdisc[tr * wstride + 32 + lane] != 0);
+            if (lane == 0) s_rowmask[tr] = ((unsigned long long)hi << 32) | lo;
+        }
     }
     __syncthreads();
-    // 4. gated median
-    const int r = blockIdx.y * BT_H + threadIdx.y, c = blockIdx.x * BT_W + threadIdx.x;
-    if (r >= H || c >= W) return;
-    const int base = threadIdx.y * TW + threadIdx.x;  // top-left tap of this pixel's window
-    const DT centre = sdep[base + m * TW + m];
-    int n_disc = 0;
-    for (int dr = 0; dr < win; ++dr)
-        for (int dc = 0; dc < win; ++dc) n_disc += sdisc[base + dr * TW + dc];
-    DT result = centre;
-    const int n = win * win - n_disc;
-    if (n_disc > 0 && n > 0) {
-        const int k = krank[n];
-        if (WS > 0) {
-            constexpr int NN = WS * WS <= 16 ? 16 : (WS * WS <= 32 ? 32 : 64);
-            DT v[NN];
+    // 4b. pixels without a discontinuity in their window keep their depth; the others are COMPACTED into a list, so the
+    //     expensive selection below runs in full warps (an edge crossing the tile touches a few lanes of every row-warp)
+    const int r = tile_y * BT_H + threadIdx.y, c = tile_x * BT_W + threadIdx.x;
+    bool need = false;
+    if (r < H && c < W) {
+        const unsigned long long wmask = (1ull << win) - 1ull;
+        int n_disc = 0;
+        for (int dr = 0; dr < win; ++dr) n_disc += __popcll((s_rowmask[threadIdx.y + dr] >> threadIdx.x) & wmask);
+        need = n_disc > 0 && n_disc < win * win;
+        if (!need) dout[(size_t)r * W + c] = wdep[(threadIdx.y + m) * wstride + threadIdx.x + m];
+    }
+    {
+        const unsigned lane = tid & 31u;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
+        int slot = 0;
+        if (lane == 0 && mask) slot = atomicAdd(&s_count, __popc(mask));
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (need) s_list[slot + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)tid;
+    }
+    __syncthreads();
+    // 4c. rank-k(n) smallest among the n window pixels with disc == 0
+    const int count = s_count;
+    for (int idx = tid; idx < count; idx += nthr) {
+        const int pix = s_list[idx];
+        const int ty = pix / BT_W, tx = pix - ty * BT_W;
+        const int base = ty * wstride + tx;  // top-left tap of this pixel's window
+        DT result;
+        if constexpr (WS > 0) {
+            DT v[WS * WS];
+            int n = 0;
 #pragma unroll
-            for (int q = 0; q < NN; ++q) {
-                DT x = pos_inf<DT>();
-                if (q < WS * WS) {
-                    const int e = base + (q / WS) * TW + (q % WS);
-                    if (!sdisc[e]) x = sdep[e];
+            for (int dr = 0; dr < WS; ++dr) {
+                const unsigned bits = (unsigned)(s_rowmask[ty + dr] >> tx);
+#pragma unroll
+                for (int dc = 0; dc < WS; ++dc) {
+                    const bool keep = !((bits >> dc) & 1u);
+                    n += keep;
+                    v[dr * WS + dc] = keep ? wdep[base + dr * wstride + dc] : pos_inf<DT>();
                 }
-                v[q] = x;
             }
-            bitonic_sort<DT, NN>(v);
+            network_sort<DT, WS * WS>(v);
+            const int k = s_k[n];  // k <= (WS*WS - 1) / 2
             result = v[0];
 #pragma unroll
-            for (int q = 1; q < WS * WS; ++q) result = (q == k) ? v[q] : result;
+            for (int q = 1; q <= (WS * WS - 1) / 2; ++q) result = (q == k) ? v[q] : result;
         } else {
             // value with  #{f < v} <= k < #{f <= v}  among the n non-discontinuity taps
+            int n = 0;
+            for (int dr = 0; dr < win; ++dr)
+                for (int dc = 0; dc < win; ++dc) n += !wdisc[base + dr * wstride + dc];
+            const int k = s_k[n];
+            result = wdep[base + m * wstride + m];
             for (int er = 0; er < win; ++er) {
                 for (int ec = 0; ec < win; ++ec) {
-                    const int e = base + er * TW + ec;
-                    if (sdisc[e]) continue;
-                    const DT v = sdep[e];
+                    const int e = base + er * wstride + ec;
+                    if (wdisc[e]) continue;
+                    const DT v = wdep[e];
                     int lt = 0, le = 0;
                     for (int dr = 0; dr < win; ++dr)
                         for (int dc = 0; dc < win; ++dc) {
-                            const int f = base + dr * TW + dc;
-                            if (!sdisc[f]) {
-                                const DT u = sdep[f];
+                            const int f = base + dr * wstride + dc;
+                            if (!wdisc[f]) {
+                                const DT u = wdep[f];
                                 lt += (u < v);
                                 le += (u <= v);
                             }
@@ -180,8 +303,61 @@ __global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __
                 }
             }
         }
+        dout[(size_t)(tile_y * BT_H + ty) * W + (tile_x * BT_W + tx)] = result;
     }
-    dout[(size_t)r * W + c] = result;
+}
+
+template <typename DT, int WS>
+__global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+                                                                   int H, int W, int win_rt, DT thr, DT* __restrict__ dout,
+                                                                   const __grid_constant__ KRank kr) {
+    bilateral_tile<DT, WS>(din, dorig, H, W, win_rt, thr, dout, blockIdx.x, blockIdx.y, kr);
+}
+
+// Ragged batch (BASELINE config 2: mixed-resolution frames): images of different H x W packed back to back in one
+// buffer; the grid is the concatenation of every image's tile list and a CTA finds its image by bisection.
+constexpr int BB_MAX = 64;
+struct BilateralBatch {
+    unsigned long long offset[BB_MAX];  // first element of image i in the packed buffers
+    unsigned tile_start[BB_MAX + 1];    // first linear tile of image i
+    int H[BB_MAX], W[BB_MAX], tiles_x[BB_MAX];
+    int n;
+};
+
+template <typename DT, int WS>
+__global__ void __launch_bounds__(BT_W* BT_H) bilateral_batch_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+                                                                    const __grid_constant__ BilateralBatch bb, int win_rt,
+                                                                    DT thr, DT* __restrict__ dout, const __grid_constant__ KRank kr) {
+    const unsigned t = blockIdx.x;
+    int lo = 0, hi = bb.n - 1;
+    while (lo < hi) {  // last image whose tile_start <= t
+        const int mid = (lo + hi + 1) >> 1;
+        if (bb.tile_start[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const unsigned local = t - bb.tile_start[lo];
+    const int tiles_x = bb.tiles_x[lo];
+    const size_t off = (size_t)bb.offset[lo];
+    bilateral_tile<DT, WS>(din + off, dorig + off, bb.H[lo], bb.W[lo], win_rt, thr, dout + off, (int)(local % tiles_x), (int)(local / tiles_x), kr);
+}
+
+template <typename DT, int WS>
+static void launch_bilateral_batch(const DT* din, const DT* dorig, const BilateralBatch& bb, unsigned tiles, int window, DT thr,
+                                   DT* dout, cudaStream_t st) {
+    const int m = window / 2;
+    const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
+    const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
+    bilateral_batch_kernel<DT, WS><<<tiles, dim3(BT_W, BT_H), smem, st>>>(din, dorig, bb, window, thr, dout, make_krank(window));
+}
+
+template <typename DT>
+static void dispatch_bilateral_batch(const DT* din, const DT* dorig, const BilateralBatch& bb, unsigned tiles, int window, DT thr,
+                                     DT* dout, cudaStream_t st) {
+    switch (window) {
+        case 3: launch_bilateral_batch<DT, 3>(din, dorig, bb, tiles, window, thr, dout, st); break;
+        case 5: launch_bilateral_batch<DT, 5>(din, dorig, bb, tiles, window, thr, dout, st); break;
+        case 7: launch_bilateral_batch<DT, 7>(din, dorig, bb, tiles, window, thr, dout, st); break;
+        default: launch_bilateral_batch<DT, 0>(din, dorig, bb, tiles, window, thr, dout, st); break;
+    }
 }
 
 template <typename DT, int WS>
@@ -190,7 +366,7 @@ static void launch_bilateral(const DT* din, const DT* dorig, int H, int W, int w
     const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
     dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_H);
-    bilateral_iter_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, H, W, window, thr, dout);
+    bilateral_iter_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, H, W, window, thr, dout, make_krank(window));
 }
 
 template <typename DT>
@@ -223,4 +399,43 @@ extern "C" int ofd_bilateral_iter(const void* depth_in, const void* depth_orig, 
     else
         dispatch_bilateral<double>((const double*)depth_in, (const double*)depth_orig, H, W, window, threshold, (double*)depth_out, st);
     return check_launch(fn);
+}
+
+extern "C" int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int dtype, int n_images,
+                                        const int* H_host, const int* W_host, const size_t* offset_host, int window,
+                                        double threshold, void* depth_out, ofd_stream_t stream) {
+    const char* fn = "ofd_bilateral_iter_batch";
+    if (dtype != OFD_F32 && dtype != OFD_F64) return fail(OFD_E_DTYPE, "%s: bad dtype %d", fn, dtype);
+    if (n_images < 0) return fail(OFD_E_SHAPE, "%s: negative image count", fn);
+    if (window < 1 || window > MAX_WIN || (window & 1) == 0)
+        return fail(OFD_E_ARG, "%s: window must be odd and in [1,%d]", fn, MAX_WIN);
+    if (n_images == 0) return OFD_OK;
+    if (!depth_in || !depth_orig || !depth_out || !H_host || !W_host || !offset_host) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    if (depth_in == depth_out) return fail(OFD_E_ARG, "%s: in-place filtering is not supported", fn);
+    for (int i = 0; i < n_images; ++i)
+        if (H_host[i] < 3 || W_host[i] < 3) return fail(OFD_E_SHAPE, "%s: image %d is %dx%d, needs H >= 3 and W >= 3", fn, i, H_host[i], W_host[i]);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n_images; i0 += BB_MAX) {
+        BilateralBatch bb = {};
+        bb.n = (n_images - i0) < BB_MAX ? (n_images - i0) : BB_MAX;
+        unsigned long long tiles = 0;
+        for (int k = 0; k < bb.n; ++k) {
+            const int H = H_host[i0 + k], W = W_host[i0 + k];
+            bb.H[k] = H, bb.W[k] = W, bb.offset[k] = offset_host[i0 + k];
+            bb.tiles_x[k] = (W + BT_W - 1) / BT_W;
+            bb.tile_start[k] = (unsigned)tiles;
+            tiles += (unsigned long long)bb.tiles_x[k] * ((H + BT_H - 1) / BT_H);
+        }
+        bb.tile_start[bb.n] = (unsigned)tiles;
+        if (tiles > 0x7FFFFFFFull) return fail(OFD_E_SHAPE, "%s: too many tiles in one launch", fn);
+        if (dtype == OFD_F32)
+            dispatch_bilateral_batch<float>((const float*)depth_in, (const float*)depth_orig, bb, (unsigned)tiles, window, (float)threshold,
+                                            (float*)depth_out, st);
+        else
+            dispatch_bilateral_batch<double>((const double*)depth_in, (const double*)depth_orig, bb, (unsigned)tiles, window, threshold,
+                                             (double*)depth_out, st);
+        int rc = check_launch(fn);
+        if (rc) return rc;
+    }
+    return OFD_OK;
 }

@@ -325,6 +325,23 @@ def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
     return out
 
 
+def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, threshold: float):
+    """One iteration over a ragged batch: packed_in / packed_orig are 1-D CUDA buffers holding image i ([H_i,W_i] dense) at
+    element offset offsets[i]; returns the filtered packed buffer (same layout)."""
+    _check("packed_in", packed_in, dtype=(torch.float32, torch.float64))
+    _check("packed_orig", packed_orig, dtype=packed_in.dtype, shape=packed_in.shape)
+    n = len(shapes)
+    if any(off + h * w > packed_in.numel() for (h, w), off in zip(shapes, offsets)):
+        raise ValueError("an image extends past the end of the packed buffer")
+    Hs = (C.c_int * n)(*[int(h) for h, _ in shapes])
+    Ws = (C.c_int * n)(*[int(w) for _, w in shapes])
+    offs = (C.c_size_t * n)(*[int(o) for o in offsets])
+    out = torch.empty_like(packed_in)
+    _lib.call("ofd_bilateral_iter_batch", _ptr(packed_in), _ptr(packed_orig), _DT[packed_in.dtype], n, Hs, Ws, offs, int(window),
+              C.c_double(threshold), _ptr(out), _stream(packed_in.device))
+    return out
+
+
 class PairPipeline:
     """Host-buffer front end (ofd_pair_pipeline_*): pinned CPU tensors in, pinned CPU tensors out."""
 

@@ -613,6 +613,29 @@ def test_cfg2_redweb_ragged_batch_bilateral_then_pair(pkg):
             assert eq(g, wnt)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cfg2_ragged_batch_bilateral_equals_per_image(pkg, dtype):
+    """ofd_bilateral_iter_batch (one launch per iteration over a mixed-resolution batch) == the per-image filter == the
+    oracle, bit-exact; includes sizes that are not tile multiples, a 3x3 image and a zero-depth (forced discontinuity) frame."""
+    sizes = [(150, 212), (98, 170), (3, 3), (201, 133), (8, 32), (64, 65)]
+    fs = [7, 7, 5, 5, 3]
+    depths = []
+    for k, (h, w) in enumerate(sizes):
+        _, depth = pkg.synthetic.redweb_frame(k, max(h, 32), max(w, 32), dtype=dtype)
+        d = oflow.normalize_depth(torch.from_numpy(depth[:, :h, :w].copy())).numpy()[0]
+        if k == 1:
+            d[10:20, 30:50] = 0  # depth_orig == 0 -> discontinuity forced (bilateral_filter.py:46)
+        depths.append(np.ascontiguousarray(d))
+    got = pkg.bilateral_filter.sparse_bilateral_filtering_batch([cu(d) for d in depths], fs, 0.04, 5)
+    for d, g in zip(depths, got):
+        one = pkg.bilateral_filter.sparse_bilateral_filtering(cu(d), None, fs, depth_threshold=0.04, num_iter=5)
+        assert torch.equal(g, one)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = obil.sparse_bilateral_filtering(d.copy(), fs, 0.04, 5)
+        assert eq(g, want)
+    assert pkg.bilateral_filter.sparse_bilateral_filtering_batch([], fs, 0.04, 5) == []
+
+
 @pytest.mark.parametrize("kind", [5, 6, 7])
 def test_cfg4_inloop_geometric_augmentation_368x496(pkg, kind):
     """cfg4: the 6-splat geometric branch of augment_flow (preprocess.py:116-147 minus inpaint) at RAFT's crop size;
