@@ -173,6 +173,14 @@ int ofd_reproject_pair(const float* img, const float* depth, const float* cam, f
 int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void* out, void* scratch,
                         ofd_stream_t stream);
 
+/*
+ * ofd_normalize_depth_ragged — ofd_normalize_depth for a RAGGED batch (BASELINE config 2): image i is count_host[i] elements
+ * at element offset offset_host[i] of depth / out (HOST arrays); each image gets its own min / max.  3 launches per 128
+ * images.  scratch: 2*n_images uint64 words (device).
+ */
+int ofd_normalize_depth_ragged(const void* depth, int dtype, int n_images, const size_t* count_host,
+                               const size_t* offset_host, void* out, void* scratch, ofd_stream_t stream);
+
 /* ofd_fix_warped_depth — utils.fix_warped_depth (utils.py:123-126), in place: 0 -> 100, > 99.5 -> 100. */
 int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ofd_frame_splat": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_reproject_pair": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ofd_normalize_depth_ragged": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
     "ofd_fix_warped_depth": (_i, [_p, _sz, _p]),
     "ofd_inpaint_mask": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofd_special_flow": (_i, [_i, _p, _i, _i, _p, _p, _p]),

@@ -41,11 +41,12 @@ def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4
     return cur.cpu().numpy() if is_numpy else cur
 
 
-def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, num_iter=None):
+def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, num_iter=None, normalize=False):
     """sparse_bilateral_filtering for a RAGGED batch of CUDA depth maps (BASELINE config 2: mixed-resolution frames): every
     depths[i] is an [H_i, W_i] tensor of one dtype and device, filtered independently exactly as the single-image call
     would, but each iteration is ONE launch over all images (ofd_bilateral_iter_batch).  Returns a list of tensors that are
-    views into one packed buffer."""
+    views into one packed buffer.  normalize=True first applies utils.normalize_depth to every image (one ragged launch
+    triple, ofd_normalize_depth_ragged) - the cfg2 front end `normalize_depth -> bilateral` without per-image launches."""
     if num_iter is None:
         raise TypeError("'NoneType' object cannot be interpreted as an integer")
     if not depths:
@@ -59,8 +60,10 @@ def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, 
     for n in sizes[:-1]:
         offsets.append(offsets[-1] + n)
     packed0 = torch.cat([d.reshape(-1) for d in depths])
-    cur = packed0
     with torch.cuda.device(dev):
+        if normalize:
+            packed0 = ops.normalize_depth_ragged(packed0, sizes, offsets)
+        cur = packed0
         for i in range(num_iter):
             cur = ops.bilateral_iter_batch(cur, packed0, shapes, offsets, int(filter_size[i]), float(depth_threshold))
     if num_iter == 0:

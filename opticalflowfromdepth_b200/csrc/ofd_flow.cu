@@ -245,6 +245,73 @@ __global__ void __launch_bounds__(256) normalize_map_kernel(const DT* __restrict
     }
 }
 
+// Ragged variants (BASELINE config 2: mixed-resolution frames packed back to back): image blockIdx.y is `count[y]` elements
+// at element offset `offset[y]`; the arithmetic is the per-frame kernels' above.
+constexpr int RAGGED_MAX = 128;
+struct RaggedTable {
+    unsigned long long offset[RAGGED_MAX];
+    unsigned long long count[RAGGED_MAX];
+};
+
+template <typename DT>
+__global__ void __launch_bounds__(256) minmax_ragged_kernel(const DT* __restrict__ depth, const __grid_constant__ RaggedTable tab,
+                                                           u64* __restrict__ scratch) {
+    typedef typename Ord<DT>::U U;
+    const int b = blockIdx.y;
+    const DT* d = depth + tab.offset[b];
+    const size_t hw = tab.count[b];
+    U mn = ~(U)0, mx = 0;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (size_t)gridDim.x * blockDim.x) {
+        DT v = d[p];
+        if (v == (DT)0 || v > (DT)100) v = (DT)100;
+        U e1 = Ord<DT>::enc(v);
+        if (v == (DT)100) v = (DT)0;
+        U e2 = Ord<DT>::enc(v);
+        mn = e1 < mn ? e1 : mn;
+        mx = e2 > mx ? e2 : mx;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        U a = __shfl_xor_sync(0xFFFFFFFFu, mn, o), c = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = c > mx ? c : mx;
+    }
+    __shared__ U smn[8], smx[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smn[w] = mn, smx[w] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            mn = smn[k] < mn ? smn[k] : mn;
+            mx = smx[k] > mx ? smx[k] : mx;
+        }
+        atomicMin(scratch + 2 * b, (u64)mn);
+        atomicMax(scratch + 2 * b + 1, (u64)mx);
+    }
+}
+
+template <typename DT>
+__global__ void __launch_bounds__(256) normalize_map_ragged_kernel(const DT* __restrict__ depth, const __grid_constant__ RaggedTable tab,
+                                                                  const u64* __restrict__ scratch, DT* __restrict__ out) {
+    typedef typename Ord<DT>::U U;
+    const int b = blockIdx.y;
+    const DT mn = Ord<DT>::dec((U)scratch[2 * b]);
+    const DT mx = Ord<DT>::dec((U)scratch[2 * b + 1]);
+    const DT range = mx - mn;
+    const DT zero_img = (((DT)0 - mn) * (DT)98) / range + (DT)1;
+    const DT* d = depth + tab.offset[b];
+    DT* o = out + tab.offset[b];
+    const size_t hw = tab.count[b];
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (size_t)gridDim.x * blockDim.x) {
+        DT v = d[p];
+        if (v == (DT)0 || v > (DT)100) v = (DT)100;
+        if (v == (DT)100) v = (DT)0;
+        DT r = ((v - mn) * (DT)98) / range + (DT)1;
+        if (r == zero_img) r = (DT)100;
+        o[p] = r;
+    }
+}
+
 __global__ void __launch_bounds__(256) fix_depth_kernel(float* __restrict__ d, size_t n) {
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
         d[p] = fix_depth(d[p]);
@@ -400,6 +467,41 @@ int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void*
         normalize_map_kernel<double><<<grid, 256, 0, st>>>((const double*)depth, hw, sc, (double*)out);
     }
     return check_launch(fn);
+}
+
+int ofd_normalize_depth_ragged(const void* depth, int dtype, int n_images, const size_t* count_host, const size_t* offset_host,
+                               void* out, void* scratch, ofd_stream_t stream) {
+    const char* fn = "ofd_normalize_depth_ragged";
+    if (dtype != OFD_F32 && dtype != OFD_F64) return fail(OFD_E_DTYPE, "%s: bad dtype %d", fn, dtype);
+    if (n_images < 0) return fail(OFD_E_SHAPE, "%s: negative image count", fn);
+    if (n_images == 0) return OFD_OK;
+    if (!depth || !out || !scratch || !count_host || !offset_host) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    if ((uintptr_t)scratch & 7) return fail(OFD_E_WORKSPACE, "%s: scratch must be 8-byte aligned (2*n_images uint64)", fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    u64* sc = (u64*)scratch;
+    minmax_init_kernel<<<(n_images + 255) / 256, 256, 0, st>>>(sc, n_images);
+    for (int i0 = 0; i0 < n_images; i0 += RAGGED_MAX) {
+        const int n = (n_images - i0) < RAGGED_MAX ? (n_images - i0) : RAGGED_MAX;
+        RaggedTable tab = {};
+        size_t big = 0;
+        for (int k = 0; k < n; ++k) {
+            tab.offset[k] = offset_host[i0 + k];
+            tab.count[k] = count_host[i0 + k];
+            big = count_host[i0 + k] > big ? count_host[i0 + k] : big;
+        }
+        if (big == 0) continue;
+        dim3 grid(blocks_for(big, 256 * 8, 296), n);
+        if (dtype == OFD_F32) {
+            minmax_ragged_kernel<float><<<grid, 256, 0, st>>>((const float*)depth, tab, sc + 2 * i0);
+            normalize_map_ragged_kernel<float><<<grid, 256, 0, st>>>((const float*)depth, tab, sc + 2 * i0, (float*)out);
+        } else {
+            minmax_ragged_kernel<double><<<grid, 256, 0, st>>>((const double*)depth, tab, sc + 2 * i0);
+            normalize_map_ragged_kernel<double><<<grid, 256, 0, st>>>((const double*)depth, tab, sc + 2 * i0, (double*)out);
+        }
+        int rc = check_launch(fn);
+        if (rc) return rc;
+    }
+    return OFD_OK;
 }
 
 int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream) {

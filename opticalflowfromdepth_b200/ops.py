@@ -235,6 +235,21 @@ def normalize_depth(depth):
     return out
 
 
+def normalize_depth_ragged(packed, counts, offsets):
+    """utils.normalize_depth per image of a ragged batch: `packed` is a 1-D CUDA buffer (f32|f64) holding image i as
+    counts[i] elements at offsets[i]; returns the normalised packed buffer (same layout)."""
+    _check("packed", packed, dtype=(torch.float32, torch.float64))
+    n = len(counts)
+    if any(o + c > packed.numel() for c, o in zip(counts, offsets)):
+        raise ValueError("an image extends past the end of the packed buffer")
+    cnt = (C.c_size_t * n)(*[int(c) for c in counts])
+    off = (C.c_size_t * n)(*[int(o) for o in offsets])
+    out = torch.empty_like(packed)
+    scratch = torch.empty(2 * max(n, 1), dtype=torch.int64, device=packed.device)
+    _lib.call("ofd_normalize_depth_ragged", _ptr(packed), _DT[packed.dtype], n, cnt, off, _ptr(out), _ptr(scratch), _stream(packed.device))
+    return out
+
+
 def fix_warped_depth_(depth):
     """utils.fix_warped_depth (utils.py:123-126), in place."""
     _check("depth", depth, dtype=torch.float32)

@@ -634,6 +634,26 @@ def test_cfg2_ragged_batch_bilateral_equals_per_image(pkg, dtype):
             want = obil.sparse_bilateral_filtering(d.copy(), fs, 0.04, 5)
         assert eq(g, want)
     assert pkg.bilateral_filter.sparse_bilateral_filtering_batch([], fs, 0.04, 5) == []
+    # ragged normalize_depth (one launch triple for the batch) == the per-image operator == the oracle
+    raws = []
+    for k, (h, w) in enumerate(sizes):
+        _, depth = pkg.synthetic.redweb_frame(20 + k, max(h, 32), max(w, 32), dtype=dtype)
+        raw = np.ascontiguousarray(depth[0, :h, :w]) * 3000.0  # spread over [0, >100]: exercises the 0 / >100 rules
+        if k % 2:
+            raw[0, 0] = 0.0
+        raws.append(raw)
+    counts = [r.size for r in raws]
+    offs = list(np.cumsum([0] + counts[:-1]))
+    packed = cu(np.concatenate([r.ravel() for r in raws]))
+    got_n = pkg.ops.normalize_depth_ragged(packed, counts, offs)
+    for r, c, o in zip(raws, counts, offs):
+        want = oflow.normalize_depth(torch.from_numpy(r.copy())[None]).numpy()[0]
+        assert eq(got_n[o:o + c].view(*r.shape), want)
+        assert torch.equal(got_n[o:o + c].view(*r.shape), pkg.ops.normalize_depth(cu(r)[None, None])[0, 0])
+    both = pkg.bilateral_filter.sparse_bilateral_filtering_batch([cu(r) for r in raws], fs, 0.04, 2, normalize=True)
+    for r, g in zip(raws, both):
+        nd = pkg.ops.normalize_depth(cu(r)[None, None])[0, 0]
+        assert torch.equal(g, pkg.bilateral_filter.sparse_bilateral_filtering(nd, None, fs, depth_threshold=0.04, num_iter=2))
 
 
 @pytest.mark.parametrize("kind", [5, 6, 7])
