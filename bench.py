@@ -390,7 +390,7 @@ def run_ours(args):
             # (b2) the reference's whole 5-pair group per frame (preprocess.py:356-432 minus inpaint): 7 splats with
             #      fused producers/epilogues = 13 launches per batch
             try:
-                Fq = min(F, 32)
+                Fq = min(F, args.group_frames)
                 Kq, invKq = synthesis.Plausible.K((H, W))
                 camsq = []
                 for k in range(Fq):
@@ -505,6 +505,30 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": n * reps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} frames x {reps} repeats of the same 480x640 workload, {cores} pthreads over frames (oracle/ofd_oracle.c)"}
+        # the reference's torch geometry path (preprocess.py:265-298) and numpy bilateral (bilateral_filter.py:13-60) on the host
+        # cores, through their op-for-op restatements (oracle/flow.py with torch's CPU threads; oracle/bilateral.py, vectorised numpy -
+        # the reference's own per-pixel Python loop needs 5.2 s for the same frame)
+        try:
+            from oracle import bilateral as obil
+            from oracle import flow as oflow
+
+            torch.set_num_threads(cores)
+            d_cpu = torch.from_numpy(cd[0])
+            torch.manual_seed(12345)
+            T1, _, _ = oflow.random_motion()
+            oflow.reproject_flow(d_cpu, T1)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                oflow.reproject_flow(d_cpu, T1)
+            t_geo = (time.perf_counter() - t0) / 10
+            t0 = time.perf_counter()
+            obil.sparse_bilateral_filtering(cd[0, 0].copy(), [7, 7, 5, 5, 5], 0.04, 5)
+            t_bil = time.perf_counter() - t0
+            line["cpu_baseline"]["geometry_6dof_flow_480x640_ms"] = 1e3 * t_geo
+            line["cpu_baseline"]["bilateral_5iter_480x640_ms"] = 1e3 * t_bil
+            line["cpu_baseline"]["geometry_bilateral_kind"] = f"port: torch CPU ops, {cores} threads / vectorised numpy, 1 thread"
+        except Exception as e:  # secondary
+            line["cpu_baseline"]["geometry_bilateral_error"] = repr(e)
 
     if world > 1:
         dist.barrier()
@@ -521,6 +545,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--e2e-frames", type=int, default=128)
     ap.add_argument("--e2e-chunk", type=int, default=8)
+    ap.add_argument("--group-frames", type=int, default=128, help="frames per step of the 5-pair group leg")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

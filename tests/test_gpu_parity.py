@@ -517,6 +517,50 @@ def test_reproject_pair_equals_unfused_path(pkg):
                 assert torch.equal(x, y)
 
 
+def test_cfg3_full_size_1080p_batch32_properties_and_sampled_frames(pkg):
+    """BASELINE config 3 at its full size (32 x 1080x1920, random 6-DoF pose per frame, C=7 splat + hole mask): counters
+    account for every pixel; masks are 0/1 and consistent; the batch result does not depend on the batch (frame b of the
+    batch == the same frame alone); three sampled frames against the oracle (splat bit-exact given the flow, flow within
+    the path's tolerance of the torch restatement)."""
+    h, w, n = 1080, 1920, 32
+    pool = 2
+    imgs, depths = zip(*(pkg.synthetic.diml_frame(100 + k, h, w) for k in range(pool)))
+    idx = torch.arange(n, device=DEV) % pool
+    img = cu(np.stack(imgs))[idx].contiguous()
+    depth = pkg.ops.normalize_depth(cu(np.stack(depths)))[idx].contiguous()
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    cams, poses = [], []
+    for k in range(n):
+        torch.manual_seed(12345 + k)
+        T1 = pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]
+        poses.append(T1)
+        cams.append(pkg.geometry.camera_constants(K, invK, T1))
+    cam = torch.cat(cams).to(DEV)
+    vin = (torch.rand(n, 1, h, w, device=DEV) > 0.05).float()
+    cnt = pkg.ops.new_counters(torch.device(DEV))
+    io, do, bo, fo, vo, co, raw = pkg.ops.reproject_pair(img, depth, cam, vin, want_raw_valid=True, counters=cnt)
+    c = cnt.cpu().tolist()
+    assert c[0] + c[1] == n * h * w and c[0] == int(torch.count_nonzero(raw)) and c[2] == int(torch.count_nonzero(co)) == 0 and c[3] == 0
+    assert bool(((raw == 0) | (raw == 1)).all()) and bool(((vo == 0) | (vo == 1)).all()) and bool((vo <= raw).all())
+    assert bool((io[(vo == 0).expand_as(io)] == 0).all()) and bool((do[vo == 0] == 100).all()) and bool((bo[(vo == 0).expand_as(bo)] == 0).all())
+    hit = c[0] / (n * h * w)
+    print(f"[cfg3 full size] hit rate {hit:.3f}, tie sources {c[4]} ({c[4] / (n * h * w):.2e} of the pixels)")
+    assert 0.4 < hit < 0.95
+    for b in (0, 17, 31):
+        one = pkg.ops.reproject_pair(img[b:b + 1], depth[b:b + 1], cam[b:b + 1], vin[b:b + 1], want_raw_valid=True)
+        for x, y in zip((io, do, bo, fo, vo, co, raw), one):
+            assert torch.equal(x[b:b + 1], y), b
+        ref = oflow.reproject_flow(depth[b].cpu(), poses[b]).numpy()
+        frac = _flow_tolerance_check(fo[b], ref, h, w, f"cfg3 frame {b}")
+        assert frac < 1e-3
+        obj = torch.cat((img[b], depth[b], fo[b] * -1.0, vin[b])).cpu().numpy()
+        o, v, cc, _, _ = oracle.fw_forward(obj, fo[b].cpu().numpy(), depth[b].cpu().numpy())
+        v2 = v * o[6:7]
+        assert eq(raw[b], v) and eq(vo[b], v2) and eq(co[b], cc)
+        assert eq(io[b], o[0:3] * v2) and eq(bo[b], o[4:6] * v2)
+        assert eq(do[b], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v2)).numpy())
+
+
 def test_chunked_batches_match_single_frames(pkg, monkeypatch):
     """The L2-sized chunk walk (every chunk reuses the same key region) gives the per-frame results."""
     import os
