@@ -24,7 +24,13 @@
 
 namespace ofd {
 
-constexpr int BT_W = 32, BT_H = 8, MAX_WIN = 15;
+// Tile = 32 x (8 * BIL_RPT) outputs for a block of 32 x 8 threads: every thread owns BIL_RPT output rows.  A taller tile
+// amortises the halo (window 7: 2.95 staged cells per output at 32x8, 2.13 at 32x16, 1.72 at 32x32).
+#ifndef OFD_BIL_RPT
+#define OFD_BIL_RPT 4
+#endif
+constexpr int BIL_RPT = OFD_BIL_RPT;
+constexpr int BT_W = 32, BT_TY = 8, BT_H = BT_TY * BIL_RPT, MAX_WIN = 15;
 
 template <typename DT>
 __device__ __forceinline__ DT pos_inf();
@@ -134,10 +140,10 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     unsigned char* sdisc = sflag + RW * RH;                                   // replicated flags (border tiles only)
     __shared__ unsigned char s_k[MAX_WIN * MAX_WIN + 3];
     __shared__ unsigned long long s_rowmask[BT_H + MAX_WIN - 1];  // discontinuity bits of every window-tile row (TW <= 46 columns)
-    __shared__ unsigned char s_list[BT_W * BT_H];                 // tile pixels that need the median (thread ids, BT_W * BT_H == 256)
+    __shared__ unsigned short s_list[BT_W * BT_H];                // tile pixels that need the median (row * BT_W + column)
     __shared__ int s_count;
     const int tid = threadIdx.y * BT_W + threadIdx.x;
-    constexpr int nthr = BT_W * BT_H;
+    constexpr int nthr = BT_W * BT_TY;
     if (tid == 0) s_count = 0;
     if (tid <= MAX_WIN * MAX_WIN) s_k[tid] = kr.k[tid];
     const int r0 = tile_y * BT_H - m - 2, c0 = tile_x * BT_W - m - 2;  // raw coordinate of raw-tile cell (0,0)
@@ -230,22 +236,25 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     __syncthreads();
     // 4b. pixels without a discontinuity in their window keep their depth; the others are COMPACTED into a list, so the
     //     expensive selection below runs in full warps (an edge crossing the tile touches a few lanes of every row-warp)
-    const int r = tile_y * BT_H + threadIdx.y, c = tile_x * BT_W + threadIdx.x;
-    bool need = false;
-    if (r < H && c < W) {
-        const unsigned long long wmask = (1ull << win) - 1ull;
-        int n_disc = 0;
-        for (int dr = 0; dr < win; ++dr) n_disc += __popcll((s_rowmask[threadIdx.y + dr] >> threadIdx.x) & wmask);
-        need = n_disc > 0 && n_disc < win * win;
-        if (!need) dout[(size_t)r * W + c] = wdep[(threadIdx.y + m) * wstride + threadIdx.x + m];
-    }
-    {
+    const int c = tile_x * BT_W + threadIdx.x;
+#pragma unroll
+    for (int rr = 0; rr < BIL_RPT; ++rr) {
+        const int ty = threadIdx.y + rr * BT_TY;
+        const int r = tile_y * BT_H + ty;
+        bool need = false;
+        if (r < H && c < W) {
+            const unsigned long long wmask = (1ull << win) - 1ull;
+            int n_disc = 0;
+            for (int dr = 0; dr < win; ++dr) n_disc += __popcll((s_rowmask[ty + dr] >> threadIdx.x) & wmask);
+            need = n_disc > 0 && n_disc < win * win;
+            if (!need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
+        }
         const unsigned lane = tid & 31u;
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
         int slot = 0;
         if (lane == 0 && mask) slot = atomicAdd(&s_count, __popc(mask));
         slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-        if (need) s_list[slot + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)tid;
+        if (need) s_list[slot + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(ty * BT_W + threadIdx.x);
     }
     __syncthreads();
     // 4c. rank-k(n) smallest among the n window pixels with disc == 0
@@ -308,7 +317,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
 }
 
 template <typename DT, int WS>
-__global__ void __launch_bounds__(BT_W* BT_H) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+__global__ void __launch_bounds__(BT_W* BT_TY) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
                                                                    int H, int W, int win_rt, DT thr, DT* __restrict__ dout,
                                                                    const __grid_constant__ KRank kr) {
     bilateral_tile<DT, WS>(din, dorig, H, W, win_rt, thr, dout, blockIdx.x, blockIdx.y, kr);
@@ -325,7 +334,7 @@ struct BilateralBatch {
 };
 
 template <typename DT, int WS>
-__global__ void __launch_bounds__(BT_W* BT_H) bilateral_batch_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+__global__ void __launch_bounds__(BT_W* BT_TY) bilateral_batch_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
                                                                     const __grid_constant__ BilateralBatch bb, int win_rt,
                                                                     DT thr, DT* __restrict__ dout, const __grid_constant__ KRank kr) {
     const unsigned t = blockIdx.x;
@@ -346,7 +355,8 @@ static void launch_bilateral_batch(const DT* din, const DT* dorig, const Bilater
     const int m = window / 2;
     const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
-    bilateral_batch_kernel<DT, WS><<<tiles, dim3(BT_W, BT_H), smem, st>>>(din, dorig, bb, window, thr, dout, make_krank(window));
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_batch_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bilateral_batch_kernel<DT, WS><<<tiles, dim3(BT_W, BT_TY), smem, st>>>(din, dorig, bb, window, thr, dout, make_krank(window));
 }
 
 template <typename DT>
@@ -365,7 +375,8 @@ static void launch_bilateral(const DT* din, const DT* dorig, int H, int W, int w
     const int m = window / 2;
     const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
-    dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_H);
+    dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_TY);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_iter_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     bilateral_iter_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, H, W, window, thr, dout, make_krank(window));
 }
 
