@@ -123,7 +123,7 @@ class PreprocessPlusAugment(nn.Module):
     """preprocess.PreprocessPlusAugment (preprocess.py:328-505): same constructor / forward signature and output files."""
 
     def __init__(self, device, inpaint="reference", writer: Optional[NpzWriter] = None, compress: bool = True,
-                 save_dtype=np.float32, quiet: bool = False):
+                 save_dtype=np.float32, quiet: bool = False, reader_compat: bool = False):
         super().__init__()
         self.device = torch.device(device)
         self.inpaint: Optional[Callable] = synthesis.inpaint if inpaint == "reference" else inpaint
@@ -131,6 +131,10 @@ class PreprocessPlusAugment(nn.Module):
         self.writer = writer if writer is not None else NpzWriter(compress=compress)
         self.save_dtype = save_dtype
         self.quiet = quiet
+        # The reference's reader wants a key `augment_img` (dataloader.py:83: 0 = the file holds the augmented FIRST image,
+        # layout img|depth|flow|back_flow; else the augmented second image, layout flow|back_flow|img|depth) that its own
+        # writer never stores.  reader_compat=True stores it, so dataloader.py reads these files as is.
+        self.reader_compat = reader_compat
         self.counters = None
 
     # ---- the group (preprocess.py:341-447) -------------------------------------------------------------------------
@@ -220,8 +224,10 @@ class PreprocessPlusAugment(nn.Module):
             for gi in range(len(GROUP_PAIRS)):
                 block = self._to_host(self.augment_pair_block(group, gi, plan[gi]))
                 for k, t in enumerate(AUGMENT_TYPES):
-                    self.writer.submit(f"{output_dir}/{gi}_{k}_1.npz", img_depth_flow=block[k, 0], augment_flow_type=t)
-                    self.writer.submit(f"{output_dir}/{gi}_{k}_2.npz", img_depth_flow=block[k, 1], augment_flow_type=t)
+                    for which in (0, 1):
+                        extra = {"augment_img": which} if self.reader_compat else {}
+                        self.writer.submit(f"{output_dir}/{gi}_{k}_{which + 1}.npz", img_depth_flow=block[k, which],
+                                           augment_flow_type=t, **extra)
         if self._own_writer:
             self.writer.drain()
         if not self.quiet:
@@ -244,6 +250,8 @@ def read_args(argv=None):
     parser.add_argument('--writer_threads', default=8, type=int)
     parser.add_argument('--output_root', default='datasets/AugmentedDatasets')
     parser.add_argument('--epochs', default=2, type=int, help='the reference always runs 2 (preprocess.py:552)')
+    parser.add_argument('--reader_compat', action='store_true',
+                        help="also store the `augment_img` key the reference's dataloader.py reads but its writer omits")
     return parser.parse_args(argv)
 
 
@@ -252,7 +260,8 @@ def run(dataset, output_dir: str, is_stereo: bool, args, epochs=2) -> Dict[str, 
     per-image reseeding (12345 + img_idx + epoch_idx * len(dataset))."""
     device = f"cuda:{args.gpu}"
     writer = NpzWriter(threads=args.writer_threads)
-    ppa = PreprocessPlusAugment(device=device, inpaint=None if args.no_inpaint else "reference", writer=writer)
+    ppa = PreprocessPlusAugment(device=device, inpaint=None if args.no_inpaint else "reference", writer=writer,
+                                reader_compat=getattr(args, "reader_compat", False))
     rng = sweep.shard_range(len(dataset), args.split, args.split_id)
     epochs = getattr(args, "epochs", epochs)
     for epoch_idx in range(epochs):

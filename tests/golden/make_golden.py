@@ -382,6 +382,41 @@ def preprocess_case(pp, ref_utils):
     return out
 
 
+def reader_case(pp, ref_utils):
+    """The reference's training reader (dataloader.AugmentedDataset.getitem_from_npz / DepthToFlowDataset, dataloader.py:79-232)
+    on files built from the preprocess_case fixture, with the `augment_img` key its writer omits added (0 for *_1, 1 for *_2).
+    Records (img0, img1, flow, img0_depth, label) for a few (file, group, seed) combinations."""
+    import tempfile
+
+    import dataloader as ref_dl
+
+    g = np.load(HERE / "preprocess_case.npz")
+    out = {}
+    cases = [("1_5_1", 1, 3, None, True), ("2_3_2", 2, 4, (16, 24), True), ("0_0_2", 0, 5, (20, 20), False), ("0_9_1", 0, 6, None, True)]
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(f"{tmp}/group.npz", img_depth_flow=g["group__data"])
+        for k, (stem, grp, seed, crop, norm) in enumerate(cases):
+            np.savez(f"{tmp}/{stem}.npz", img_depth_flow=g[f"{stem}__data"], augment_flow_type=g[f"{stem}__type"],
+                     augment_img=int(stem[-1]) - 1)
+            ds = ref_dl.AugmentedDataset(normalize_dataset=norm, crop_size=crop, do_flip=True)
+            np.random.seed(seed)
+            res = ds.getitem_from_npz(f"{tmp}/{stem}.npz", f"{tmp}/group.npz", grp, 0)
+            assert len(res) == 5
+            for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+                out[f"aug{k}_{name}"] = t.numpy()
+            out[f"aug{k}_meta"] = np.array([grp, seed, -1 if crop is None else crop[0], -1 if crop is None else crop[1], int(norm)])
+            out[f"aug{k}_stem"] = np.array(stem)
+        # DepthToFlowDataset crops with undefined h, w (dataloader.py:221): only the crop-free call runs in the reference
+        for k, (grp, seed) in enumerate([(0, 7), (1, 8), (2, 9)]):
+            ds = ref_dl.DepthToFlowDataset(crop_size=None, do_flip=True)
+            np.random.seed(seed)
+            res = ds.getitem_from_npz(f"{tmp}/group.npz", grp, 0)
+            for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+                out[f"d2f{k}_{name}"] = t.numpy()
+            out[f"d2f{k}_meta"] = np.array([grp, seed])
+    return out
+
+
 def main():
     torch.set_num_threads(1)
     pp, ref_utils, ref_geo, ref_bil, RefFW = install_reference()
@@ -395,6 +430,7 @@ def main():
         "pipeline_case": lambda: pipeline_case(pp, ref_utils),
         "inpaint_case": lambda: inpaint_case(pp, ref_utils),
         "preprocess_case": lambda: preprocess_case(pp, ref_utils),
+        "reader_case": lambda: reader_case(pp, ref_utils),
     }
     only = set(sys.argv[1:])
     for name, job in jobs.items():

@@ -829,6 +829,38 @@ def test_preprocess_plus_augment_writes_the_reference_files(pkg, golden, tmp_pat
     print(f"[preprocess] 121 files, worst differing fraction {worst:.2e}")
 
 
+def test_preprocess_files_feed_the_training_reader(pkg, tmp_path):
+    """8f-2 -> 8f-3 round trip: the driver's files (with the `augment_img` key the reference's reader wants) read back through
+    dataloader.AugmentedFolder / DepthToFlowDataset; the sample's planes are the written ones."""
+    from opticalflowfromdepth_b200 import dataloader as dl
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    h, w = 40, 56
+    ds = pp.SyntheticDataset(2, h, w)
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True, reader_compat=True)
+    for i in range(2):
+        pkg.synthesis.set_seed(12345 + i)
+        ppa(ds[i], str(tmp_path / str(i)), False)
+    ppa.close()
+    folder = dl.AugmentedFolder(str(tmp_path), 2, normalize_dataset=False, crop_size=(32, 48))
+    folder.do_flip = False
+    np.random.seed(0)
+    for i in range(2):
+        img0, img1, flow, depth, label = folder[i]
+        assert img0.shape == (3, 32, 48) and img1.shape == (3, 32, 48) and flow.shape == (2, 32, 48) and depth.shape == (1, 32, 48)
+        assert label.shape == (4,) and float(label.sum()) == 1.0 and bool(torch.isfinite(flow).all())
+    z = np.load(tmp_path / "0" / "1_6_2.npz")
+    assert sorted(z.files) == ["augment_flow_type", "augment_img", "img_depth_flow"] and int(z["augment_img"]) == 1
+    plain = dl.AugmentedDataset(normalize_dataset=False, do_flip=False)
+    img0, img1, flow, depth, label = plain.getitem_from_npz(tmp_path / "0" / "1_6_2.npz", tmp_path / "0" / "group.npz", 1)
+    grp = np.load(tmp_path / "0" / "group.npz")["img_depth_flow"]
+    assert eq(img0, grp[4:7]) and eq(depth, grp[7:8]) and eq(flow, z["img_depth_flow"][0:2]) and eq(img1, z["img_depth_flow"][4:7])
+    assert label.tolist() == [0, 0, 1, 0]
+    d2f = dl.DepthToFlowDataset(do_flip=False).getitem_from_npz(tmp_path / "1" / "group.npz", 2)
+    g1 = np.load(tmp_path / "1" / "group.npz")["img_depth_flow"]
+    assert eq(d2f[0], g1[0:3]) and eq(d2f[1], g1[8:11]) and eq(d2f[2], g1[20:22])
+
+
 def test_preprocess_float64_dataset_depth_and_stereo_input(pkg, tmp_path):
     """Dataset-shaped inputs: float64 depth (cv2.imread(...).astype(float)) and the stereo triple (img0, img1, disp0) of
     DIML (preprocess.py:350-355).  Pair 0->1 equals the oracle fed with the float64 depth."""

@@ -165,3 +165,42 @@ def test_special_flow_params_follow_the_reference_draw_order():
         for _ in range(n_calls):
             synthesis.get_random(1, 0)
         assert torch.equal(after, torch.rand(1))
+
+
+def test_reader_matches_the_reference_dataloader(golden, tmp_path):
+    """dataloader.AugmentedDataset / DepthToFlowDataset .getitem_from_npz vs the reference's own reader run on the same
+    files with the same np.random seed (golden reader_case, generated by tests/golden/make_golden.py): bit-exact.  Also:
+    the `augment_img` key may be absent (inferred from the file name), which is how the reference's writer leaves it."""
+    import numpy as np
+
+    from opticalflowfromdepth_b200 import dataloader as dl
+
+    g, pc = golden("reader_case"), golden("preprocess_case")
+    np.savez(tmp_path / "group.npz", img_depth_flow=pc["group__data"])
+    k = 0
+    while f"aug{k}_meta" in g:
+        grp, seed, ch, cw, norm = (int(v) for v in g[f"aug{k}_meta"])
+        stem = str(g[f"aug{k}_stem"])
+        for with_key in (True, False):
+            extra = {"augment_img": int(stem[-1]) - 1} if with_key else {}
+            np.savez(tmp_path / f"{stem}.npz", img_depth_flow=pc[f"{stem}__data"], augment_flow_type=pc[f"{stem}__type"], **extra)
+            ds = dl.AugmentedDataset(normalize_dataset=bool(norm), crop_size=None if ch < 0 else (ch, cw), do_flip=True)
+            np.random.seed(seed)
+            res = ds.getitem_from_npz(tmp_path / f"{stem}.npz", tmp_path / "group.npz", grp, 0)
+            for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+                assert np.array_equal(t.numpy(), g[f"aug{k}_{name}"]), (k, name, with_key)
+        k += 1
+    assert k == 4
+    k = 0
+    while f"d2f{k}_meta" in g:
+        grp, seed = (int(v) for v in g[f"d2f{k}_meta"])
+        np.random.seed(seed)
+        res = dl.DepthToFlowDataset(crop_size=None).getitem_from_npz(tmp_path / "group.npz", grp, 0)
+        for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+            assert np.array_equal(t.numpy(), g[f"d2f{k}_{name}"]), (k, name)
+        k += 1
+    assert k == 3
+    # the crop the reference cannot do (undefined h, w at dataloader.py:221) works here
+    np.random.seed(1)
+    img0, img1, flow, depth, label = dl.DepthToFlowDataset(crop_size=(8, 12)).getitem_from_npz(tmp_path / "group.npz", 1, 0)
+    assert img0.shape == (3, 8, 12) and flow.shape == (2, 8, 12) and depth.shape == (1, 8, 12) and label.tolist() == [1, 0, 0, 0]
