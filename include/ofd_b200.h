@@ -181,6 +181,21 @@ int ofd_normalize_depth(const void* depth, int dtype, int B, int H, int W, void*
 int ofd_normalize_depth_ragged(const void* depth, int dtype, int n_images, const size_t* count_host,
                                const size_t* offset_host, void* out, void* scratch, ofd_stream_t stream);
 
+/*
+ * ofd_depth_from_png — the arithmetic of the reference's depth loaders after cv2.imread, on the device, so a
+ * depth map crosses PCIe as its 8/16-bit PNG payload instead of float64:
+ *   OFD_SRC_RELDEPTH  = utils.get_depth(smooth=True) (utils.py:47-59) with utils.smooth_closer (utils.py:118-121):
+ *                       depth = 1 / (255 - min(v, 240))
+ *   OFD_SRC_DISPARITY = utils.get_disparity (utils.py:61-72) + Convert.disparity_to_depth (preprocess.py:257-262):
+ *                       depth = (1 / (v * 63 / 255 + 0.005)) * 50   (torch evaluates int / tensor as reciprocal * int)
+ * evaluated in float64 in numpy's / torch's op order; depth_dtype OFD_F64 (what the reference holds) or OFD_F32 (that value
+ * rounded once).  src: n samples of src_bits (8 or 16) bits; the result feeds ofd_normalize_depth.
+ */
+#define OFD_SRC_RELDEPTH 0
+#define OFD_SRC_DISPARITY 1
+int ofd_depth_from_png(const void* src, int src_bits, int kind, size_t n, void* depth, int depth_dtype,
+                       ofd_stream_t stream);
+
 /* ofd_fix_warped_depth — utils.fix_warped_depth (utils.py:123-126), in place: 0 -> 100, > 99.5 -> 100. */
 int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream);
 

@@ -13,6 +13,7 @@ LIB_PATH = Path(os.environ["OFD_LIB_PATH"]) if os.environ.get("OFD_LIB_PATH") el
 
 F32, F64 = 0, 1
 EPI_NONE, EPI_CONCAT, EPI_BACK = 0, 1, 2
+SRC_RELDEPTH, SRC_DISPARITY = 0, 1
 MAX_CHANNELS = 8
 CNT_HIT, CNT_HOLE, CNT_COLLISION, CNT_DROPPED, CNT_TIE_SRC, CNT_FRAMES, CNT_PAIRS, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 6, 8
 
@@ -35,6 +36,7 @@ SIGNATURES = {
     "ofd_reproject_pair": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ofd_normalize_depth_ragged": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
+    "ofd_depth_from_png": (_i, [_p, _i, _i, _sz, _p, _i, _p]),
     "ofd_fix_warped_depth": (_i, [_p, _sz, _p]),
     "ofd_inpaint_mask": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofd_special_flow": (_i, [_i, _p, _i, _i, _p, _p, _p]),

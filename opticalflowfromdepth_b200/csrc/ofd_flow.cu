@@ -342,6 +342,26 @@ __global__ void __launch_bounds__(256) inpaint_mask_kernel(const float* __restri
     mask[base + p] = (unsigned char)(1 - hp);
 }
 
+// ---- depth loaders' arithmetic (utils.get_depth / get_disparity + Convert.disparity_to_depth) ----------------
+// float64 end to end as numpy / torch evaluate it; the float32 output is the float64 value rounded once.
+template <typename SRC, typename OUT>
+__global__ void __launch_bounds__(256) depth_from_png_kernel(const SRC* __restrict__ src, int kind, size_t n, OUT* __restrict__ out) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        double v = (double)src[p];
+        double d;
+        if (kind == OFD_SRC_RELDEPTH) {
+            if (v > 240.0) v = 240.0;                      // utils.py:119
+            d = __ddiv_rn(1.0, __dsub_rn(255.0, v));       // utils.py:120
+        } else {
+            const double disp = __ddiv_rn(__dmul_rn(v, 63.0), 255.0);  // utils.py:66
+            // preprocess.py:258-261: `50 / (disparity + 0.005)` with an int numerator is Tensor.__rtruediv__, which torch
+            // evaluates as reciprocal() * 50 - two roundings, reproduced here
+            d = __dmul_rn(__ddiv_rn(1.0, __dadd_rn(disp, 0.005)), 50.0);
+        }
+        out[p] = (OUT)d;
+    }
+}
+
 static unsigned blocks_for(size_t n, unsigned per_block, unsigned cap) {
     size_t g = (n + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -502,6 +522,25 @@ int ofd_normalize_depth_ragged(const void* depth, int dtype, int n_images, const
         if (rc) return rc;
     }
     return OFD_OK;
+}
+
+int ofd_depth_from_png(const void* src, int src_bits, int kind, size_t n, void* depth, int depth_dtype, ofd_stream_t stream) {
+    const char* fn = "ofd_depth_from_png";
+    if (src_bits != 8 && src_bits != 16) return fail(OFD_E_DTYPE, "%s: src_bits must be 8 or 16", fn);
+    if (kind != OFD_SRC_RELDEPTH && kind != OFD_SRC_DISPARITY) return fail(OFD_E_ARG, "%s: bad kind %d", fn, kind);
+    if (depth_dtype != OFD_F32 && depth_dtype != OFD_F64) return fail(OFD_E_DTYPE, "%s: bad depth dtype %d", fn, depth_dtype);
+    if (n == 0) return OFD_OK;
+    if (!src || !depth) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = blocks_for(n, 256 * 4, 148 * 8);
+    if (src_bits == 8) {
+        if (depth_dtype == OFD_F64) depth_from_png_kernel<uint8_t, double><<<g, 256, 0, st>>>((const uint8_t*)src, kind, n, (double*)depth);
+        else depth_from_png_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)src, kind, n, (float*)depth);
+    } else {
+        if (depth_dtype == OFD_F64) depth_from_png_kernel<uint16_t, double><<<g, 256, 0, st>>>((const uint16_t*)src, kind, n, (double*)depth);
+        else depth_from_png_kernel<uint16_t, float><<<g, 256, 0, st>>>((const uint16_t*)src, kind, n, (float*)depth);
+    }
+    return check_launch(fn);
 }
 
 int ofd_fix_warped_depth(float* depth, size_t n, ofd_stream_t stream) {

@@ -250,6 +250,22 @@ def normalize_depth_ragged(packed, counts, offsets):
     return out
 
 
+def depth_from_png(raw, kind: str, dtype=torch.float64):
+    """The depth loaders' arithmetic on the device: `raw` is the decoded PNG payload as a uint8 / uint16 (stored as
+    int16 bit pattern is not accepted: pass torch.uint16) CUDA tensor of any shape; kind "reldepth" = utils.get_depth with
+    smooth_closer (utils.py:47-59,118-121), "disparity" = utils.get_disparity + Convert.disparity_to_depth (utils.py:61-72,
+    preprocess.py:257-262).  Returns a tensor of `raw`'s shape in float64 (the reference's dtype) or float32."""
+    if not raw.is_cuda or not raw.is_contiguous():
+        raise RuntimeError("raw must be a contiguous CUDA tensor")
+    bits = {torch.uint8: 8, torch.uint16: 16}.get(raw.dtype)
+    if bits is None:
+        raise TypeError(f"raw must be uint8 or uint16, got {raw.dtype}")
+    code = {"reldepth": _lib.SRC_RELDEPTH, "disparity": _lib.SRC_DISPARITY}[kind]
+    out = torch.empty(raw.shape, dtype=dtype, device=raw.device)
+    _lib.call("ofd_depth_from_png", _ptr(raw), bits, code, C.c_size_t(raw.numel()), _ptr(out), _DT[dtype], _stream(raw.device))
+    return out
+
+
 def fix_warped_depth_(depth):
     """utils.fix_warped_depth (utils.py:123-126), in place."""
     _check("depth", depth, dtype=torch.float32)

@@ -28,7 +28,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import geometry, ops, sweep, synthesis
+from . import _lib, geometry, ops, sweep, synthesis
 
 AUGMENT_TYPES = [0, 5, 6, 7, 1, 5, 6, 7, 2, 5, 6, 7]  # preprocess.py:455
 GROUP_CHANNELS = ("img0", "depth0", "img1", "depth1", "img2", "depth2", "img3", "depth3", "img2_prime", "depth2_prime",
@@ -143,9 +143,14 @@ class PreprocessPlusAugment(nn.Module):
         if not is_stereo:
             img0, depth = datas
         else:
-            img0, _img1_unused, disp0 = datas  # the real right view is ignored and overwritten (preprocess.py:352,361)
-            depth = synthesis.Convert.disparity_to_depth(disp0)
+            img0, _img1_unused, depth = datas  # the real right view is ignored and overwritten (preprocess.py:352,361)
         img0 = img0.to(dev).float().contiguous()[None]
+        if depth.dtype in (torch.uint8, torch.uint16):
+            # raw PNG payload: the loaders' arithmetic runs on the device, 1-2 B/px over PCIe instead of 8
+            with torch.cuda.device(dev):
+                depth = ops.depth_from_png(depth.to(dev).contiguous(), "disparity" if is_stereo else "reldepth")
+        elif is_stereo:
+            depth = synthesis.Convert.disparity_to_depth(depth)
         depth = depth.to(dev)
         if depth.dtype not in (torch.float32, torch.float64):
             depth = depth.float()
@@ -159,6 +164,8 @@ class PreprocessPlusAugment(nn.Module):
         if self.counters is None:
             self.counters = ops.new_counters(dev)
         res = synthesis.synthesize_group(img0, depth0, sBf, cam, inpaint=self.inpaint, counters=self.counters)
+        self.counters[_lib.CNT_FRAMES] += 1
+        self.counters[_lib.CNT_PAIRS] += len(GROUP_PAIRS)
         return res
 
     # ---- the 60 augmentations (preprocess.py:453-476) ------------------------------------------------------------------
@@ -295,6 +302,16 @@ def main(argv=None):
     (README.md:53 of the reference).  DIML / ReDWeb use the reference's own dataset classes (its `dataloader.py` must be
     importable, i.e. run from / with PYTHONPATH at the reference checkout)."""
     args = read_args(argv)
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        # torchrun: one process per GPU, the dataset sharded by rank exactly like the reference's manual --split / --split_id;
+        # the only collective is the end-of-run counter sum
+        import torch.distributed as dist
+
+        args.split, args.split_id = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+        args.gpu = int(os.environ.get("LOCAL_RANK", args.split_id))
+        torch.cuda.set_device(args.gpu)
+        if args.split > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", args.gpu))
     if args.dataset and args.dataset.startswith("synthetic"):
         parts = args.dataset.split(":")
         n = int(parts[1]) if len(parts) > 1 else 8
@@ -309,7 +326,8 @@ def main(argv=None):
         raise SystemExit(f"unknown --dataset {args.dataset!r}")
     t0 = time.time()
     totals = run(dataset, f"{args.output_root}/{name}", is_stereo, args)
-    print(f"done in {time.time() - t0:.1f} s: {totals}")
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"done in {time.time() - t0:.1f} s: {totals}")
 
 
 if __name__ == "__main__":

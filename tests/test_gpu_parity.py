@@ -829,6 +829,33 @@ def test_preprocess_plus_augment_writes_the_reference_files(pkg, golden, tmp_pat
     print(f"[preprocess] 121 files, worst differing fraction {worst:.2e}")
 
 
+def test_depth_loaders_arithmetic_on_the_device(pkg):
+    """8f-4: ofd_depth_from_png == utils.get_depth(smooth=True) / utils.get_disparity + Convert.disparity_to_depth evaluated
+    by numpy / torch in float64 on every 8-bit code and a sample of 16-bit ones (bit-exact), and the float32 output is that
+    value rounded once; the result then goes through normalize_depth like a dataset frame."""
+    for bits, codes in ((8, np.arange(256, dtype=np.uint8)), (16, np.random.default_rng(0).integers(0, 65536, 5000).astype(np.uint16))):
+        v = codes.astype(float)
+        rel = v.copy()
+        rel[rel > 240] = 240                      # utils.smooth_closer (utils.py:118-121)
+        with np.errstate(divide="ignore"):
+            rel = 1 / (255 - rel)
+        disp = v * 63 / 255                       # utils.get_disparity (utils.py:66)
+        dep = (50 / (torch.from_numpy(disp) + 0.005)).numpy()   # Convert.disparity_to_depth (preprocess.py:257-262)
+        raw = torch.from_numpy(codes).to(DEV)
+        for kind, want in (("reldepth", rel), ("disparity", dep)):
+            if bits == 16 and kind == "reldepth":
+                continue  # relative-depth maps are 8-bit (cv2.IMREAD_GRAYSCALE, utils.py:48)
+            got64 = pkg.ops.depth_from_png(raw, kind)
+            assert got64.dtype == torch.float64 and eq(got64, want), (bits, kind)
+            assert eq(pkg.ops.depth_from_png(raw, kind, torch.float32), want.astype(np.float32))
+    png = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (2, 1, 40, 56)).astype(np.uint8)).to(DEV)
+    d = pkg.ops.depth_from_png(png, "disparity")
+    nd = pkg.ops.normalize_depth(d)
+    for b in range(2):
+        want = oflow.normalize_depth(50 / (torch.from_numpy(png[b].cpu().numpy().astype(float) * 63 / 255) + 0.005)).numpy()
+        assert eq(nd[b], want)
+
+
 def test_preprocess_files_feed_the_training_reader(pkg, tmp_path):
     """8f-2 -> 8f-3 round trip: the driver's files (with the `augment_img` key the reference's reader wants) read back through
     dataloader.AugmentedFolder / DepthToFlowDataset; the sample's planes are the written ones."""
@@ -882,6 +909,12 @@ def test_preprocess_float64_dataset_depth_and_stereo_input(pkg, tmp_path):
     assert eq(grp["depth1"][0], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v)).numpy())
     assert eq(grp["flow01"][0], flow64.astype(np.float32))
     assert grp["depth0"].dtype == torch.float32 and eq(grp["depth0"][0], d64.astype(np.float32))
+    # the same frame with the disparity PNG payload handed over as uint8: decoded on the device, identical group
+    codes = np.random.default_rng(1).integers(1, 255, (1, h, w)).astype(np.uint8)
+    pkg.synthesis.set_seed(99)
+    grp8 = ppa.synthesize((torch.from_numpy(img), torch.from_numpy(img), torch.from_numpy(codes)), is_stereo=True)
+    for name in grp:
+        assert torch.equal(grp[name], grp8[name]), name
     ppa.close()
 
 
