@@ -250,14 +250,16 @@ def sample_special_params(kinds, size, generator=None):
     reference_draws=True) keeps the reference's sequence."""
     h, w = size
     B = len(kinds)
-    sign = (torch.randint(0, 2, (B, 3), generator=generator) * 2 - 1).to(torch.float32)
-    u = torch.rand((B, 3), generator=generator)
-    cx = sign[:, 0] * (u[:, 0] * (w / 4) + (w / 2)) + w / 2
-    cy = sign[:, 1] * (u[:, 1] * (h / 4) + (h / 2)) + h / 2
-    theta = torch.deg2rad(sign[:, 2] * (u[:, 2] * 2 + 8))
-    shear = sign[:, 2] * (u[:, 2] * 0.15 + 0.2)
-    cos, sin, ncos, nsin = torch.cos(theta), torch.sin(theta), torch.cos(-theta), torch.sin(-theta)
-    cols = torch.stack((cx, cy, cos, -sin, sin, cos, ncos, -nsin, nsin, ncos, shear), 1).tolist()
+    f32 = np.float32
+    sign = (torch.randint(0, 2, (B, 3), generator=generator).numpy() * 2 - 1).astype(f32)
+    u = torch.rand((B, 3), generator=generator).numpy()
+    # float32 numpy arithmetic from here on: ~20 us per batch instead of ~15 small torch ops
+    cx = sign[:, 0] * (u[:, 0] * f32(w / 4) + f32(w / 2)) + f32(w / 2)
+    cy = sign[:, 1] * (u[:, 1] * f32(h / 4) + f32(h / 2)) + f32(h / 2)
+    theta = (sign[:, 2] * (u[:, 2] * f32(2) + f32(8))) * f32(math.pi / 180.0)
+    shear = sign[:, 2] * (u[:, 2] * f32(0.15) + f32(0.2))
+    cos, sin = np.cos(theta), np.sin(theta)
+    cols = np.stack((cx, cy, cos, -sin, sin, cos, cos, sin, -sin, cos, shear), 1).astype(f32).tolist()
     out = []
     for b in range(B):
         k = int(kinds[b])
