@@ -14,7 +14,7 @@ from torch import nn
 
 from . import _lib, ops
 
-__all__ = ["BackprojectDepth", "Project3D", "transformation_from_parameters"]
+__all__ = ["BackprojectDepth", "Project3D", "transformation_from_parameters", "rot_from_axisangle", "get_translation_matrix"]
 
 
 class BackprojectDepth(nn.Module):
@@ -83,6 +83,16 @@ def _translation_matrix(t):
     M = torch.eye(4, dtype=torch.float32, device=t.device).repeat(t.shape[0], 1, 1)
     M[:, :3, 3] = t.contiguous().view(-1, 3)
     return M
+
+
+def rot_from_axisangle(vec):
+    """geometry.rot_from_axisangle (geometry.py:108-153): axis-angle [b,1,3] -> rotation as a [b,4,4] matrix."""
+    return _skew_free_rotation(vec)
+
+
+def get_translation_matrix(translation_vector):
+    """geometry.get_translation_matrix (geometry.py:91-105): [b,1,3] -> homogeneous translation [b,4,4]."""
+    return _translation_matrix(translation_vector)
 
 
 def transformation_from_parameters(axisangle, translation, invert=False):

@@ -36,6 +36,11 @@ def test_transformation_from_parameters_invert():
     assert torch.allclose(M @ Mi, torch.eye(4)[None], atol=1e-6)
     cam = geometry.camera_constants(*synthesis.Plausible.K((48, 64)), M)
     assert cam.shape == (1, 21) and cam.dtype == torch.float32
+    # the reference's helper names (geometry.py:91-153) are part of the drop-in surface
+    R, Tm = geometry.rot_from_axisangle(aa), geometry.get_translation_matrix(tr)
+    assert R.shape == (1, 4, 4) and Tm.shape == (1, 4, 4) and torch.equal(Tm @ R, M)
+    assert torch.allclose(R[:, :3, :3] @ R[:, :3, :3].transpose(1, 2), torch.eye(3)[None], atol=1e-6)
+    assert torch.equal(Tm[0, :3, 3], tr[0, 0]) and torch.equal(Tm[0, :3, :3], torch.eye(3))
 
 
 def test_special_flow_parameters_follow_reference_draws(golden, monkeypatch):
