@@ -107,7 +107,8 @@ def test_dropin_modules_expose_the_reference_names(monkeypatch):
     assert callable(fw_cuda.forward_warping)
     m = fw.FW("cuda:0")
     assert hasattr(m, "forward") and hasattr(m, "set_shape") and m.device == "cuda:0"
-    assert geo.__all__ == ["BackprojectDepth", "Project3D", "transformation_from_parameters"]
+    assert geo.__all__ == ["BackprojectDepth", "Project3D", "transformation_from_parameters", "rot_from_axisangle", "get_translation_matrix"]
+    assert callable(geo.rot_from_axisangle) and callable(geo.get_translation_matrix)
     assert all(hasattr(geo, n) for n in geo.__all__)
     assert bil.__all__ == ["sparse_bilateral_filtering"]
     import inspect
