@@ -23,12 +23,16 @@ __all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "aug
 
 
 # ---- utils.py helpers ------------------------------------------------------------------------------------------
-def set_seed(seed=42):
-    """utils.set_seed (utils.py:178-188) without the cudnn switches."""
+def set_seed(seed=42, loader=None):
+    """utils.set_seed (utils.py:178-188) without the cudnn switches; `loader` is accepted and seeded like the reference does."""
     torch.manual_seed(seed)
     torch.cuda.manual_seed_all(seed)
     np.random.seed(seed)
     random.seed(seed)
+    try:
+        loader.sampler.generator.manual_seed(seed)
+    except AttributeError:
+        pass
 
 
 def get_random(random_range, random_begin, random_sign=True):
