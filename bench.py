@@ -259,7 +259,7 @@ def run_ours(args):
                    "frames_per_step_per_gpu": F, "H": H, "W": W, "parallelism": f"frames sharded by image index over {world} GPU(s), no collective on the hot path",
                    "l2": f"inputs {F * 4 * H * W * 4 / 1e6:.0f} MB + outputs {F * 10 * H * W * 4 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)"},
         "gpu_launches": K,
-        "roofline": {"bound": "hbm", "kernel": "pair_rows_persistent<float,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pair_rows_persistent<float,2,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_px": PAIR_BYTES_PER_PX, "bytes_per_launch": PAIR_BYTES_PER_PX * H * W * F},

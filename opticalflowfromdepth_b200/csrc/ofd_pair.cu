@@ -232,13 +232,18 @@ struct PairPlan {
     }
 };
 
-template <typename DT, int NITER>
+template <typename DT, int NITER, bool GROUPED>
 __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __restrict__ img0, const DT* __restrict__ depth0,
                                                            const float* __restrict__ sBf, float* __restrict__ img1,
                                                            float* __restrict__ depth1, float* __restrict__ back_flow,
                                                            float* __restrict__ flow, float* __restrict__ valid,
                                                            float* __restrict__ collision, uint64_t* __restrict__ counters,
-                                                           int B, int H, int W, int in_stages_rt, int out_stages_rt) {
+                                                           int B, int H, int W, int G, int in_stages_rt, int out_stages_rt) {
+    // A work unit is G consecutive rows of one frame, handled as ONE virtual row of VW = G * W pixels: the rows are contiguous in
+    // every plane, so each plane still moves with one bulk copy per unit; sources stay in their row, so the row-local z-buffer
+    // only needs the virtual target index r * W + tx.  G > 1 (a) makes narrow rows long enough to amortise the per-unit barrier /
+    // TMA-issue chain and (b) restores the 16-byte size / address alignment TMA needs when W is not a multiple of 4 (G even for
+    // W % 4 == 2, G % 4 == 0 for odd W; the launcher only takes this kernel when H is a multiple of that alignment).
 #ifdef OFD_PAIR_IN_STAGES
     constexpr int kInStages = OFD_PAIR_IN_STAGES, kOutStages = OFD_PAIR_OUT_STAGES;  // tuning builds: compile-time rings
 #else
@@ -247,39 +252,51 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t hw = (size_t)H * W;
-    const int total_rows = B * H;
+    // GROUPED = false is the G == 1 specialisation: the index arithmetic below folds back to the one-row form
+    const int VW = GROUPED ? G * W : W;
+    const int upf = GROUPED ? (H + G - 1) / G : H;  // units per frame
+    const int total_rows = B * upf;                 // work units
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stage][0 depth, 1 colour]
     float* base = reinterpret_cast<float*>(smem_raw + 128);
     typedef PairPlan<DT> Plan;
-    auto in_stage = [&](int s) { return base + (size_t)s * Plan::kIn * W; };
-    auto out_stage = [&](int s) { return base + (size_t)(kInStages * Plan::kIn + s * Plan::kOut) * W; };
-    float* misc = base + (size_t)(kInStages * Plan::kIn + kOutStages * Plan::kOut) * W;
+    auto in_stage = [&](int s) { return base + (size_t)s * Plan::kIn * VW; };
+    auto out_stage = [&](int s) { return base + (size_t)(kInStages * Plan::kIn + s * Plan::kOut) * VW; };
+    float* misc = base + (size_t)(kInStages * Plan::kIn + kOutStages * Plan::kOut) * VW;
     float* zero_row = misc;
-    float* negzero_row = misc + W;
-    uint32_t* sord = reinterpret_cast<uint32_t*>(misc + 2 * (size_t)W);
-    uint32_t* sidx = sord + W;
-    float* sdepth32 = misc + 4 * (size_t)W;  // only when DT is double
+    float* negzero_row = misc + VW;
+    uint32_t* sord = reinterpret_cast<uint32_t*>(misc + 2 * (size_t)VW);
+    uint32_t* sidx = sord + VW;
+    float* sdepth32 = misc + 4 * (size_t)VW;  // only when DT is double
 
     if (tid == 0) {
         for (int k = 0; k < 2 * kInStages; ++k) mbar_init(&bars[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < W; i += nt) {
+    for (int i = tid; i < VW; i += nt) {
         zero_row[i] = 0.0f;
         negzero_row[i] = -0.0f;
     }
     fence_async_smem();
     __syncthreads();
+    // the thread's pixels are the same virtual indices in every unit: row-in-unit and column are computed once
+    int vr[NITER], vi[NITER];
+#pragma unroll
+    for (int k = 0; k < NITER; ++k) {
+        const int v = tid + k * nt;
+        vr[k] = GROUPED ? v / W : 0;
+        vi[k] = GROUPED ? v - vr[k] * W : v;
+    }
 
     auto issue_loads = [&](int row, int s) {  // one thread (the loader)
-        const int b = row / H, j = row - b * H;
+        const int b = row / upf, j = GROUPED ? (row - b * upf) * G : row - b * upf;
+        const int n = GROUPED ? ((H - j) < G ? (H - j) : G) * W : W;  // pixels of this unit
         DT* sraw = reinterpret_cast<DT*>(in_stage(s));
-        float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
-        mbar_expect_tx(&bars[2 * s], (unsigned)(W * sizeof(DT)));
-        bulk_g2s(sraw, depth0 + (size_t)b * hw + (size_t)j * W, (unsigned)(W * sizeof(DT)), &bars[2 * s]);
-        mbar_expect_tx(&bars[2 * s + 1], (unsigned)(3 * W * 4));
+        float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)VW;
+        mbar_expect_tx(&bars[2 * s], (unsigned)(n * sizeof(DT)));
+        bulk_g2s(sraw, depth0 + (size_t)b * hw + (size_t)j * W, (unsigned)(n * sizeof(DT)), &bars[2 * s]);
+        mbar_expect_tx(&bars[2 * s + 1], (unsigned)(3 * n * 4));
         const float* g = img0 + (size_t)b * 3 * hw + (size_t)j * W;
-        for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * W, g + c * hw, (unsigned)(W * 4), &bars[2 * s + 1]);
+        for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * VW, g + c * hw, (unsigned)(n * 4), &bars[2 * s + 1]);
     };
 
     int row = blockIdx.x;
@@ -294,16 +311,17 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     unsigned ph = 0;
     for (; row < total_rows; row += gridDim.x, s = (s + 1 == kInStages ? 0 : s + 1), so = (so + 1 == kOutStages ? 0 : so + 1),
                              s_fill = (s_fill + 1 == kInStages ? 0 : s_fill + 1), ph ^= (s == 0 ? 1u : 0u)) {
-        const int b = row / H, j = row - b * H;
+        const int b = row / upf, j = GROUPED ? (row - b * upf) * G : row - b * upf;
+        const int NV = GROUPED ? ((H - j) < G ? (H - j) : G) * W : W;  // pixels of this unit (the last unit of a frame may be shorter)
         const DT* sraw = reinterpret_cast<const DT*>(in_stage(s));
-        const float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)W;
+        const float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)VW;
         const float* sdep = sizeof(DT) == 4 ? reinterpret_cast<const float*>(sraw) : sdepth32;
         float* o_img = out_stage(so);
-        float* o_dep = o_img + 3 * (size_t)W;
-        float* o_bfx = o_dep + W;
-        float* o_flx = o_bfx + W;
-        float* o_val = o_flx + W;
-        float* o_col = o_val + W;
+        float* o_dep = o_img + 3 * (size_t)VW;
+        float* o_bfx = o_dep + VW;
+        float* o_flx = o_bfx + VW;
+        float* o_val = o_flx + VW;
+        float* o_col = o_val + VW;
 
         if (tid == loader) {
             // the stage being refilled was released by the barrier that ended row n-1
@@ -322,7 +340,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
 #pragma unroll
         for (int k = 0; k < NITER; ++k) {
             const int i = tid + k * nt;
-            if (i < W) sord[i] = 0xFFFFFFFFu, sidx[i] = 0xFFFFFFFFu;
+            if (i < NV) sord[i] = 0xFFFFFFFFu, sidx[i] = 0xFFFFFFFFu;
         }
         mbar_wait(&bars[2 * s], ph);
         __syncthreads();
@@ -332,17 +350,17 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         uint32_t tx[NITER], hi[NITER];
 #pragma unroll
         for (int k = 0; k < NITER; ++k) {
-            const int i = tid + k * nt;
+            const int i = tid + k * nt;  // virtual index: row vr[k] of the unit, column vi[k]
             tx[k] = T_DROPPED;
             hi[k] = 0;
-            if (i < W) {
+            if (i < NV) {
                 const DT d = sraw[i];
                 const DT fx = (sc / d) * (DT)-1.0;
-                DT px = (DT)(float)i + fx;
+                DT px = (DT)(float)vi[k] + fx;
                 if (px == px) {
                     px = px < (DT)0 ? (DT)0 : px;
                     px = px > (DT)(W - 1) ? (DT)(W - 1) : px;
-                    tx[k] = (uint32_t)(int)px;
+                    tx[k] = GROUPED ? (uint32_t)(vr[k] * W + (int)px) : (uint32_t)(int)px;
                 }
                 o_flx[i] = (float)fx;
                 if (sizeof(DT) == 8) sdepth32[i] = (float)d;
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
 #pragma unroll
         for (int k = 0; k < NITER; ++k) {
             const int t = tid + k * nt;
-            if (t < W) {
+            if (t < NV) {
                 const uint32_t h32 = sord[t];
                 const bool hit = h32 != 0xFFFFFFFFu;
                 const bool win = h32 < HI_NOWIN;
@@ -373,14 +391,14 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                 float r = 0.f, g = 0.f, bl = 0.f, dd = 0.f, bx = 0.f;
                 if (win) {
                     r = simg[src];
-                    g = simg[W + src];
-                    bl = simg[2 * W + src];
+                    g = simg[VW + src];
+                    bl = simg[2 * VW + src];
                     dd = sdep[src];
                     bx = o_flx[src] * -1.0f;
                 }
                 o_img[t] = r * v;
-                o_img[W + t] = g * v;
-                o_img[2 * W + t] = bl * v;
+                o_img[VW + t] = g * v;
+                o_img[2 * VW + t] = bl * v;
                 o_dep[t] = fix_depth(dd * v);
                 o_bfx[t] = bx * v;
                 o_val[t] = v;
@@ -399,9 +417,9 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         __syncthreads();
         if (tid == 0) {
             const size_t r1 = (size_t)b * hw + (size_t)j * W;
-            const unsigned rb = (unsigned)(W * 4);
+            const unsigned rb = (unsigned)(NV * 4);
             float* gi = img1 + (size_t)b * 3 * hw + (size_t)j * W;
-            for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * hw, o_img + (size_t)c * W, rb);
+            for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * hw, o_img + (size_t)c * VW, rb);
             bulk_s2g(depth1 + r1, o_dep, rb);
             float* gb = back_flow + (size_t)b * 2 * hw + (size_t)j * W;
             bulk_s2g(gb, o_bfx, rb);
@@ -432,6 +450,25 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
                                   uint64_t* counters, cudaStream_t st, bool* handled) {
     *handled = false;
     if ((long long)B * H > 0x7FFFFFFFll) return OFD_OK;
+    // rows per work unit: a multiple of the alignment group (1 / 2 / 4 rows for W % 4 == 0 / 2 / odd).  Measured on B200
+    // (profiles/r1/tune_pair_groups.txt): units of ~1900-2048 pixels (1024 threads x 2 px, one CTA per SM, deep rings) reach 92-93 %
+    // of the HBM peak at every width tried, 1000-1500 pixel units only 87-89 %; rows of 512-656 pixels are best left alone (two
+    // CTAs per SM with the deepest rings: 96.8 % on the 480x640 headline against 93.7 % with three rows per unit).
+    const int align_rows = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
+    if (H % align_rows != 0) return OFD_OK;  // a frame would end inside an alignment group: one-row kernel
+    int G;
+    if (align_rows == 1 && W >= 512 && W <= 656) {
+        G = 1;
+    } else {
+        G = (2048 / (align_rows * W)) * align_rows;
+        if (G < align_rows) G = align_rows;
+    }
+    if (const char* e = std::getenv("OFD_PAIR_GROUP")) {
+        const int g = std::atoi(e);
+        if (g > 0 && g % align_rows == 0) G = g;
+    }
+    if (G > H) G = (H / align_rows) * align_rows;
+    const int VW = G * W;
     // ring depths, tuned on B200 (profiles/r1/tune_pair.txt): the deepest plan that still lets two CTAs share an SM
 #ifdef OFD_PAIR_IN_STAGES
     static const int plans[][2] = {{OFD_PAIR_IN_STAGES, OFD_PAIR_OUT_STAGES}};
@@ -442,20 +479,24 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
     size_t smem = 0;
     for (int pass = 0; pass < 2 && !in_stages; ++pass)
         for (const auto& pl : plans) {
-            const size_t need = PairPlan<DT>::bytes(W, pl[0], pl[1]);
+            const size_t need = PairPlan<DT>::bytes(VW, pl[0], pl[1]);
             if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
                 in_stages = pl[0], out_stages = pl[1], smem = need;
                 break;
             }
         }
     if (!in_stages) return OFD_OK;  // row too wide for shared memory: fall back to the one-row kernel
-    // each thread owns NITER pixels of a row; threads = ceil(W / NITER) rounded up to a warp
+    // each thread owns NITER pixels of a (virtual) row; threads = ceil(VW / NITER) rounded up to a warp
     int niter = OFD_PAIR_NITER;
-    while ((W + niter - 1) / niter > 1024) niter *= 2;
+    while ((VW + niter - 1) / niter > 1024) niter *= 2;
     if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
-    int threads = ((W + niter - 1) / niter + 31) / 32 * 32;
-    auto kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER>
-                                        : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER> : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER>);
+    int threads = ((VW + niter - 1) / niter + 31) / 32 * 32;
+    auto kern = G == 1 ? (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, false>
+                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, false>
+                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, false>))
+                       : (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, true>
+                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, true>
+                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, true>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     int dev = 0, sms = 0, per_sm = 0;
@@ -464,11 +505,12 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
     long long grid = (long long)sms * per_sm;
-    if (grid > (long long)B * H) grid = (long long)B * H;
+    const long long units = (long long)B * ((H + G - 1) / G);
+    if (grid > units) grid = units;
     if (std::getenv("OFD_DEBUG"))
-        fprintf(stderr, "[ofd] %s: persistent pair kernel: in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM x %d SMs -> grid %lld\n",
-                fn, in_stages, out_stages, niter, threads, smem, per_sm, sms, grid);
-    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W,
+        fprintf(stderr, "[ofd] %s: persistent pair kernel: G=%d rows/unit in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM x %d SMs -> grid %lld\n",
+                fn, G, in_stages, out_stages, niter, threads, smem, per_sm, sms, grid);
+    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W, G,
                                                 in_stages, out_stages);
     *handled = true;
     return check_launch(fn);
@@ -479,8 +521,10 @@ template <typename DT>
 static int launch_pair(const char* fn, const float* img0, const DT* depth0, const float* sBf, int B, int H, int W,
                        float* img1, float* depth1, float* back_flow, float* flow, float* valid, float* collision,
                        uint64_t* counters, cudaStream_t st) {
-    const bool aligned = (W % 4 == 0) && (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 |
-                                            (uintptr_t)back_flow | (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
+    // TMA needs 16-byte addresses and sizes: plane bases are aligned when the buffers are and H*W % 4 == 0 (checked through H %
+    // align_rows in launch_pair_persistent); rows that are not a multiple of 4 pixels travel in groups of 2 or 4 rows
+    const bool aligned = (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 |
+                           (uintptr_t)back_flow | (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
     if (aligned) {
         bool handled = false;
         int rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,

@@ -237,7 +237,10 @@ def test_against_the_reference_kernel_itself(pkg):
 # ---------------------------------------------------------------------------------------------------------------
 # fused virtual-stereo pair
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("h,w", [(480, 640), (37, 53), (64, 4), (5, 130), (1, 1)])
+# sizes: TMA row groups of 1 / 2 / 4 rows (W % 4 == 0 / 2 / odd), frames that end inside a unit, the one-row fallback (H not a
+# multiple of the alignment group), a unit wider than 1024 threads x 2 pixels, degenerate frames
+@pytest.mark.parametrize("h,w", [(480, 640), (37, 53), (64, 4), (5, 130), (1, 1), (36, 53), (38, 130), (7, 640), (96, 642),
+                                 (8, 333), (12, 2561), (33, 496), (368, 496)])
 def test_disparity_pair_vs_oracle(pkg, h, w):
     rng = np.random.default_rng(h * 1000 + w)
     B = 3
@@ -288,6 +291,16 @@ def test_pair_equals_general_splat_path(pkg):
     img1, d1, back, flow, valid, coll = pkg.ops.disparity_pair(img, depth, sBf)
     flow2 = pkg.ops.disparity_flow(depth, sBf)
     assert torch.equal(flow, flow2)
+    # the result does not depend on how many rows travel per work unit
+    import os
+    for g in ("1", "3", "5"):
+        os.environ["OFD_PAIR_GROUP"] = g
+        try:
+            again = pkg.ops.disparity_pair(img, depth, sBf)
+        finally:
+            os.environ.pop("OFD_PAIR_GROUP", None)
+        for x, y in zip(again, (img1, d1, back, flow, valid, coll)):
+            assert torch.equal(x, y), g
     i2, d2, b2, v2, c2, raw = pkg.ops.frame_splat(img, depth, flow2, None, want_raw_valid=True)
     assert torch.equal(img1, i2) and torch.equal(d1, d2) and torch.equal(back, b2) and torch.equal(valid, v2)
     assert torch.equal(coll, c2) and torch.equal(raw, v2)
