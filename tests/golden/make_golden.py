@@ -263,6 +263,40 @@ def pipeline_case(pp, ref_utils):
     return dict(img0=img0, raw_depth=raw, group=group.astype(np.float32), sBf=np.float32(sBf.item()), T1=T1.numpy())
 
 
+def pipeline_case_f64(pp, ref_utils):
+    """pipeline_case with the depth the reference's loaders really deliver: float64 (cv2.imread(...).astype(float),
+    utils.py:48,62).  The reference then keeps float64 in normalize_depth, the disparity flow, the FW target computation and the
+    flow composition; the group tensor comes out float64."""
+    rng = np.random.default_rng(2025)
+    h, w = 40, 56
+    img0 = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+    raw = diml_depth(rng, h, w, quant=False).astype(np.float64)  # continuous depth: float32 evaluation could move targets
+    grabbed = {}
+
+    class Stop(Exception):
+        pass
+
+    def fake_savez(path, **kw):
+        grabbed.update(kw)
+        raise Stop()
+
+    ppa = pp.PreprocessPlusAugment(device="cpu")
+    ref_utils.set_seed(12345 + 12)
+    real = np.savez_compressed
+    np.savez_compressed = fake_savez
+    pp.os.makedirs = lambda *a, **k: None
+    try:
+        with redirect_stdout(io.StringIO()):
+            ppa((torch.from_numpy(img0), torch.from_numpy(raw.copy())[None]), "/tmp/ofd_golden/0", is_stereo=False)
+    except Stop:
+        pass
+    finally:
+        np.savez_compressed = real
+    group = grabbed["img_depth_flow"]
+    assert group.shape == (44, h, w) and group.dtype == np.float64
+    return dict(img0=img0, raw_depth=raw, group=group)
+
+
 def inpaint_case(pp, ref_utils):
     """The same pipeline with the reference's REAL utils.inpaint (utils.py:136-151; OpenCV Telea on the CPU).  Records
     the group tensor and, for each of the 5 inpaint calls, (valid, collision) and the mask handed to cv2.inpaint."""
@@ -428,6 +462,7 @@ def main():
         "bilateral_cases": lambda: bilateral_cases(ref_bil),
         "concat_back_cases": lambda: concat_back_cases(pp),
         "pipeline_case": lambda: pipeline_case(pp, ref_utils),
+        "pipeline_case_f64": lambda: pipeline_case_f64(pp, ref_utils),
         "inpaint_case": lambda: inpaint_case(pp, ref_utils),
         "preprocess_case": lambda: preprocess_case(pp, ref_utils),
         "reader_case": lambda: reader_case(pp, ref_utils),

@@ -496,6 +496,38 @@ def test_group_vs_reference_pipeline_golden(pkg, golden):
         print(f"[group] {k}: differing fraction {diff:.2e}")
 
 
+def test_group_float64_dataset_path_vs_reference_golden(pkg, golden):
+    """The reference's own pipeline fed with float64, continuous depth (golden pipeline_case_f64; its group tensor is float64).
+    Pair 0->1 is evaluated from the float64 depth here as there (float64 disparity and target): img1 / depth1 / back_flow01 are
+    bit-exact and flow01 is the reference's float64 flow rounded once.  The later pairs take depth0's / flow01's float32 rounding
+    (the reference keeps float64: <= 1.2e-7 relative), so they are held to the path's tolerance."""
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    g = golden("pipeline_case_f64")
+    grp = g["group"]
+    assert grp.dtype == np.float64
+    h, w = grp.shape[1:]
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    pkg.synthesis.set_seed(12345 + 12)
+    res = ppa.synthesize((torch.from_numpy(g["img0"]), torch.from_numpy(g["raw_depth"].copy())[None]), is_stereo=False)
+    ppa.close()
+    names = pp.GROUP_CHANNELS
+    widths = [3 if n.startswith("img") else (1 if n.startswith("depth") else 2) for n in names]
+    off = np.cumsum([0] + widths)
+    sl = {n: (int(off[k]), int(off[k + 1])) for k, n in enumerate(names)}
+    for k in ("img0", "img1", "depth1", "back_flow01"):   # float32-valued in the reference as well
+        a, b = sl[k]
+        assert eq(res[k][0].double(), grp[a:b]), k
+    for k in ("depth0", "flow01"):                         # float64 in the reference: ours is that value rounded once
+        a, b = sl[k]
+        assert eq(res[k][0], grp[a:b].astype(np.float32)), k
+    for k, (a, b) in sl.items():
+        got = res[k][0].cpu().numpy().astype(np.float64)
+        frac = float((np.abs(got - grp[a:b]) > 1e-3).mean())
+        assert frac <= 0.02, f"{k}: {frac:.4f} of the plane differs from the float64 reference"
+        print(f"[group f64] {k}: differing fraction {frac:.2e}")
+
+
 def test_frame_splat_vs_oracle_composition(pkg):
     img, depth = _cfg1_inputs(pkg, 2, 120, 160)
     flow = torch.cat([_six_dof_flow(pkg, depth[k:k + 1], 21 + k)[0] for k in range(2)])
