@@ -9,7 +9,9 @@ Random numbers are drawn on the host with torch's CPU generator in the reference
 from __future__ import annotations
 
 import math
+import os
 import random
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -73,7 +75,16 @@ def inpaint(img, valid, collision):
     with torch.cuda.device(im.device):
         mask = ops.inpaint_mask(v, c).cpu().numpy()
     im_u8 = im.permute(0, 2, 3, 1).to(torch.uint8).cpu().numpy()  # .astype(np.uint8): truncation, utils.py:147
-    out = np.stack([cv2.inpaint(np.ascontiguousarray(im_u8[b]), mask[b, 0], 3, cv2.INPAINT_TELEA) for b in range(im_u8.shape[0])])
+    n = im_u8.shape[0]
+
+    def fill(b):
+        return cv2.inpaint(np.ascontiguousarray(im_u8[b]), mask[b, 0], 3, cv2.INPAINT_TELEA)
+
+    if n > 1:  # OpenCV releases the GIL: the frames of a batch are filled on a pool of host threads
+        with ThreadPoolExecutor(max_workers=min(n, os.cpu_count() or 1)) as pool:
+            out = np.stack(list(pool.map(fill, range(n))))
+    else:
+        out = np.stack([fill(0)])
     res = torch.from_numpy(out.astype(np.float32)).permute(0, 3, 1, 2).contiguous().to(im.device)
     return res[0] if single else res
 

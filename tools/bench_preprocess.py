@@ -27,11 +27,12 @@ class Discard:
 def main():
     ds = pp.SyntheticDataset(64)
     n = 8
-    for label, writer, frames in (("discarding writer (device + D2H + host staging)", Discard(), n),
-                                  ("npz uncompressed, 16 threads, tmpfs", pp.NpzWriter(16, compress=False), n),
-                                  ("npz compressed (reference format), 16 threads, tmpfs", pp.NpzWriter(16, compress=True), 3)):
+    for label, writer, frames, inpaint in (("discarding writer (device + D2H + host staging)", Discard(), n, None),
+                                           ("same + utils.inpaint (OpenCV Telea, 95 calls/frame, host thread pool)", Discard(), 3, "reference"),
+                                           ("npz uncompressed, 16 threads, tmpfs", pp.NpzWriter(16, compress=False), n, None),
+                                           ("npz compressed (reference format), 16 threads, tmpfs", pp.NpzWriter(16, compress=True), 3, None)):
         with tempfile.TemporaryDirectory(dir="/dev/shm") as tmp:
-            ppa = pp.PreprocessPlusAugment("cuda:0", inpaint=None, writer=writer, quiet=True)
+            ppa = pp.PreprocessPlusAugment("cuda:0", inpaint=inpaint, writer=writer, quiet=True)
             synthesis.set_seed(1)
             ppa(ds[0], f"{tmp}/w", False)
             writer.drain()
@@ -43,7 +44,7 @@ def main():
             writer.drain()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / frames
-            print(f"{label:58s}: {dt*1e3:8.1f} ms/frame = {1/dt:6.2f} frames/s ({121/dt:7.0f} arrays/s, {300/dt:7.0f} flow pairs/s incl. augmented)", flush=True)
+            print(f"{label:75s}: {dt*1e3:8.1f} ms/frame = {1/dt:6.2f} frames/s ({121/dt:7.0f} arrays/s, {300/dt:7.0f} flow pairs/s incl. augmented)", flush=True)
             writer.close()
 
 
