@@ -29,6 +29,11 @@ namespace ofd {
 #ifndef OFD_BIL_RPT
 #define OFD_BIL_RPT 4
 #endif
+// float kernels: 6 CTAs per SM (<= 42 registers) hide the tile-load latency better than 3 CTAs at 72 registers (cfg2 step
+// 1.19 -> 1.06 ms); the double kernels keep their registers (the 49-key network alone holds 98 of them).
+#ifndef OFD_BIL_MINB
+#define OFD_BIL_MINB 6
+#endif
 constexpr int BIL_RPT = OFD_BIL_RPT;
 constexpr int BT_W = 32, BT_TY = 8, BT_H = BT_TY * BIL_RPT, MAX_WIN = 15;
 
@@ -236,19 +241,39 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     __syncthreads();
     // 4b. pixels without a discontinuity in their window keep their depth; the others are COMPACTED into a list, so the
     //     expensive selection below runs in full warps (an edge crossing the tile touches a few lanes of every row-warp)
+    //     A thread owns BIL_RPT CONSECUTIVE rows of one column, so the windows of its pixels overlap: each row mask is
+    //     loaded and counted once (BIL_RPT + win - 1 loads instead of BIL_RPT * win) and the window counts slide.
     const int c = tile_x * BT_W + threadIdx.x;
+    int n_disc_row[BIL_RPT];
+    if constexpr (WS > 0) {
+        const unsigned long long wmask = (1ull << WS) - 1ull;
+        int pc[BIL_RPT + WS - 1];
+#pragma unroll
+        for (int q = 0; q < BIL_RPT + WS - 1; ++q)
+            pc[q] = __popcll((s_rowmask[threadIdx.y * BIL_RPT + q] >> threadIdx.x) & wmask);
+#pragma unroll
+        for (int rr = 0; rr < BIL_RPT; ++rr) {
+            int n = 0;
+#pragma unroll
+            for (int dr = 0; dr < WS; ++dr) n += pc[rr + dr];
+            n_disc_row[rr] = n;
+        }
+    } else {
+        const unsigned long long wmask = (1ull << win) - 1ull;
+#pragma unroll
+        for (int rr = 0; rr < BIL_RPT; ++rr) {
+            int n = 0;
+            for (int dr = 0; dr < win; ++dr) n += __popcll((s_rowmask[threadIdx.y * BIL_RPT + rr + dr] >> threadIdx.x) & wmask);
+            n_disc_row[rr] = n;
+        }
+    }
 #pragma unroll
     for (int rr = 0; rr < BIL_RPT; ++rr) {
-        const int ty = threadIdx.y + rr * BT_TY;
+        const int ty = threadIdx.y * BIL_RPT + rr;
         const int r = tile_y * BT_H + ty;
-        bool need = false;
-        if (r < H && c < W) {
-            const unsigned long long wmask = (1ull << win) - 1ull;
-            int n_disc = 0;
-            for (int dr = 0; dr < win; ++dr) n_disc += __popcll((s_rowmask[ty + dr] >> threadIdx.x) & wmask);
-            need = n_disc > 0 && n_disc < win * win;
-            if (!need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
-        }
+        const bool inside = r < H && c < W;
+        const bool need = inside && n_disc_row[rr] > 0 && n_disc_row[rr] < win * win;
+        if (inside && !need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
         const unsigned lane = tid & 31u;
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
         int slot = 0;
@@ -317,7 +342,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
 }
 
 template <typename DT, int WS>
-__global__ void __launch_bounds__(BT_W* BT_TY) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+__global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 1) bilateral_iter_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
                                                                    int H, int W, int win_rt, DT thr, DT* __restrict__ dout,
                                                                    const __grid_constant__ KRank kr) {
     bilateral_tile<DT, WS>(din, dorig, H, W, win_rt, thr, dout, blockIdx.x, blockIdx.y, kr);
@@ -334,7 +359,7 @@ struct BilateralBatch {
 };
 
 template <typename DT, int WS>
-__global__ void __launch_bounds__(BT_W* BT_TY) bilateral_batch_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
+__global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 1) bilateral_batch_kernel(const DT* __restrict__ din, const DT* __restrict__ dorig,
                                                                     const __grid_constant__ BilateralBatch bb, int win_rt,
                                                                     DT thr, DT* __restrict__ dout, const __grid_constant__ KRank kr) {
     const unsigned t = blockIdx.x;
