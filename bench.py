@@ -406,6 +406,27 @@ def run_ours(args):
                                            "launches_per_step": 13, "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats)"}
             except Exception as e:
                 extras["group_480x640"] = {"error": repr(e)}
+        if "sweep" not in skip:
+            # (b4) cfg5 end to end: the sweep driver (per-image reseeding, host frames in, 44-channel group tensors out to pinned
+            #      host memory), inpaint and .npz writing excluded as SURVEY 8d says
+            try:
+                n_sw, b_sw = 96, 32
+                pool_f = [(img_pool[k % POOL], raw_pool[k % POOL]) for k in range(n_sw)]
+                sink = sweep.PinnedGroupSink()
+                # warm-up over two batches: page-locked staging (2 input slots, 2 x 1.7 GB output slots) is allocated once
+                sweep.run_sweep(range(2 * b_sw), lambda i: pool_f[i], dev, batch=b_sw, dataset_len=n_sw, sink=sink)
+                sync()
+                sink.frames = sink.bytes = 0
+                t0 = time.perf_counter()
+                sweep.run_sweep(range(n_sw), lambda i: pool_f[i], dev, batch=b_sw, dataset_len=n_sw, sink=sink)
+                sync()
+                ts = time.perf_counter() - t0
+                extras["cfg5_sweep_e2e"] = {"frames_per_s": n_sw / ts, "pairs_per_s": 5 * n_sw / ts, "frames": n_sw, "batch": b_sw,
+                                            "d2h_bytes_per_frame": sink.bytes // max(sink.frames, 1), "h2d_bytes_per_frame": 4 * H * W * 4,
+                                            "what": "sweep.run_sweep: host frames -> normalize_depth -> 5-pair group (reference RNG draw order per frame) -> "
+                                                    "44-channel group tensor in pinned host memory (double-buffered async D2H); wall clock incl. host RNG, staging copy, H2D, D2H"}
+            except Exception as e:
+                extras["cfg5_sweep_e2e"] = {"error": repr(e)}
         if "ref" not in skip:
             # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
             try:
@@ -550,7 +571,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll NVML during the timed region (diagnostics)")
-    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,bilateral,augment,group,ref,e2e (profiling runs)")
+    ap.add_argument("--skip", default="", help="comma list of secondary legs to skip: general,sixdof,bilateral,augment,group,sweep,ref,e2e (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

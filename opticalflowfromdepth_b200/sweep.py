@@ -55,6 +55,61 @@ def reduce_counters(counters: torch.Tensor, group=None) -> Dict[str, int]:
     return {name: int(host[slot]) for name, slot in COUNTER_NAMES.items()}
 
 
+class PinnedGroupSink:
+    """A `sink` for run_sweep that brings every batch's 44-channel group tensor (preprocess.py:437-447 channel order) to the
+    host: one torch.cat on the device, one D2H copy into page-locked memory per batch, issued on a side stream into one of two
+    pinned slots, so the copy of batch k overlaps the host-side preparation and the kernels of batch k+1.
+    `on_batch(idx_list, array[B,44,H,W])` receives the host array once its copy has landed (when its slot is reused, or at
+    flush()) - e.g. to hand it to preprocess.NpzWriter; without it the sink only counts."""
+
+    def __init__(self, on_batch: Optional[Callable] = None):
+        self.on_batch = on_batch
+        self.frames = 0
+        self.bytes = 0
+        self._slots = [None, None]   # (pinned tensor, event, idx_list, n) per slot
+        self._k = 0
+        self._stream = None
+
+    def _deliver(self, slot):
+        entry = self._slots[slot]
+        if entry is None:
+            return
+        host, event, idx_list, n = entry
+        event.synchronize()
+        self._slots[slot] = (host, event, None, 0)
+        if idx_list is not None and self.on_batch is not None:
+            self.on_batch(idx_list, host[:n].numpy())
+
+    def __call__(self, idx_list, res):
+        from .preprocess import GROUP_CHANNELS
+
+        stack = torch.cat([res[n].float() for n in GROUP_CHANNELS], 1)
+        dev = stack.device
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(dev)
+        slot = self._k & 1
+        self._k += 1
+        self._deliver(slot)  # the slot's previous copy has landed and is handed over before the buffer is reused
+        entry = self._slots[slot]
+        host = entry[0] if entry is not None and entry[0].shape[1:] == stack.shape[1:] and entry[0].shape[0] >= stack.shape[0] else None
+        if host is None:
+            host = torch.empty(stack.shape, dtype=stack.dtype, pin_memory=True)
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._stream):
+            host[:stack.shape[0]].copy_(stack, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(self._stream)
+        stack.record_stream(self._stream)
+        self._slots[slot] = (host, event, list(idx_list), stack.shape[0])
+        self.frames += len(idx_list)
+        self.bytes += stack.numel() * stack.element_size()
+
+    def flush(self):
+        """Wait for the outstanding copies and hand their batches over (oldest first)."""
+        for slot in (self._k & 1, (self._k + 1) & 1):
+            self._deliver(slot)
+
+
 def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device, batch: int = 32, epoch: int = 0,
               dataset_len: int = 0, inpaint: Optional[Callable] = None, sink: Optional[Callable] = None,
               counters: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -71,10 +126,29 @@ def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device
     dev = torch.device(device)
     if counters is None:
         counters = ops.new_counters(dev)
+    stage = {}  # page-locked staging of the input batch: frames are copied in once, the H2D copy is asynchronous
     for idx_list in batches(indices, batch):
         frames = [load_frame(i) for i in idx_list]
-        img = torch.from_numpy(np.stack([f[0] for f in frames])).to(dev)
-        raw = torch.from_numpy(np.stack([f[1] for f in frames])).to(dev)
+        n = len(frames)
+        key = (frames[0][0].shape, frames[0][0].dtype, frames[0][1].shape, frames[0][1].dtype)
+        if stage.get("key") != key or stage["img"][0].shape[0] < n:
+            stage = {"key": key, "flip": 0,
+                     "img": [torch.empty((max(batch, n),) + frames[0][0].shape, dtype=torch.from_numpy(frames[0][0]).dtype, pin_memory=True) for _ in range(2)],
+                     "raw": [torch.empty((max(batch, n),) + frames[0][1].shape, dtype=torch.from_numpy(frames[0][1]).dtype, pin_memory=True) for _ in range(2)],
+                     "ev": [None, None]}
+        slot = stage["flip"]
+        stage["flip"] ^= 1
+        if stage["ev"][slot] is not None:
+            stage["ev"][slot].synchronize()  # the previous H2D copy out of this staging slot has finished
+        h_img, h_raw = stage["img"][slot], stage["raw"][slot]
+        for k, f in enumerate(frames):
+            h_img[k].copy_(torch.from_numpy(f[0]))
+            h_raw[k].copy_(torch.from_numpy(f[1]))
+        img = h_img[:n].to(dev, non_blocking=True)
+        raw = h_raw[:n].to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        stage["ev"][slot] = ev
         h, w = img.shape[-2:]
         K, inv_K = synthesis.Plausible.K((h, w))
         s_vals, cams = [], []
@@ -92,4 +166,6 @@ def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device
         counters[_lib.CNT_PAIRS] += 5 * len(idx_list)
         if sink is not None:
             sink(idx_list, res)
+    if sink is not None and hasattr(sink, "flush"):
+        sink.flush()
     return counters
