@@ -41,6 +41,13 @@ def test_version_and_workspace_bytes():
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 5, None, None, 1, 1 << 20, None), -4),   # epilogue
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 1, None, None, 1, 1 << 20, None), -1),   # concat w/o aux
     ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 4, 4, 1, 1, 1, None, 0, None, None, 8, 16, None), -5),        # ws too small
+    ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 65536, 32768, 1, 1, 1, None, 0, None, None, 8, 1 << 20, None), -2),  # H*W = 2^31
+    ("ofd_splat_flow", (1, 1, 0, 1, 1, 2, 600000, 8, 1, 1, 1, None, 0, None, None, 8, 1 << 20, None), -2),     # H / 8 > 65535 grid rows
+    ("ofd_disparity_pair", (1, 1, 0, 1, 1, 65536, 32768, 1, 1, 1, 1, 1, 1, None, None), -2),                   # H*W = 2^31
+    ("ofd_augment_pairs", (1, 1, 1, 1, 1, 1, None, None, 2, 8, 8) + (1,) * 15 + (None, 8, 1 << 20, None), -1), # NULL kinds
+    ("ofd_bilateral_iter_batch", (1, 1, 0, 1, None, None, None, 5, 0.04, 1, None), -1),                        # NULL tables
+    ("ofd_depth_from_png", (1, 12, 0, 16, 1, 1, None), -3),                                                    # 12-bit source
+    ("ofd_depth_from_png", (1, 8, 7, 16, 1, 1, None), -4),                                                     # unknown kind
     ("ofd_splat_targets", (1, 1, 1, 1, 5, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 1 << 20, None), -3),      # bad dtype
     ("ofd_splat_targets", (1, 1, 1, 1, 1, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 200, None), -5),          # f64: 2 key planes
     ("ofd_splat_targets", (None, 1, 1, 1, 0, 1, 2, 4, 4, 1, 1, 1, None, None, 8, 1 << 20, None), -1),   # NULL obj
