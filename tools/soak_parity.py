@@ -1,5 +1,6 @@
 """Randomised parity soak (not part of the test suite): random shapes / batches / flows through the fused pair kernel, the
-general splat and the ragged bilateral, each checked bit-exactly against the CPU oracle.  `python tools/soak_parity.py SECONDS`."""
+general splat, the ragged bilateral, the fused 6-DoF pair and the batched augmentation, each checked against the CPU oracle
+(bit-exact; the 6-DoF flow within the path's 1e-5 coordinate-relative tolerance).  `python tools/soak_parity.py SECONDS`."""
 import sys
 import time
 from pathlib import Path
@@ -79,11 +80,78 @@ def trial_bilateral(rng):
     return ok, f"bilateral {[d.shape for d in depths]} windows {fs}"
 
 
+def trial_reproject_pair(rng):
+    """Fused 6-DoF pair: flow within the path's tolerance of the torch restatement, splat bit-exact given OUR flow."""
+    from oracle import flow as oflow
+    from opticalflowfromdepth_b200 import geometry, synthesis
+
+    h, w, b = int(rng.integers(2, 70)), int(rng.integers(2, 160)), int(rng.integers(1, 4))
+    img = rng.integers(0, 256, (b, 3, h, w)).astype(np.float32)
+    depth = np.stack([depth_field(rng, h, w, rng.random() < 0.5) for _ in range(b)])[:, None]
+    vin = (rng.random((b, 1, h, w)) > 0.1).astype(np.float32)
+    K, invK = synthesis.Plausible.K((h, w))
+    cams, poses = [], []
+    for _ in range(b):
+        torch.manual_seed(int(rng.integers(0, 1 << 30)))
+        T1 = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]
+        poses.append(T1)
+        cams.append(geometry.camera_constants(K, invK, T1))
+    io, do, bo, fo, vo, co, raw = ops.reproject_pair(cu(img), cu(depth), torch.cat(cams).to(DEV), cu(vin), want_raw_valid=True)
+    ok = True
+    for k in range(b):
+        ref = oflow.reproject_flow(torch.from_numpy(depth[k]), poses[k]).numpy()
+        got = fo[k].cpu().numpy()
+        yy, xx = np.mgrid[0:h, 0:w]
+        tol_x = 1e-5 * np.maximum(np.abs(ref[0] + xx), max(w - 1, 1))
+        tol_y = 1e-5 * np.maximum(np.abs(ref[1] + yy), max(h - 1, 1))
+        ok &= bool((np.abs(got[0] - ref[0]) <= tol_x).all() and (np.abs(got[1] - ref[1]) <= tol_y).all())
+        obj = np.concatenate([img[k], depth[k], got * -1.0, vin[k]])
+        o, v, cc, _, _ = oracle.fw_forward(obj, got, depth[k])
+        v2 = v * o[6:7]
+        ok &= eq(raw[k], v) and eq(vo[k], v2) and eq(co[k], cc) and eq(io[k], o[0:3] * v2) and eq(bo[k], o[4:6] * v2)
+        ok &= eq(do[k], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v2)).numpy())
+    return ok, f"reproject_pair {b}x{h}x{w}"
+
+
+def trial_augment(rng):
+    """ofd_augment_pairs: every one of the six splats against the oracle fed with the same special flow."""
+    from oracle import flow as oflow
+    from opticalflowfromdepth_b200 import synthesis
+
+    h, w, b = int(rng.integers(4, 60)), int(rng.integers(4, 120)), int(rng.integers(1, 4))
+    img = rng.integers(0, 256, (b, 3, h, w)).astype(np.float32)
+    depth = np.stack([depth_field(rng, h, w, True) for _ in range(b)])[:, None]
+    p01 = ops.disparity_pair(cu(img), cu(depth), cu(rng.uniform(40, 55, b).astype(np.float32)))
+    img1, d1, back, flow = p01[0], p01[1], p01[2], p01[3]
+    kinds = [int(rng.integers(5, 8)) for _ in range(b)]
+    params = synthesis.sample_special_params(kinds, (h, w), torch.Generator().manual_seed(int(rng.integers(0, 1 << 30))))
+    r = ops.augment_pairs(cu(img), cu(depth), img1, d1, flow, back, kinds, params)
+    n = lambda t: t.cpu().numpy()  # noqa: E731
+    ok = True
+    for k in range(b):
+        sf, bsf = n(r["special_flow"][k]), n(r["back_special_flow"][k])
+        o, v, _, _, _ = oracle.fw_forward(n(flow[k]), sf, depth[k])
+        ok &= eq(r["aug0_flow"][k], (o + bsf) * v)
+        o, v, _, _, _ = oracle.fw_forward(sf, n(back[k]), n(d1[k]))
+        ok &= eq(r["aug1_flow"][k], (o + n(flow[k])) * v)
+        for tag, im, dp in (("0", img[k], depth[k]), ("1", n(img1[k]), n(d1[k]))):
+            o, v, cc, _, _ = oracle.fw_forward(np.concatenate([im, dp]), sf, dp)
+            ok &= eq(r["aug_img" + tag][k], o[0:3]) and eq(r["valid_img" + tag][k], v) and eq(r["collision_img" + tag][k], cc)
+            ok &= eq(r["aug_depth" + tag][k], oflow.fix_warped_depth(torch.from_numpy(o[3:4].copy())).numpy())
+        a0 = n(r["aug0_flow"][k])
+        o, v, _, _, _ = oracle.fw_forward(a0, a0, n(r["aug_depth0"][k]))
+        ok &= eq(r["back_aug0_flow"][k], (o * -1.0) * v)
+        a1 = n(r["aug1_flow"][k])
+        o, v, _, _, _ = oracle.fw_forward(a1, a1, depth[k])
+        ok &= eq(r["back_aug1_flow"][k], (o * -1.0) * v)
+    return ok, f"augment {b}x{h}x{w} kinds {kinds}"
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, counts, fails = time.time(), {}, []
-    trials = (trial_pair, trial_splat, trial_bilateral)
+    trials = (trial_pair, trial_splat, trial_bilateral, trial_reproject_pair, trial_augment)
     k = 0
     while time.time() - t0 < budget:
         fn = trials[k % len(trials)]
