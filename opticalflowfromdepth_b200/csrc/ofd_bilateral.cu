@@ -202,9 +202,10 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
         const int tr = e / RW, tc = e - tr * RW;
         const int r = r0 + tr, c = c0 + tc;
         if (tr > 0 && tr < RH - 1 && tc > 0 && tc < RW - 1 && r >= 1 && r <= H - 2 && c >= 1 && c <= W - 2) {
+            // branch-free: the four comparisons are evaluated and OR-ed (| not ||), one predicated store
             const DT inv = sinv[e];
-            const bool disc = (fabs(inv - sinv[e - RW]) > thr) || (fabs(inv - sinv[e + RW]) > thr) ||
-                              (fabs(inv - sinv[e - 1]) > thr) || (fabs(inv - sinv[e + 1]) > thr);
+            const bool disc = (fabs(inv - sinv[e - RW]) > thr) | (fabs(inv - sinv[e + RW]) > thr) |
+                              (fabs(inv - sinv[e - 1]) > thr) | (fabs(inv - sinv[e + 1]) > thr);
             if (disc) sflag[e] |= 1;
         }
     }
