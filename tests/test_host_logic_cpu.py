@@ -210,3 +210,38 @@ def test_reader_matches_the_reference_dataloader(golden, tmp_path):
     np.random.seed(1)
     img0, img1, flow, depth, label = dl.DepthToFlowDataset(crop_size=(8, 12)).getitem_from_npz(tmp_path / "group.npz", 1, 0)
     assert img0.shape == (3, 8, 12) and flow.shape == (2, 8, 12) and depth.shape == (1, 8, 12) and label.tolist() == [1, 0, 0, 0]
+
+
+def test_npz_writer_files_read_back_with_numpy(tmp_path):
+    """preprocess.NpzWriter / save_npz write the reference's container (np.savez_compressed: a zip of .npy members) at any deflate
+    level: np.load returns the same keys, dtypes and values; level 6 is byte-compatible with what np.savez_compressed stores."""
+    import numpy as np
+
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    rng = np.random.default_rng(0)
+    data = rng.normal(0, 3, (8, 30, 44)).astype(np.float32)
+    data[:, 5:20] = 0  # a compressible block
+    for compress in (True, False, 1, 9):
+        w = pp.NpzWriter(threads=2, compress=compress)
+        for k in range(3):
+            w.submit(str(tmp_path / f"f{compress}_{k}.npz"), img_depth_flow=data + k, augment_flow_type=5 + k)
+        w.close()
+        assert w.files == 3
+        for k in range(3):
+            z = np.load(tmp_path / f"f{compress}_{k}.npz")
+            assert sorted(z.files) == ["augment_flow_type", "img_depth_flow"]
+            assert z["img_depth_flow"].dtype == np.float32 and np.array_equal(z["img_depth_flow"], data + k)
+            assert int(z["augment_flow_type"]) == 5 + k
+    np.savez_compressed(tmp_path / "ref.npz", img_depth_flow=data, augment_flow_type=5)
+    ours, ref = (tmp_path / "fTrue_0.npz").stat().st_size, (tmp_path / "ref.npz").stat().st_size
+    assert abs(ours - ref) <= 0.02 * ref  # same deflate level: same size up to zip header details
+    assert (tmp_path / "f1_0.npz").stat().st_size < (tmp_path / "fFalse_0.npz").stat().st_size
+    # a failing write surfaces at close()
+    bad = pp.NpzWriter(threads=1)
+    bad.submit(str(tmp_path / "no_such_dir" / "x.npz"), a=data)
+    try:
+        bad.close()
+        raise AssertionError("expected the write error to propagate")
+    except (FileNotFoundError, OSError):
+        pass
