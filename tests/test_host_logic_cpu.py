@@ -245,3 +245,25 @@ def test_npz_writer_files_read_back_with_numpy(tmp_path):
         raise AssertionError("expected the write error to propagate")
     except (FileNotFoundError, OSError):
         pass
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line with the driver's keys, the CPU restatement as the thing measured."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "flow pairs/s @480x640" and line["unit"] == "pairs/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and "workload" in line["config"]
+    # under torchrun only rank 0 prints
+    r2 = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=str(ROOT),
+                        env={**__import__("os").environ, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
