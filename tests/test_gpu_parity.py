@@ -1133,3 +1133,31 @@ def test_sweep_results_do_not_depend_on_the_partition(pkg, golden):
     sweep.run_sweep([11], lambda i: (g["img0"], g["raw_depth"][None]), DEV, batch=1, dataset_len=0, sink=sink_into(one))
     assert eq(one[11]["img1"], g["group"][4:7]) and eq(one[11]["flow01"], g["group"][24:26])
     _flow_tolerance_check(one[11]["flow12"], g["group"][28:30], *g["group"].shape[1:], "sweep flow12")
+
+
+def test_bench_default_arm_prints_the_contract_line():
+    """bench.py (reduced sizes): one JSON line with the driver's keys - metric / value / roofline / e2e / clocks / gpu_launches."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "4", "--warmup", "3", "--frames", "32", "--e2e-frames", "16",
+                        "--no-cpu", "--skip", "general,sixdof,bilateral,augment,group,sweep,ref,compact"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout must be exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["metric"] == "flow pairs/s @480x640" and d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["steps"] == 4
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["gpu_launches"] == 4 and "workload" in d["config"]
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1.05 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["traffic"] is None or rf["traffic"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16 * (4 * 480 * 640 * 4 + 4) and e["d2h_bytes_per_step"] == 16 * 10 * 480 * 640 * 4
+    assert e["value"] < d["value"]  # host buffers cross PCIe: never the device-resident number
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["counters"]["frames"] == 32 and d["counters"]["hit"] + d["counters"]["hole"] == 32 * 480 * 640
