@@ -214,8 +214,9 @@ class BackFlow(nn.Module):
 class SpecialFlow(nn.Module):
     """Analytic augmentation flows; returns (p1 - p0, p_prev - p0) as [2,h,w] float32 tensors.
 
-    Like the reference, a fresh instance always takes the vertical-flip branch and the [[1,s],[0,1]] shear branch
-    (the toggles at preprocess.py:49,83 flip from their initial True on first use)."""
+    Like the reference, a fresh instance takes the vertical-flip branch and the [[1,s],[0,1]] shear branch first (the toggles at
+    preprocess.py:49,83 flip from their initial True on first use) and alternates on later uses of the same instance; the
+    reference builds a fresh instance per augment_flow call, so in its pipeline only the first branches occur."""
 
     def __init__(self, device=None):
         super().__init__()
@@ -245,7 +246,9 @@ class SpecialFlow(nn.Module):
         if augment_flow_type >= 5.:
             self.horizontal_flip = not self.horizontal_flip
             if self.horizontal_flip:
-                raise NotImplementedError("horizontal flip is unreachable in the reference (fresh instance per call)")
+                # second use of one instance (preprocess.py:52): p1 = (w-1-x, y).  Expressed as the affine map about
+                # c = ((w-1)/2, 0) with M = diag(-1, 1): every intermediate is a half-integer, so the flow (w-1-2x, +0) is exact
+                return 6, [(w - 1) / 2.0, 0.0, -1.0, 0.0, 0.0, 1.0, -1.0, 0.0, 0.0, 1.0]
             return 5, None
         raise ValueError("augment_flow_type must be >= 5 for a special flow")
 

@@ -203,6 +203,18 @@ def special_cases(pp, ref_utils):
             assert torch.equal(f, mf) and torch.equal(bfl, mb), kind
             out[f"k{kind}_{rep}_flow"], out[f"k{kind}_{rep}_back"] = f.numpy(), bfl.numpy()
             out[f"k{kind}_{rep}_params"] = np.array(params if params is not None else [0.0] * 10, np.float64)
+    # a REUSED instance alternates its branches (preprocess.py:49,83): second call = horizontal flip / the other shear matrix
+    h, w = 23, 31
+    sf = pp.SpecialFlow(device="cpu")
+    sf((h, w), 5.0)
+    f, bfl = sf((h, w), 5.0)
+    out["k5_reuse_flow"], out["k5_reuse_back"] = f.numpy(), bfl.numpy()
+    sf = pp.SpecialFlow(device="cpu")
+    ref_utils.set_seed(2000)
+    sf((h, w), 7.0)
+    ref_utils.set_seed(2001)
+    f, bfl = sf((h, w), 7.0)
+    out["k7_reuse_flow"], out["k7_reuse_back"] = f.numpy(), bfl.numpy()
     return out
 
 

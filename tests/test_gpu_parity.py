@@ -430,6 +430,49 @@ def test_special_flows_vs_reference_golden(pkg, golden):
             assert np.abs(b.cpu().numpy() - g[f"k{kind}_{rep}_back"]).max() <= tol, kind
 
 
+def test_special_flow_reused_instance_vs_reference_golden(pkg, golden):
+    """Second use of ONE SpecialFlow instance against the reference's own second call: horizontal flip (exact) and the other
+    shear matrix (matmul rounding: 2e-4 like the first-use goldens)."""
+    g = golden("special_cases")
+    h, w = 23, 31
+    sf = pkg.synthesis.SpecialFlow(DEV)
+    sf((h, w), 5.0)
+    f, b = sf((h, w), 5.0)
+    assert eq(f, g["k5_reuse_flow"]) and eq(b, g["k5_reuse_back"])
+    sf = pkg.synthesis.SpecialFlow(DEV)
+    pkg.synthesis.set_seed(2000)
+    sf((h, w), 7.0)
+    pkg.synthesis.set_seed(2001)
+    f, b = sf((h, w), 7.0)
+    assert np.abs(f.cpu().numpy() - g["k7_reuse_flow"]).max() <= 2e-4 and np.abs(b.cpu().numpy() - g["k7_reuse_back"]).max() <= 2e-4
+    assert np.abs(g["k7_reuse_flow"][0]).max() > 1 and not g["k7_reuse_flow"][1].any()  # the x-shear branch
+
+
+def test_special_flow_instance_reuse_alternates_like_the_reference(pkg):
+    """A reused SpecialFlow instance alternates vertical / horizontal flip and the two shear matrices (preprocess.py:49,83):
+    flows are exact integers / products, checked against the reference's formulas p1 - p0."""
+    h, w = 37, 54
+    sf = pkg.synthesis.SpecialFlow(DEV)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    f, b = sf((h, w), 5.0)   # first use: vertical flip
+    assert eq(f[0], np.zeros((h, w), np.float32)) and eq(f[1], (h - 1 - yy) - yy) and torch.equal(f, b)
+    f, b = sf((h, w), 5.0)   # second use: horizontal flip
+    assert eq(f[0], (w - 1 - xx) - xx) and eq(f[1], np.zeros((h, w), np.float32)) and torch.equal(f, b)
+    assert not np.signbit(f[1].cpu().numpy()).any()
+    f, b = sf((h, w), 5.0)   # third: vertical again
+    assert eq(f[1], (h - 1 - yy) - yy)
+    pkg.synthesis.set_seed(4)
+    f1, b1 = sf((h, w), 7.0)  # first shear: [[1, s], [0, 1]] -> flow (0, s x)
+    pkg.synthesis.set_seed(4)
+    s_val = np.float32(pkg.synthesis.get_random(0.15, 0.2))
+    assert eq(f1[0], np.zeros((h, w), np.float32)) and eq(f1[1], (xx * s_val + yy) - yy) and eq(b1[1], (xx * -s_val + yy) - yy)
+    pkg.synthesis.set_seed(4)
+    f2, b2 = sf((h, w), 7.0)  # second shear: [[1, 0], [s, 1]] -> flow (s y, 0)
+    # x' = x * 1 + y * s accumulates like the reference's matmul (first product rounded, second fused: the order the rotation goldens pin)
+    fma = lambda a, b, c: (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)  # noqa: E731
+    assert eq(f2[1], np.zeros((h, w), np.float32)) and eq(f2[0], fma(yy, s_val, xx) - xx) and eq(b2[0], fma(yy, -s_val, xx) - xx)
+
+
 def test_concat_and_back_flow_vs_reference_golden(pkg, golden):
     g = golden("concat_back_cases")
     cf, bf = pkg.synthesis.ConcatFlow(DEV), pkg.synthesis.BackFlow(DEV)
