@@ -110,31 +110,7 @@ class NpzWriter:
             t.join()
 
 
-def photometric_draws(augment_flow_type: float):
-    """Host random draws of the photometric branch of augment_flow in the reference's order (preprocess.py:150-163)."""
-    if augment_flow_type >= 2.:
-        return None
-    if augment_flow_type >= 1.:
-        channel = int(synthesis.get_random(3, 0, False))
-        shift = synthesis.get_random(10, 15)
-        return channel, shift
-    return synthesis.get_random(1, 0, False)
-
-
-def photometric_apply(img: torch.Tensor, augment_flow_type: float, draws) -> torch.Tensor:
-    """augment_img_func of preprocess.py:150-163 on img[...,3,H,W]: 0 brightness scale, 1 one-channel shift, 2 grayscale."""
-    if augment_flow_type >= 2.:
-        # (img.permute(1,2,0) @ gray).permute(2,0,1) with gray[k, :] = (0.2989, 0.5870, 0.1140)[k]: every output channel is the
-        # same K=3 dot product, evaluated here as an ascending-k chain (the reference's order is a BLAS detail)
-        r, g, b = img.select(-3, 0), img.select(-3, 1), img.select(-3, 2)
-        gray = (r * 0.2989 + g * 0.5870) + b * 0.1140
-        return gray.unsqueeze(-3).expand_as(img).contiguous()
-    if augment_flow_type >= 1.:
-        channel, shift = draws
-        out = img.clone()
-        out.select(-3, channel).add_(shift.to(img.device))
-        return out
-    return img * draws.to(img.device)
+photometric_draws, photometric_apply = synthesis.photometric_draws, synthesis.photometric_apply
 
 
 class PreprocessPlusAugment(nn.Module):

@@ -21,6 +21,7 @@ from . import geometry, ops
 from .fw import FW
 
 __all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "sample_special_params",
+           "photometric_draws", "photometric_apply",
            "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
 
 
@@ -293,15 +294,50 @@ def sample_special_params(kinds, size, generator=None):
     return out
 
 
+def photometric_draws(augment_flow_type: float):
+    """Host random draws of the photometric branch of augment_flow in the reference's order (preprocess.py:150-163)."""
+    if augment_flow_type >= 2.:
+        return None
+    if augment_flow_type >= 1.:
+        channel = int(get_random(3, 0, False))
+        shift = get_random(10, 15)
+        return channel, shift
+    return get_random(1, 0, False)
+
+
+def photometric_apply(img: torch.Tensor, augment_flow_type: float, draws) -> torch.Tensor:
+    """augment_img_func of preprocess.py:150-163 on img[...,3,H,W]: 0 brightness scale, 1 one-channel shift, 2 grayscale."""
+    if augment_flow_type >= 2.:
+        # (img.permute(1,2,0) @ gray).permute(2,0,1) with gray[k, :] = (0.2989, 0.5870, 0.1140)[k]: every output channel is the
+        # same K=3 dot product, evaluated here as an ascending-k chain (the reference's order is a BLAS detail)
+        r, g, b = img.select(-3, 0), img.select(-3, 1), img.select(-3, 2)
+        gray = (r * 0.2989 + g * 0.5870) + b * 0.1140
+        return gray.unsqueeze(-3).expand_as(img).contiguous()
+    if augment_flow_type >= 1.:
+        channel, shift = draws
+        out = img.clone()
+        out.select(-3, channel).add_(shift.to(img.device))
+        return out
+    return img * draws.to(img.device)
+
+
 def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device=None, augment_flow_type=None,
                  inpaint=None):
-    """Geometric branch of preprocess.augment_flow (preprocess.py:116-147): 6 splats.  `inpaint(img, valid, collision)`
-    is the caller's hole filler (utils.inpaint in the reference — CPU OpenCV, outside this path); None skips it."""
+    """preprocess.augment_flow (preprocess.py:106-182): the geometric branch (types 5-7, 6 splats) and the photometric one
+    (types 0-2).  `inpaint(img, valid, collision)` is the caller's hole filler (utils.inpaint in the reference — CPU OpenCV,
+    outside this path); None skips it."""
     _, h, w = img0.shape
     if augment_flow_type is None:
         augment_flow_type = get_random(8, 0, False)
+    if augment_flow_type < 3.:
+        # photometric branch (preprocess.py:150-182): brightness scale / one-channel shift / grayscale, no warping
+        draws = photometric_draws(float(augment_flow_type))
+        aug0 = photometric_apply(img0, float(augment_flow_type), draws)
+        aug1 = photometric_apply(img1, float(augment_flow_type), draws)
+        return ((aug0, img0_depth, flow01, back_flow01, img1, img1_depth),
+                (img0, img0_depth, flow01, back_flow01, aug1, img1_depth), int(augment_flow_type), None)
     if augment_flow_type < 5.:
-        raise NotImplementedError("photometric augmentation types 0-2 do no warping and are outside this path")
+        return None  # the reference's `elif augment_flow_type >= 3.: pass` (preprocess.py:148-149) falls off the end
     fw, cf, bf, sf = FW(device), ConcatFlow(device), BackFlow(device), SpecialFlow(device)
     special_flow, back_special_flow = sf((h, w), augment_flow_type)
     aug0_flow, _ = cf(back_special_flow, special_flow, flow01, img0_depth)
