@@ -257,6 +257,17 @@ int ofd_bilateral_iter(const void* depth_in, const void* depth_orig, int dtype, 
                        double threshold, void* depth_out, ofd_stream_t stream);
 
 /*
+ * ofd_bilateral_iter_masked — one iteration with the reference's BINARY mask (bilateral_filter.py:48-49,72-80,156,160-162,181-182):
+ * a neighbour difference counts only between two unmasked pixels; masked pixels are never discontinuities and keep their depth;
+ * masked taps and taps outside the image (the mask is zero-padded, not ring-replicated) are left out of the median.
+ * mask: uint8 [H,W] on the device, 0 = masked.  mask_coef_f64: 1 when the reference's mask array is float64 or integer (its median
+ * coefficients, float32 * mask.dtype, are then float64 and the rank rule k(n) runs in float64), 0 for uint8 / bool / float32 masks.
+ * Windows 3, 5, 7.
+ */
+int ofd_bilateral_iter_masked(const void* depth_in, const void* depth_orig, const uint8_t* mask, int mask_coef_f64, int dtype,
+                              int H, int W, int window, double threshold, void* depth_out, ofd_stream_t stream);
+
+/*
  * ofd_bilateral_iter_batch — the same iteration over a RAGGED batch (BASELINE config 2: mixed-resolution frames, each
  * filtered independently exactly as ofd_bilateral_iter would): image i is H_host[i] x W_host[i], stored densely at element
  * offset offset_host[i] of depth_in / depth_orig / depth_out (the three buffers share one layout).  One launch per 64

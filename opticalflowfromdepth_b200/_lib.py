@@ -43,6 +43,7 @@ SIGNATURES = {
     "ofd_special_flow_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "ofd_augment_pairs": (_i, [_p] * 8 + [_i, _i, _i] + [_p] * 17 + [_sz, _p]),
     "ofd_bilateral_iter": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
+    "ofd_bilateral_iter_masked": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _d, _p, _p]),
     "ofd_bilateral_iter_batch": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),

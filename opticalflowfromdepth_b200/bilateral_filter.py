@@ -3,7 +3,8 @@
 On the branch the reference takes (discontinuity map given, mask None) the filter is a depth-edge-gated median;
 each iteration is one ofd_bilateral_iter launch.  numpy in -> numpy out (copies inside); CUDA tensor in -> CUDA tensor
 out.  `image`, sigma_r, sigma_s, HR, gsHR, edge_id and num_gs_iter have no effect on the reference's return value and
-are accepted and ignored here as well; `mask` is not supported (the reference never passes one).
+are accepted and ignored here as well; a binary `mask` takes the reference's mask path (windows 3 / 5 / 7; the reference itself never
+passes one).
 """
 from __future__ import annotations
 
@@ -17,8 +18,6 @@ __all__ = ["sparse_bilateral_filtering", "sparse_bilateral_filtering_batch"]
 
 def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4.0, depth_threshold=0.04, HR=False,
                                mask=None, gsHR=True, edge_id=None, num_iter=None, num_gs_iter=None, device=None):
-    if mask is not None:
-        raise NotImplementedError("sparse_bilateral_filtering: the mask path is not implemented on the B200 path")
     if num_iter is None:
         raise TypeError("'NoneType' object cannot be interpreted as an integer")  # range(None) in the reference (:33)
     is_numpy = isinstance(depth, np.ndarray)
@@ -33,9 +32,25 @@ def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4
             d0 = d0.double()
         dev = d0.device
     cur = d0
+    m_u8, coef_f64 = None, False
+    if mask is not None:
+        # the reference's mask path with a BINARY mask; its median coefficients are float32 * mask.dtype (bilateral_filter.py:185-187)
+        mk = torch.as_tensor(np.asarray(mask) if isinstance(mask, np.ndarray) else mask)
+        if tuple(mk.shape) != tuple(d0.shape):
+            raise ValueError("mask must have the shape of depth")
+        if not bool(((mk == 0) | (mk == 1)).all()):
+            raise NotImplementedError("sparse_bilateral_filtering: only binary masks (0 / 1) are implemented; a fractional mask "
+                                      "turns the reference's median into a weighted one")
+        coef_f64 = torch.promote_types(torch.float32, mk.dtype) == torch.float64
+        m_u8 = (mk != 0).to(device=dev, dtype=torch.uint8).contiguous()
+        if any(int(f) not in (3, 5, 7) for f in filter_size[:num_iter]):
+            raise NotImplementedError("sparse_bilateral_filtering: the mask path supports filter sizes 3, 5 and 7")
     with torch.cuda.device(dev):
         for i in range(num_iter):
-            cur = ops.bilateral_iter(cur, d0, int(filter_size[i]), float(depth_threshold))
+            if m_u8 is None:
+                cur = ops.bilateral_iter(cur, d0, int(filter_size[i]), float(depth_threshold))
+            else:
+                cur = ops.bilateral_iter_masked(cur, d0, m_u8, coef_f64, int(filter_size[i]), float(depth_threshold))
     if num_iter == 0:
         cur = d0.clone()
     return cur.cpu().numpy() if is_numpy else cur

@@ -113,15 +113,25 @@ struct KRank {
     unsigned char k[MAX_WIN * MAX_WIN + 3];
 };
 
-static KRank make_krank(int window) {
+// coef_f64: the coefficients are float64 (mask path with a float64 / integer mask, bilateral_filter.py:187), else float32
+static KRank make_krank(int window, bool coef_f64 = false) {
     KRank kr = {};
     for (int n = 1; n <= window * window; ++n) {
-        const float w = 1.0f / (float)n;
-        volatile float cum = 0.0f;  // volatile: every partial sum is rounded to float32
         int k = 0;
-        for (int q = 0; q < n; ++q) {
-            cum = cum + w;
-            k += (cum <= 0.5f);
+        if (coef_f64) {
+            const double w = 1.0 / (double)n;
+            volatile double cum = 0.0;
+            for (int q = 0; q < n; ++q) {
+                cum = cum + w;
+                k += (cum <= 0.5);
+            }
+        } else {
+            const float w = 1.0f / (float)n;
+            volatile float cum = 0.0f;  // volatile: every partial sum is rounded to float32
+            for (int q = 0; q < n; ++q) {
+                cum = cum + w;
+                k += (cum <= 0.5f);
+            }
         }
         kr.k[n] = (unsigned char)k;
     }
@@ -129,10 +139,15 @@ static KRank make_krank(int window) {
 }
 
 // WS > 0: compile-time window (register sort); WS == 0: run-time window (rank count in shared memory)
-template <typename DT, int WS>
+// MASK: the reference's binary-mask path (bilateral_filter.py:48-49,72-80,156,160-162,181-182; WS > 0 only): a neighbour difference
+// counts only between two unmasked pixels, masked pixels are never discontinuities and keep their depth, masked taps and taps
+// outside the image (the mask is zero-padded, not ring-replicated) are left out of the median.  Flag byte: bit 0 discontinuity,
+// bit 1 depth_orig == 0, bit 2 unmasked.
+template <typename DT, int WS, bool MASK = false>
 __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const DT* __restrict__ dorig, int H, int W,
                                                int win_rt, DT thr, DT* __restrict__ dout, int tile_x, int tile_y,
-                                               const KRank& kr) {
+                                               const KRank& kr, const unsigned char* __restrict__ mask = nullptr) {
+    static_assert(!MASK || WS > 0, "the mask path is built for the compile-time windows");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int win = WS > 0 ? WS : win_rt;
     const int m = win / 2;
@@ -145,6 +160,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     unsigned char* sdisc = sflag + RW * RH;                                   // replicated flags (border tiles only)
     __shared__ unsigned char s_k[MAX_WIN * MAX_WIN + 3];
     __shared__ unsigned long long s_rowmask[BT_H + MAX_WIN - 1];  // discontinuity bits of every window-tile row (TW <= 46 columns)
+    __shared__ unsigned long long s_rowexcl[MASK ? BT_H + MAX_WIN - 1 : 1];  // MASK: taps left out of the median (discontinuity | masked)
     __shared__ unsigned short s_list[BT_W * BT_H];                // tile pixels that need the median (row * BT_W + column)
     __shared__ int s_count;
     const int tid = threadIdx.y * BT_W + threadIdx.x;
@@ -159,16 +175,19 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
         constexpr int CELLS = (BT_W + 2 * (WS / 2) + 4) * (BT_H + 2 * (WS / 2) + 4);
         constexpr int NL = (CELLS + nthr - 1) / nthr;
         DT dv[NL], ov[NL];
+        unsigned char mv[MASK ? NL : 1];
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
             const int e = tid + k * nthr;
             const int tr = e / RW, tc = e - tr * RW;
             const int r = r0 + tr, c = c0 + tc;
             dv[k] = (DT)0, ov[k] = (DT)1;
+            if (MASK) mv[k] = 0;
             if (e < CELLS && r >= 0 && r < H && c >= 0 && c < W) {
                 const size_t p = (size_t)r * W + c;
                 dv[k] = din[p];
                 ov[k] = dorig[p];
+                if (MASK) mv[k] = mask[p];
             }
         }
 #pragma unroll
@@ -177,7 +196,9 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
             if (e < CELLS) {
                 sraw[e] = dv[k];
                 sinv[e] = (DT)1.0 / dv[k];
-                sflag[e] = (ov[k] == (DT)0) ? 2 : 0;  // bit 1: forced discontinuity (:46)
+                unsigned char f = (ov[k] == (DT)0) ? 2 : 0;  // bit 1: forced discontinuity (:46)
+                if (MASK) f |= mv[k] ? 4 : 0;                // bit 2: unmasked (zero outside the image: the zero padding of :156)
+                sflag[e] = f;
             }
         }
     } else {
@@ -201,12 +222,26 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     for (int e = tid; e < RW * RH; e += nthr) {
         const int tr = e / RW, tc = e - tr * RW;
         const int r = r0 + tr, c = c0 + tc;
-        if (tr > 0 && tr < RH - 1 && tc > 0 && tc < RW - 1 && r >= 1 && r <= H - 2 && c >= 1 && c <= W - 2) {
-            // branch-free: the four comparisons are evaluated and OR-ed (| not ||), one predicated store
-            const DT inv = sinv[e];
-            const bool disc = (fabs(inv - sinv[e - RW]) > thr) | (fabs(inv - sinv[e + RW]) > thr) |
-                              (fabs(inv - sinv[e - 1]) > thr) | (fabs(inv - sinv[e + 1]) > thr);
-            if (disc) sflag[e] |= 1;
+        const bool tested = tr > 0 && tr < RH - 1 && tc > 0 && tc < RW - 1 && r >= 1 && r <= H - 2 && c >= 1 && c <= W - 2;
+        if constexpr (!MASK) {
+            if (tested) {
+                // branch-free: the four comparisons are evaluated and OR-ed (| not ||), one predicated store
+                const DT inv = sinv[e];
+                const bool disc = (fabs(inv - sinv[e - RW]) > thr) | (fabs(inv - sinv[e + RW]) > thr) |
+                                  (fabs(inv - sinv[e - 1]) > thr) | (fabs(inv - sinv[e + 1]) > thr);
+                if (disc) sflag[e] |= 1;
+            }
+        } else {
+            // a difference counts only between two unmasked pixels (:72-80); then depth_orig == 0 forces (:46) and the mask clears
+            // (:48-49).  Bit 2 of a neighbour is stable while other threads rewrite bits 0-1 of their own cells.
+            const unsigned char fe = sflag[e];
+            bool disc = false;
+            if (tested) {
+                const DT inv = sinv[e];
+                disc = ((fabs(inv - sinv[e - RW]) > thr) & ((sflag[e - RW] & 4) != 0)) | ((fabs(inv - sinv[e + RW]) > thr) & ((sflag[e + RW] & 4) != 0)) |
+                       ((fabs(inv - sinv[e - 1]) > thr) & ((sflag[e - 1] & 4) != 0)) | ((fabs(inv - sinv[e + 1]) > thr) & ((sflag[e + 1] & 4) != 0));
+            }
+            sflag[e] = (fe & 4) | (((fe & 4) && (disc || (fe & 2))) ? 1 : 0);  // bit 0 = final discontinuity, bit 1 dropped
         }
     }
     __syncthreads();
@@ -225,7 +260,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
             c = c < 1 ? 1 : (c > W - 2 ? W - 2 : c);
             const int src = (r - r0) * RW + (c - c0);
             sdep[e] = sraw[src];
-            sdisc[e] = sflag[src];
+            sdisc[e] = MASK ? (sflag[src] & 1) : sflag[src];
         }
         wdep = sdep, wdisc = sdisc, wstride = TW;
         __syncthreads();
@@ -233,10 +268,20 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     // 4a. one 64-bit discontinuity mask per window-tile row (ballots), so a pixel tests its whole window with `win` loads
     {
         const int lane = tid & 31, warp = tid >> 5;
+        constexpr unsigned char kDiscBits = MASK ? 1 : 0xFF;  // MASK: bit 2 of a raw flag byte is the mask, not a discontinuity
         for (int tr = warp; tr < TH; tr += nthr / 32) {
-            const unsigned lo = __ballot_sync(0xFFFFFFFFu, wdisc[tr * wstride + lane] != 0);
-            const unsigned hi = __ballot_sync(0xFFFFFFFFu, (32 + lane < TW) && wdisc[tr * wstride + 32 + lane] != 0);
+            const bool d_lo = (wdisc[tr * wstride + lane] & kDiscBits) != 0;
+            const bool d_hi = (32 + lane < TW) && (wdisc[tr * wstride + 32 + lane] & kDiscBits) != 0;
+            const unsigned lo = __ballot_sync(0xFFFFFFFFu, d_lo);
+            const unsigned hi = __ballot_sync(0xFFFFFFFFu, d_hi);
             if (lane == 0) s_rowmask[tr] = ((unsigned long long)hi << 32) | lo;
+            if constexpr (MASK) {
+                // the mask of a tap is read at its OWN coordinates (raw cell tr + 2, tc + 2), never ring-replicated
+                const unsigned char* mrow = sflag + (tr + 2) * RW + 2;
+                const unsigned xlo = __ballot_sync(0xFFFFFFFFu, d_lo || !(mrow[lane] & 4));
+                const unsigned xhi = __ballot_sync(0xFFFFFFFFu, (32 + lane < TW) && (d_hi || !(mrow[32 + lane] & 4)));
+                if (lane == 0) s_rowexcl[tr] = ((unsigned long long)xhi << 32) | xlo;
+            }
         }
     }
     __syncthreads();
@@ -246,6 +291,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     //     loaded and counted once (BIL_RPT + win - 1 loads instead of BIL_RPT * win) and the window counts slide.
     const int c = tile_x * BT_W + threadIdx.x;
     int n_disc_row[BIL_RPT];
+    int n_excl_row[MASK ? BIL_RPT : 1];
     if constexpr (WS > 0) {
         const unsigned long long wmask = (1ull << WS) - 1ull;
         int pc[BIL_RPT + WS - 1];
@@ -258,6 +304,18 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
 #pragma unroll
             for (int dr = 0; dr < WS; ++dr) n += pc[rr + dr];
             n_disc_row[rr] = n;
+        }
+        if constexpr (MASK) {
+#pragma unroll
+            for (int q = 0; q < BIL_RPT + WS - 1; ++q)
+                pc[q] = __popcll((s_rowexcl[threadIdx.y * BIL_RPT + q] >> threadIdx.x) & wmask);
+#pragma unroll
+            for (int rr = 0; rr < BIL_RPT; ++rr) {
+                int n = 0;
+#pragma unroll
+                for (int dr = 0; dr < WS; ++dr) n += pc[rr + dr];
+                n_excl_row[rr] = n;
+            }
         }
     } else {
         const unsigned long long wmask = (1ull << win) - 1ull;
@@ -273,7 +331,9 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
         const int ty = threadIdx.y * BIL_RPT + rr;
         const int r = tile_y * BT_H + ty;
         const bool inside = r < H && c < W;
-        const bool need = inside && n_disc_row[rr] > 0 && n_disc_row[rr] < win * win;
+        bool need = inside && n_disc_row[rr] > 0 && n_disc_row[rr] < win * win;
+        if constexpr (MASK)  // masked pixels are skipped (:160-162); the median needs at least one tap that is neither (:188-190)
+            need = inside && n_disc_row[rr] > 0 && n_excl_row[rr] < win * win && (sflag[(ty + m + 2) * RW + threadIdx.x + m + 2] & 4) != 0;
         if (inside && !need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
         const unsigned lane = tid & 31u;
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
@@ -295,7 +355,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
             int n = 0;
 #pragma unroll
             for (int dr = 0; dr < WS; ++dr) {
-                const unsigned bits = (unsigned)(s_rowmask[ty + dr] >> tx);
+                const unsigned bits = (unsigned)((MASK ? s_rowexcl[ty + dr] : s_rowmask[ty + dr]) >> tx);
 #pragma unroll
                 for (int dc = 0; dc < WS; ++dc) {
                     const bool keep = !((bits >> dc) & 1u);
@@ -347,6 +407,35 @@ __global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 
                                                                    int H, int W, int win_rt, DT thr, DT* __restrict__ dout,
                                                                    const __grid_constant__ KRank kr) {
     bilateral_tile<DT, WS>(din, dorig, H, W, win_rt, thr, dout, blockIdx.x, blockIdx.y, kr);
+}
+
+template <typename DT, int WS>
+__global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 1) bilateral_masked_kernel(
+    const DT* __restrict__ din, const DT* __restrict__ dorig, const unsigned char* __restrict__ mask, int H, int W, DT thr,
+    DT* __restrict__ dout, const __grid_constant__ KRank kr) {
+    bilateral_tile<DT, WS, true>(din, dorig, H, W, WS, thr, dout, blockIdx.x, blockIdx.y, kr, mask);
+}
+
+template <typename DT, int WS>
+static void launch_bilateral_masked(const DT* din, const DT* dorig, const unsigned char* mask, int H, int W, DT thr, DT* dout,
+                                    bool coef_f64, cudaStream_t st) {
+    constexpr int m = WS / 2;
+    constexpr int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
+    const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
+    dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_TY);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_masked_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bilateral_masked_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, mask, H, W, thr, dout, make_krank(WS, coef_f64));
+}
+
+template <typename DT>
+static int dispatch_bilateral_masked(const DT* din, const DT* dorig, const unsigned char* mask, int H, int W, int window, DT thr,
+                                     DT* dout, bool coef_f64, cudaStream_t st) {
+    switch (window) {
+        case 3: launch_bilateral_masked<DT, 3>(din, dorig, mask, H, W, thr, dout, coef_f64, st); return 0;
+        case 5: launch_bilateral_masked<DT, 5>(din, dorig, mask, H, W, thr, dout, coef_f64, st); return 0;
+        case 7: launch_bilateral_masked<DT, 7>(din, dorig, mask, H, W, thr, dout, coef_f64, st); return 0;
+        default: return 1;
+    }
 }
 
 // Ragged batch (BASELINE config 2: mixed-resolution frames): images of different H x W packed back to back in one
@@ -475,4 +564,24 @@ extern "C" int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_
         if (rc) return rc;
     }
     return OFD_OK;
+}
+
+extern "C" int ofd_bilateral_iter_masked(const void* depth_in, const void* depth_orig, const uint8_t* mask, int mask_coef_f64,
+                                         int dtype, int H, int W, int window, double threshold, void* depth_out,
+                                         ofd_stream_t stream) {
+    const char* fn = "ofd_bilateral_iter_masked";
+    if (dtype != OFD_F32 && dtype != OFD_F64) return fail(OFD_E_DTYPE, "%s: bad dtype %d", fn, dtype);
+    if (H < 3 || W < 3) return fail(OFD_E_SHAPE, "%s: needs H >= 3 and W >= 3", fn);
+    if ((H + BT_H - 1) / BT_H > 65535) return fail(OFD_E_SHAPE, "%s: H too large", fn);
+    if (window != 3 && window != 5 && window != 7) return fail(OFD_E_ARG, "%s: the mask path supports windows 3, 5 and 7", fn);
+    if (!depth_in || !depth_orig || !mask || !depth_out) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    if (depth_in == depth_out) return fail(OFD_E_ARG, "%s: in-place filtering is not supported", fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OFD_F32)
+        dispatch_bilateral_masked<float>((const float*)depth_in, (const float*)depth_orig, mask, H, W, window, (float)threshold,
+                                         (float*)depth_out, mask_coef_f64 != 0, st);
+    else
+        dispatch_bilateral_masked<double>((const double*)depth_in, (const double*)depth_orig, mask, H, W, window, threshold,
+                                          (double*)depth_out, mask_coef_f64 != 0, st);
+    return check_launch(fn);
 }

@@ -356,6 +356,20 @@ def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
     return out
 
 
+def bilateral_iter_masked(depth_in, depth_orig, mask_u8, coef_f64: bool, window: int, threshold: float):
+    """One iteration with the reference's binary mask (ofd_bilateral_iter_masked): mask_u8 [H,W] uint8 CUDA, 0 = masked."""
+    _check("depth_in", depth_in, dtype=(torch.float32, torch.float64))
+    _check("depth_orig", depth_orig, dtype=depth_in.dtype, shape=depth_in.shape)
+    _check("mask", mask_u8, dtype=torch.uint8, shape=depth_in.shape)
+    if depth_in.dim() != 2:
+        raise ValueError("depth must be [H,W]")
+    H, W = depth_in.shape
+    out = torch.empty_like(depth_in)
+    _lib.call("ofd_bilateral_iter_masked", _ptr(depth_in), _ptr(depth_orig), _ptr(mask_u8), int(bool(coef_f64)), _DT[depth_in.dtype],
+              H, W, int(window), C.c_double(threshold), _ptr(out), _stream(depth_in.device))
+    return out
+
+
 def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, threshold: float):
     """One iteration over a ragged batch: packed_in / packed_orig are 1-D CUDA buffers holding image i ([H_i,W_i] dense) at
     element offset offsets[i]; returns the filtered packed buffer (same layout)."""

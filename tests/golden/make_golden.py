@@ -235,6 +235,28 @@ def bilateral_cases(ref_bil):
         out[f"{tag}_in"], out[f"{tag}_out"] = depth, ref
         out[f"{tag}_fs"] = np.array(fs)
     out["rank_table"] = obil.rank_table(225)
+    # the mask path (bilateral_filter.py:48-49,72-80,156,160-162,181-182) with BINARY masks of three dtypes: the median
+    # coefficients are float32 * mask.dtype, so the rank rule runs in float32 (uint8 / bool masks) or float64 (float64 masks)
+    for tag, dt, mdt, (h, w), fs in (("m_f32_u8", np.float32, np.uint8, (36, 52), [7, 5, 5]), ("m_f32_f64", np.float32, np.float64, (30, 44), [7, 7, 5]),
+                                     ("m_f64_bool", np.float64, np.bool_, (28, 33), [5, 3])):
+        depth = diml_depth(rng, h, w).astype(dt)
+        depth = (depth / depth.max()).astype(dt) * dt(8) + dt(0.5)
+        depth[4:7, 5:8] = 0
+        mask = (rng.random((h, w)) > 0.25)
+        mask[10:16, 8:30] = False
+        mask[0, :5] = False
+        mask[5, 6] = False          # a masked zero-depth pixel: the depth == 0 rule is undone by the mask rule
+        mask = mask.astype(mdt)
+        img = np.zeros((h, w, 3), np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref = ref_bil.sparse_bilateral_filtering(depth.copy(), img, fs, depth_threshold=0.04, num_iter=len(fs), mask=mask)
+            mine = obil.sparse_bilateral_filtering(depth.copy(), fs, 0.04, len(fs), mask=mask)
+        assert ref.dtype == mine.dtype and np.array_equal(ref, mine, equal_nan=True), tag
+        with np.errstate(divide="ignore", invalid="ignore"):
+            plain = obil.sparse_bilateral_filtering(depth.copy(), fs, 0.04, len(fs))
+        assert not np.array_equal(ref, plain, equal_nan=True), "the mask must matter in this case"
+        out[f"{tag}_in"], out[f"{tag}_mask"], out[f"{tag}_out"], out[f"{tag}_fs"] = depth, mask, ref, np.array(fs)
+    out["rank_table_f64"] = obil.rank_table(225, np.float64)
     return out
 
 

@@ -496,6 +496,39 @@ def test_bilateral_vs_reference_golden(pkg, golden, tag):
     assert eq(out_t, g[f"{tag}_out"])
 
 
+@pytest.mark.parametrize("tag", ["m_f32_u8", "m_f32_f64", "m_f64_bool"])
+def test_bilateral_mask_path_vs_reference_golden(pkg, golden, tag):
+    """The reference's mask path (binary masks of three dtypes: float32 or float64 median coefficients) against its own output,
+    from numpy inputs and from CUDA tensors; a fractional mask is refused."""
+    g = golden("bilateral_cases")
+    depth, mask, want, fs = g[f"{tag}_in"], g[f"{tag}_mask"], g[f"{tag}_out"], [int(v) for v in g[f"{tag}_fs"]]
+    got = pkg.bilateral_filter.sparse_bilateral_filtering(depth.copy(), None, fs, depth_threshold=0.04, mask=mask, num_iter=len(fs))
+    assert isinstance(got, np.ndarray) and got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True)
+    got_t = pkg.bilateral_filter.sparse_bilateral_filtering(cu(depth), None, fs, depth_threshold=0.04, mask=torch.from_numpy(mask), num_iter=len(fs))
+    assert eq(got_t, want)
+    plain = pkg.bilateral_filter.sparse_bilateral_filtering(depth.copy(), None, fs, depth_threshold=0.04, num_iter=len(fs))
+    assert not np.array_equal(plain, want, equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        pkg.bilateral_filter.sparse_bilateral_filtering(depth.copy(), None, fs, mask=mask.astype(np.float32) * 0.5, num_iter=1)
+
+
+def test_bilateral_mask_path_sizes_vs_oracle(pkg):
+    """Mask path on sizes that are not tile multiples and on a 480x640 frame, all-ones and all-zeros masks included."""
+    rng = np.random.default_rng(9)
+    for (h, w), dt in (((3, 3), np.float32), ((33, 65), np.float64), ((70, 41), np.float32), ((480, 640), np.float32)):
+        _, depth = pkg.synthetic.redweb_frame(3, max(h, 32), max(w, 32), dtype=dt)
+        d = oflow.normalize_depth(torch.from_numpy(depth[:, :h, :w].copy())).numpy()[0]
+        if h > 8:
+            d[2:5, 3:6] = 0
+        for kind in ("random", "ones", "zeros"):
+            mask = {"random": rng.random((h, w)) > 0.3, "ones": np.ones((h, w), bool), "zeros": np.zeros((h, w), bool)}[kind].astype(np.uint8)
+            fs = [7, 5, 3]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                want = obil.sparse_bilateral_filtering(d.copy(), fs, 0.04, 3, mask=mask)
+            got = pkg.bilateral_filter.sparse_bilateral_filtering(d.copy(), None, fs, depth_threshold=0.04, mask=mask, num_iter=3)
+            assert np.array_equal(got, want, equal_nan=True), (h, w, kind)
+
+
 def test_bilateral_redweb_size_vs_oracle(pkg):
     (h, w), = pkg.synthetic.redweb_sizes(1, seed=3)
     _, depth = pkg.synthetic.redweb_frame(0, h, w)

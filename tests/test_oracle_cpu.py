@@ -153,3 +153,19 @@ def test_inpaint_mask_oracle_matches_reference(golden):
     for b in range(g["mask_valid"].shape[0]):
         assert np.array_equal(oflow.inpaint_mask(g["mask_valid"][b, 0], g["mask_collision"][b, 0]), g["mask_out"][b, 0])
     assert g["mask_out"].any() and not g["mask_out"].all()
+
+
+def test_bilateral_mask_path_oracle_matches_reference(golden):
+    """oracle/bilateral.py with a binary mask == the reference's mask path (golden m_* cases: uint8, float64 and bool masks)."""
+    import numpy as np
+
+    from oracle import bilateral as obil
+
+    g = golden("bilateral_cases")
+    for tag in ("m_f32_u8", "m_f32_f64", "m_f64_bool"):
+        fs = [int(v) for v in g[f"{tag}_fs"]]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            got = obil.sparse_bilateral_filtering(g[f"{tag}_in"].copy(), fs, 0.04, len(fs), mask=g[f"{tag}_mask"])
+        assert got.dtype == g[f"{tag}_out"].dtype and np.array_equal(got, g[f"{tag}_out"], equal_nan=True), tag
+    assert np.array_equal(obil.rank_table(225, np.float64), g["rank_table_f64"])
+    assert not np.array_equal(g["rank_table"], g["rank_table_f64"])
