@@ -257,7 +257,7 @@ int ofd_bilateral_iter(const void* depth_in, const void* depth_orig, int dtype, 
                        double threshold, void* depth_out, ofd_stream_t stream);
 
 /*
- * ofd_bilateral_iter_masked — one iteration with the reference's BINARY mask (bilateral_filter.py:48-49,72-80,156,160-162,181-182):
+ * ofd_bilateral_iter_masked — one iteration with the reference's BINARY mask (bilateral_filter.py:48-49,72-80,161,169-170,180-182):
  * a neighbour difference counts only between two unmasked pixels; masked pixels are never discontinuities and keep their depth;
  * masked taps and taps outside the image (the mask is zero-padded, not ring-replicated) are left out of the median.
  * mask: uint8 [H,W] on the device, 0 = masked.  mask_coef_f64: 1 when the reference's mask array is float64 or integer (its median

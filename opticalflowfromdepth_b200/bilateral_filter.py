@@ -34,7 +34,7 @@ def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4
     cur = d0
     m_u8, coef_f64 = None, False
     if mask is not None:
-        # the reference's mask path with a BINARY mask; its median coefficients are float32 * mask.dtype (bilateral_filter.py:185-187)
+        # the reference's mask path with a BINARY mask; its median coefficients are float32 * mask.dtype (bilateral_filter.py:180-182)
         mk = torch.as_tensor(np.asarray(mask) if isinstance(mask, np.ndarray) else mask)
         if tuple(mk.shape) != tuple(d0.shape):
             raise ValueError("mask must have the shape of depth")

@@ -113,7 +113,7 @@ struct KRank {
     unsigned char k[MAX_WIN * MAX_WIN + 3];
 };
 
-// coef_f64: the coefficients are float64 (mask path with a float64 / integer mask, bilateral_filter.py:187), else float32
+// coef_f64: the coefficients are float64 (mask path with a float64 / integer mask, bilateral_filter.py:182), else float32
 static KRank make_krank(int window, bool coef_f64 = false) {
     KRank kr = {};
     for (int n = 1; n <= window * window; ++n) {
@@ -139,7 +139,7 @@ static KRank make_krank(int window, bool coef_f64 = false) {
 }
 
 // WS > 0: compile-time window (register sort); WS == 0: run-time window (rank count in shared memory)
-// MASK: the reference's binary-mask path (bilateral_filter.py:48-49,72-80,156,160-162,181-182; WS > 0 only): a neighbour difference
+// MASK: the reference's binary-mask path (bilateral_filter.py:48-49,72-80,161,169-170,180-182; WS > 0 only): a neighbour difference
 // counts only between two unmasked pixels, masked pixels are never discontinuities and keep their depth, masked taps and taps
 // outside the image (the mask is zero-padded, not ring-replicated) are left out of the median.  Flag byte: bit 0 discontinuity,
 // bit 1 depth_orig == 0, bit 2 unmasked.
@@ -197,7 +197,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
                 sraw[e] = dv[k];
                 sinv[e] = (DT)1.0 / dv[k];
                 unsigned char f = (ov[k] == (DT)0) ? 2 : 0;  // bit 1: forced discontinuity (:46)
-                if (MASK) f |= mv[k] ? 4 : 0;                // bit 2: unmasked (zero outside the image: the zero padding of :156)
+                if (MASK) f |= mv[k] ? 4 : 0;                // bit 2: unmasked (zero outside the image: the zero padding of :161)
                 sflag[e] = f;
             }
         }
@@ -332,7 +332,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
         const int r = tile_y * BT_H + ty;
         const bool inside = r < H && c < W;
         bool need = inside && n_disc_row[rr] > 0 && n_disc_row[rr] < win * win;
-        if constexpr (MASK)  // masked pixels are skipped (:160-162); the median needs at least one tap that is neither (:188-190)
+        if constexpr (MASK)  // masked pixels are skipped (:169-170); the median needs at least one tap that is neither (:188-190)
             need = inside && n_disc_row[rr] > 0 && n_excl_row[rr] < win * win && (sflag[(ty + m + 2) * RW + threadIdx.x + m + 2] & 4) != 0;
         if (inside && !need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
         const unsigned lane = tid & 31u;

@@ -30,7 +30,7 @@ from torch import nn
 
 from . import _lib, geometry, ops, sweep, synthesis
 
-AUGMENT_TYPES = [0, 5, 6, 7, 1, 5, 6, 7, 2, 5, 6, 7]  # preprocess.py:455
+AUGMENT_TYPES = [0, 5, 6, 7, 1, 5, 6, 7, 2, 5, 6, 7]  # preprocess.py:454
 GROUP_CHANNELS = ("img0", "depth0", "img1", "depth1", "img2", "depth2", "img3", "depth3", "img2_prime", "depth2_prime",
                   "img3_prime", "depth3_prime", "flow01", "back_flow01", "flow12", "back_flow12", "flow02",
                   "back_flow02_prime", "flow03", "back_flow03", "flow13", "back_flow13_prime")  # preprocess.py:437-441

@@ -14,7 +14,7 @@ import numpy as np
 
 def rank_table(nmax, coef_dtype=np.float32):
     """k(n) = #{m <= n : running sum (in coef_dtype) of m copies of 1/n <= 0.5}  (bilateral_filter.py:194-197).  The coefficients
-    are float32 without a mask (:185) and float32 * mask.dtype with one (:187: float64 for float64 / integer masks)."""
+    are float32 without a mask (:180) and float32 * mask.dtype with one (:182: float64 for float64 / integer masks)."""
     k = np.zeros(nmax + 1, np.int64)
     for n in range(1, nmax + 1):
         coef = np.ones(n, coef_dtype)
@@ -48,8 +48,8 @@ def discontinuity(depth, depth_orig, thr, mask=None):
 
 def bilateral_iter(depth, depth_orig, window, thr, mask=None):
     """One iteration (bilateral_filter.py:33-58) -> new depth [H,W], same dtype.  mask: BINARY (0 / non-zero... the weighted case of
-    a fractional mask is not restated); masked pixels keep their (ring-replicated) depth (:160-162), masked taps - and taps outside
-    the image, the mask being zero-padded (:156) - are left out of the median (:181-182)."""
+    a fractional mask is not restated); masked pixels keep their (ring-replicated) depth (:169-170), masked taps - and taps outside
+    the image, the mask being zero-padded (:161) - are left out of the median (:180-182)."""
     if mask is not None:
         return _bilateral_iter_masked(depth, depth_orig, window, thr, mask)
     with np.errstate(divide="ignore"):

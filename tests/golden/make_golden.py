@@ -235,7 +235,7 @@ def bilateral_cases(ref_bil):
         out[f"{tag}_in"], out[f"{tag}_out"] = depth, ref
         out[f"{tag}_fs"] = np.array(fs)
     out["rank_table"] = obil.rank_table(225)
-    # the mask path (bilateral_filter.py:48-49,72-80,156,160-162,181-182) with BINARY masks of three dtypes: the median
+    # the mask path (bilateral_filter.py:48-49,72-80,161,169-170,180-182) with BINARY masks of three dtypes: the median
     # coefficients are float32 * mask.dtype, so the rank rule runs in float32 (uint8 / bool masks) or float64 (float64 masks)
     for tag, dt, mdt, (h, w), fs in (("m_f32_u8", np.float32, np.uint8, (36, 52), [7, 5, 5]), ("m_f32_f64", np.float32, np.float64, (30, 44), [7, 7, 5]),
                                      ("m_f64_bool", np.float64, np.bool_, (28, 33), [5, 3])):
