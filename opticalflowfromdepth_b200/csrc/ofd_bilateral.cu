@@ -8,18 +8,20 @@
 //   pixels with disc == 0 (centre value when n == 0); all other pixels keep the (ring-replicated) depth   :167-198
 //   k(n) = #{ m in 1..n : float32 running sum of m copies of float32(1/n) <= 0.5 }   :194-197 (cumsum + digitize)
 //
-// Kernel plan (one CTA = a 32x8 output tile, all staging in shared memory, 4-12 B/px of HBM traffic):
-//   1. the raw depth tile with a halo of window/2 + 2 is loaded once (zero outside the image) and 1/d is formed once
-//      per cell - not once per tap;
+// Kernel plan (one CTA of 256 threads = a 32x32 output tile, all staging in shared memory, 4-12 B/px of HBM traffic):
+//   1. the raw depth tile with a halo of window/2 + 2 is loaded once (zero outside the image; every global load of a thread
+//      is issued before the first use) and 1/d is formed once per cell - not once per tap;
 //   2. the discontinuity flag of every interior cell comes from its four shared-memory neighbours;
-//   3. a replication pass applies the reference's border rule (every tap reads row clamp(r,1,H-2), column
-//      clamp(c,1,W-2)) so the window taps are plain offsets;
-//   4. pixels whose window holds a discontinuity are COMPACTED into a per-tile list (so the selection runs in full
-//      warps), pull their window into REGISTERS (discontinuity taps -> +inf) and sort it with a fully unrolled odd-even
-//      merge-sort network over exactly 9/25/49 keys (28/140/394 compare-exchanges of 2 FMNMX each; the half of the
+//   3. tiles on the image border run a replication pass that applies the reference's border rule (every tap reads row
+//      clamp(r,1,H-2), column clamp(c,1,W-2)); interior tiles read the raw tile in place;
+//   4. one 64-bit discontinuity mask per window row (ballots); every thread counts the windows of its 4 consecutive rows
+//      with sliding sums; pixels whose window holds a discontinuity are COMPACTED into a per-tile list (so the selection
+//      runs in full warps), pull their window into REGISTERS (discontinuity taps -> +inf) and sort it with a fully unrolled
+//      odd-even merge-sort network over exactly 9/25/49 keys (28/140/394 compare-exchanges of 2 FMNMX each; the half of the
 //      outputs that can never be selected is dead code); other window sizes use a rank count in shared memory.
-// A TMA 2-D tiled load was considered for step 1 (the north star suggests it); a 40x16 float tile is 2.5 loads per
-// thread, so plain coalesced loads are as fast and need no tensor map per call - the time goes into step 4.
+// Variants: a ragged batch (one launch for images of different sizes) and the reference's binary-mask path.
+// The kernel is instruction-bound, not HBM-bound; a TMA 2-D tiled load for step 1 (the north star
+// suggests it) would not change that: a 42x42 float tile is 7 plain coalesced loads per thread and needs no tensor map.
 #include "ofd_common.cuh"
 
 namespace ofd {
