@@ -200,10 +200,11 @@ __global__ void __launch_bounds__(256) pair_row_kernel(const float* __restrict__
 // ---- v2: persistent, TMA-in / TMA-out row pipeline ---------------------------------------------------------------
 // ncu on the one-row-per-CTA kernel above showed it ISSUE-bound (sm__throughput 84 %, ~330 instructions per pixel,
 // mostly 64-bit global address arithmetic and scalar stores), not HBM-bound.  Here every global access is a TMA
-// 1-D bulk copy (UBLKCP): input rows are prefetched one row ahead into a 2-stage ring, results are staged in
-// shared memory and written back by bulk stores that drain while the next row is computed; the SIMT threads only
-// touch shared memory (32-bit addressing, no per-pixel global pointer math).  Each thread owns NITER fixed pixels
-// of the row and keeps their target column and ordered depth in registers across the three z-buffer phases.
+// 1-D bulk copy (UBLKCP): input rows are prefetched up to three work units ahead into an mbarrier ring (2-4 stages, chosen per
+// row width), results are staged in a 1-3 deep shared-memory ring and written back by bulk stores that drain while the next
+// units are computed; the SIMT threads only touch shared memory (32-bit addressing, no per-pixel global pointer math).  Each
+// thread owns NITER fixed pixels of the (virtual) row and keeps their target column and ordered depth in registers across
+// the three z-buffer phases.
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                  : "memory");
