@@ -80,6 +80,21 @@ def trial_bilateral(rng):
     return ok, f"bilateral {[d.shape for d in depths]} windows {fs}"
 
 
+def trial_bilateral_masked(rng):
+    """The binary-mask path of the gated median (uint8 / float64 masks: float32 / float64 rank rule)."""
+    h, w = int(rng.integers(3, 90)), int(rng.integers(3, 130))
+    dt = np.float32 if rng.random() < 0.7 else np.float64
+    d = depth_field(rng, h, w, rng.random() < 0.5).astype(dt)
+    if rng.random() < 0.4:
+        d[rng.integers(0, h), rng.integers(0, w)] = 0
+    mask = (rng.random((h, w)) > rng.uniform(0.0, 0.6)).astype(np.uint8 if rng.random() < 0.5 else np.float64)
+    fs = [int(rng.choice([3, 5, 7])) for _ in range(2)]
+    got = bilateral_filter.sparse_bilateral_filtering(d.copy(), None, fs, depth_threshold=0.04, mask=mask, num_iter=2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = obil.sparse_bilateral_filtering(d.copy(), fs, 0.04, 2, mask=mask)
+    return bool(np.array_equal(got, want, equal_nan=True)), f"bilateral masked {h}x{w} {dt.__name__} mask {mask.dtype} windows {fs}"
+
+
 def trial_reproject_pair(rng):
     """Fused 6-DoF pair: flow within the path's tolerance of the torch restatement, splat bit-exact given OUR flow."""
     from oracle import flow as oflow
@@ -151,7 +166,7 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, counts, fails = time.time(), {}, []
-    trials = (trial_pair, trial_splat, trial_bilateral, trial_reproject_pair, trial_augment)
+    trials = (trial_pair, trial_splat, trial_bilateral, trial_bilateral_masked, trial_reproject_pair, trial_augment)
     k = 0
     while time.time() - t0 < budget:
         fn = trials[k % len(trials)]
