@@ -282,7 +282,9 @@ int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int d
  * tensors binds; the reference crosses host<->device around every FW call, preprocess.py:350-366,437-447).
  * A pipeline owns three device staging slots with one stream each: chunk k does host->device copies, the pair
  * kernel and device->host copies on slot k%3, so both copy engines and the SMs overlap.  Host buffers should be
- * page-locked for the copies to overlap.  `run` returns after every result byte has landed in the host buffers.
+ * page-locked for the copies to overlap.  `run` returns after every result byte has landed in the host buffers.  The y planes of
+ * flow and back_flow are constants of the virtual-stereo pair (-0.0 / +0.0): they are not transferred (8 of the 40 result bytes per
+ * pixel) but written into the host buffers by a host thread while the copies run - the buffers end up complete either way.
  */
 typedef struct ofd_pair_pipeline ofd_pair_pipeline;
 int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out);

@@ -2,7 +2,10 @@
 // binds (the reference moves every frame host->device->host around its FW call, preprocess.py:350-366,437-447).
 // A pipeline owns NSLOT device staging slots, each with its own stream; chunk k runs H2D -> pair kernel -> D2H
 // on slot k % NSLOT, so the two copy engines and the SMs overlap across chunks.
+#include <emmintrin.h>
+
 #include <new>
+#include <thread>
 
 #include "ofd_common.cuh"
 
@@ -28,6 +31,16 @@ __global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict_
 }  // namespace ofd
 
 using namespace ofd;
+
+// constant plane written by the host: non-temporal stores (the plane is not read back by this thread; no read-for-ownership)
+static void fill_plane(float* dst, size_t n, float value) {
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15)) dst[i++] = value;
+    const __m128 v = _mm_set1_ps(value);
+    for (; i + 4 <= n; i += 4) _mm_stream_ps(dst + i, v);
+    for (; i < n; ++i) dst[i] = value;
+    _mm_sfence();
+}
 
 #define OFD_CUDA(call)                                                                    \
     do {                                                                                  \
@@ -88,6 +101,25 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         return fail(OFD_E_NULL, "%s: NULL host pointer", fn);
     OFD_CUDA(cudaSetDevice(p->device));
     const size_t hw = (size_t)p->H * p->W, F = sizeof(float);
+    // The y planes of both flows are constants of the virtual-stereo pair (flow.y == -0.0, back_flow.y == +0.0, preprocess.py:253,
+    // 361-363): they are not sent over PCIe (8 of the 40 result bytes per pixel) but written into the host buffers by a host
+    // thread while the copies run.
+    constexpr int kFillers = 4;
+    std::thread fillers[kFillers];
+    struct Joiner {
+        std::thread* t;
+        ~Joiner() {
+            for (int i = 0; i < kFillers; ++i)
+                if (t[i].joinable()) t[i].join();
+        }
+    } joiner{fillers};
+    for (int f = 0; f < kFillers; ++f)
+        fillers[f] = std::thread([=]() {
+            for (int b = f; b < B; b += kFillers) {
+                fill_plane(back_flow_host + ((size_t)b * 2 + 1) * hw, hw, 0.0f);
+                if (flow_host) fill_plane(flow_host + ((size_t)b * 2 + 1) * hw, hw, -0.0f);
+            }
+        });
     int k = 0;
     for (int b0 = 0; b0 < B; b0 += p->chunk, ++k) {
         const int s = k % ofd_pair_pipeline::NSLOT;
@@ -111,15 +143,16 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         if (rc) return rc;
         OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
         OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
-        OFD_CUDA(cudaMemcpyAsync(back_flow_host + (size_t)b0 * 2 * hw, o_bf, n * 2 * hw * F, cudaMemcpyDeviceToHost, st));
+        // x planes only: plane 0 of every [2,H,W] frame (pitch 2*hw floats on both sides)
+        OFD_CUDA(cudaMemcpy2DAsync(back_flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_bf, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
         if (flow_host)
-            OFD_CUDA(cudaMemcpyAsync(flow_host + (size_t)b0 * 2 * hw, o_fl, n * 2 * hw * F, cudaMemcpyDeviceToHost, st));
+            OFD_CUDA(cudaMemcpy2DAsync(flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_fl, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
         OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
         if (collision_host)
             OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
-    return OFD_OK;
+    return OFD_OK;  // ~Joiner waits for the host fills
 }
 
 // Compact transport of the same pipeline: colour and masks as uint8, the two constant planes (flow.y == -0.0,

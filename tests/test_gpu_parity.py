@@ -312,12 +312,19 @@ def test_pair_pipeline_host_front_end(pkg):
     img = torch.from_numpy(rng.integers(0, 256, (B, 3, h, w)).astype(np.float32)).pin_memory()
     depth = torch.from_numpy(rng.integers(1, 60, (B, 1, h, w)).astype(np.float32)).pin_memory()
     sBf = torch.from_numpy(rng.uniform(40, 55, B).astype(np.float32))
-    outs = [torch.empty((B, c, h, w)).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+    outs = [torch.full((B, c, h, w), 7.0).pin_memory() for c in (3, 1, 2, 2, 1, 1)]  # poisoned: every plane must be written
     pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=3)
     pipe.run(img, depth, sBf, *outs)
-    pipe.close()
     want = oracle.disparity_pair(img.numpy(), depth.numpy(), sBf.numpy())
     for o, wnt in zip(outs, want):
+        assert np.array_equal(o.numpy(), wnt)
+    # the constant planes are written on the host, bit patterns included: flow.y == -0.0, back_flow.y == +0.0
+    assert np.signbit(outs[3].numpy()[:, 1]).all() and not np.signbit(outs[2].numpy()[:, 1]).any()
+    # optional outputs skipped: flow and collision NULL
+    outs2 = [torch.full((B, c, h, w), 7.0).pin_memory() for c in (3, 1, 2, 1)]
+    pipe.run(img, depth, sBf, outs2[0], outs2[1], outs2[2], None, outs2[3], None)
+    pipe.close()
+    for o, wnt in zip(outs2, (want[0], want[1], want[2], want[4])):
         assert np.array_equal(o.numpy(), wnt)
 
 
@@ -1233,7 +1240,8 @@ def test_bench_default_arm_prints_the_contract_line():
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1.05 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert rf["traffic"] is None or rf["traffic"] > 0
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16 * (4 * 480 * 640 * 4 + 4) and e["d2h_bytes_per_step"] == 16 * 10 * 480 * 640 * 4
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16 * (4 * 480 * 640 * 4 + 4)
+    assert e["d2h_bytes_per_step"] + e["host_filled_bytes_per_step"] == 16 * 10 * 480 * 640 * 4  # every result plane lands in host memory
     assert e["value"] < d["value"]  # host buffers cross PCIe: never the device-resident number
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["counters"]["frames"] == 32 and d["counters"]["hit"] + d["counters"]["hole"] == 32 * 480 * 640
