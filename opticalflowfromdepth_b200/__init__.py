@@ -8,7 +8,10 @@ Product layout (only what the path needs):
     bilateral_filter.py  sparse_bilateral_filtering
     synthesis.py         Plausible / Convert / ConcatFlow / BackFlow / SpecialFlow / augment_flow, batched
                          synthesize_pairs / synthesize_group
-    sweep.py             multi-GPU sharding of frames by image index + end-of-run counter reduction
+    sweep.py             multi-GPU sharding of frames by image index + end-of-run counter reduction, host-in / host-out sweep
+    preprocess.py        the reference's driver (PreprocessPlusAugment, CLI) over the fused path, asynchronous .npz writer
+    dataloader.py        the training-side reader of those files (host code)
+    synthetic.py         seeded DIML- / ReDWeb-shaped synthetic frames for tests and benches
 """
 from . import _lib, ops  # noqa: F401
 from .fw import FW  # noqa: F401
