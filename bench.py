@@ -481,11 +481,12 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": world * Fe * Ke / float(te_t.item()), "unit": "pairs/s",
-                       "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * 8 * H * W * 4,
-                       "host_filled_bytes_per_step": Fe * 2 * H * W * 4,
+                       "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * (6 * H * W * 4 + H * W),
+                       "host_filled_bytes_per_step": Fe * 4 * H * W * 4,
                        "frames_per_step": Fe, "steps": Ke,
                        "api": "ofd_pair_pipeline_run (C ABI, pinned float32 host buffers in and out - all 10 result planes, 3-slot H2D/kernel/D2H pipeline; "
-                              "the two constant planes flow.y / back_flow.y are written by a host thread instead of crossing PCIe)"}
+                              "the two constant planes flow.y / back_flow.y are written by host threads instead of crossing PCIe, valid / collision cross as one "
+                              "packed byte per pixel and are expanded into the float planes by the same threads)"}
 
     if "e2e" not in skip and "compact" not in skip:
         # same pipeline with the compact transport (uint8 colour + masks, constant planes not transferred): extra information,

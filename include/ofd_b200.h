@@ -284,7 +284,10 @@ int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int d
  * kernel and device->host copies on slot k%3, so both copy engines and the SMs overlap.  Host buffers should be
  * page-locked for the copies to overlap.  `run` returns after every result byte has landed in the host buffers.  The y planes of
  * flow and back_flow are constants of the virtual-stereo pair (-0.0 / +0.0): they are not transferred (8 of the 40 result bytes per
- * pixel) but written into the host buffers by a host thread while the copies run - the buffers end up complete either way.
+ * pixel) but written into the host buffers by host threads while the copies run; valid / collision (0.0f / 1.0f planes) cross PCIe as
+ * one packed byte per pixel and are expanded into the caller's float planes by the same threads (25 instead of 40 B/px on the wire,
+ * H*W a multiple of 4) - the buffers end up complete and bit-identical either way.  OFD_HOST_WORKERS (default 2) sets the thread count,
+ * OFD_HOST_MASK_BYTES=0 sends the masks as float planes.
  */
 typedef struct ofd_pair_pipeline ofd_pair_pipeline;
 int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out);

@@ -4,8 +4,11 @@
 // on slot k % NSLOT, so the two copy engines and the SMs overlap across chunks.
 #include <emmintrin.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <new>
 #include <thread>
+#include <vector>
 
 #include "ofd_common.cuh"
 
@@ -17,6 +20,11 @@ struct ofd_pair_pipeline {
     float* d_out[NSLOT];  // img1 (3) | depth1 (1) | back_flow (2) | flow (2) | valid (1) | collision (1)
     float* d_s[NSLOT];
     unsigned char* d_u8[NSLOT];  // compact transport staging: img0 u8 (3) in | img1 u8 (3) + valid (1) + collision (1) out
+    // float32 contract: valid / collision cross PCIe as ONE byte per pixel (bit 0 / bit 1) into this pinned buffer and are
+    // expanded into the caller's float planes by host threads (grow-only, B * H * W bytes)
+    unsigned char* h_mask;
+    size_t h_mask_cap;
+    std::vector<cudaEvent_t> ev;  // one per chunk of a run: "this chunk's mask bytes have landed"
 };
 
 namespace ofd {
@@ -27,6 +35,21 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const unsigned char* __r
 __global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (unsigned char)__float2uint_rn(fminf(fmaxf(in[i], 0.0f), 255.0f));
+}
+// valid (bit 0) and collision (bit 1) of four pixels per thread
+__global__ void __launch_bounds__(256) pack_masks_kernel(const float4* __restrict__ valid, const float4* __restrict__ collision,
+                                                         uchar4* __restrict__ out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = valid[i];
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (collision) c = collision[i];
+        uchar4 o;
+        o.x = (unsigned char)((v.x != 0.f) | ((c.x != 0.f) << 1));
+        o.y = (unsigned char)((v.y != 0.f) | ((c.y != 0.f) << 1));
+        o.z = (unsigned char)((v.z != 0.f) | ((c.z != 0.f) << 1));
+        o.w = (unsigned char)((v.w != 0.f) | ((c.w != 0.f) << 1));
+        out[i] = o;
+    }
 }
 }  // namespace ofd
 
@@ -40,6 +63,31 @@ static void fill_plane(float* dst, size_t n, float value) {
     for (; i + 4 <= n; i += 4) _mm_stream_ps(dst + i, v);
     for (; i < n; ++i) dst[i] = value;
     _mm_sfence();
+}
+
+// bit `shift` of 16 mask bytes -> 16 floats (0.0f / 1.0f), non-temporal stores (dst 16-byte aligned)
+static inline void expand16(__m128i b, int shift, float* dst) {
+    const __m128i z = _mm_setzero_si128();
+    const __m128i m = _mm_and_si128(_mm_srl_epi16(b, _mm_cvtsi32_si128(shift)), _mm_set1_epi8(1));
+    const __m128i lo = _mm_unpacklo_epi8(m, z), hi = _mm_unpackhi_epi8(m, z);
+    const __m128 f0 = _mm_cvtepi32_ps(_mm_unpacklo_epi16(lo, z)), f1 = _mm_cvtepi32_ps(_mm_unpackhi_epi16(lo, z));
+    const __m128 f2 = _mm_cvtepi32_ps(_mm_unpacklo_epi16(hi, z)), f3 = _mm_cvtepi32_ps(_mm_unpackhi_epi16(hi, z));
+    _mm_stream_ps(dst, f0), _mm_stream_ps(dst + 4, f1), _mm_stream_ps(dst + 8, f2), _mm_stream_ps(dst + 12, f3);
+}
+
+static void expand_plane(const unsigned char* m, size_t n, int shift, float* dst) {
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15)) dst[i] = (float)((m[i] >> shift) & 1), ++i;
+    for (; i + 16 <= n; i += 16) expand16(_mm_loadu_si128((const __m128i*)(m + i)), shift, dst + i);
+    for (; i < n; ++i) dst[i] = (float)((m[i] >> shift) & 1);
+    _mm_sfence();
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
 }
 
 #define OFD_CUDA(call)                                                                    \
@@ -60,6 +108,8 @@ void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
         cudaFree(p->d_s[s]);
         cudaFree(p->d_u8[s]);
     }
+    for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+    if (p->h_mask) cudaFreeHost(p->h_mask);
     delete p;
 }
 
@@ -71,6 +121,7 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     ofd_pair_pipeline* p = new (std::nothrow) ofd_pair_pipeline();
     if (!p) return fail(OFD_E_ARG, "ofd_pair_pipeline_create: out of host memory");
     p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
+    p->h_mask = nullptr, p->h_mask_cap = 0;
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) p->st[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
@@ -101,27 +152,71 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         return fail(OFD_E_NULL, "%s: NULL host pointer", fn);
     OFD_CUDA(cudaSetDevice(p->device));
     const size_t hw = (size_t)p->H * p->W, F = sizeof(float);
-    // The y planes of both flows are constants of the virtual-stereo pair (flow.y == -0.0, back_flow.y == +0.0, preprocess.py:253,
-    // 361-363): they are not sent over PCIe (8 of the 40 result bytes per pixel) but written into the host buffers by a host
-    // thread while the copies run.
-    constexpr int kFillers = 4;
-    std::thread fillers[kFillers];
-    struct Joiner {
-        std::thread* t;
-        ~Joiner() {
-            for (int i = 0; i < kFillers; ++i)
-                if (t[i].joinable()) t[i].join();
+    // Two things do not cross PCIe as float planes (14 of the 40 result bytes per pixel):
+    //  - the y planes of both flows are constants of the virtual-stereo pair (flow.y == -0.0, back_flow.y == +0.0,
+    //    preprocess.py:253,361-363) and are written into the host buffers by host threads;
+    //  - valid / collision are 0.0f / 1.0f planes: they are packed on the device into one byte per pixel, land in the
+    //    pipeline's pinned staging buffer and are expanded into the caller's float planes by the same host threads,
+    //    chunk by chunk, as soon as a chunk's event fires.   OFD_HOST_MASK_BYTES=0 sends them as float planes instead.
+    static const int kWorkers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
+    static const bool kMaskBytes = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
+    const bool mask_bytes = kMaskBytes && hw % 4 == 0;
+    const int K = (B + p->chunk - 1) / p->chunk;
+    if (mask_bytes) {
+        if (p->h_mask_cap < (size_t)B * hw) {
+            if (p->h_mask) cudaFreeHost(p->h_mask);
+            p->h_mask = nullptr, p->h_mask_cap = 0;
+            OFD_CUDA(cudaHostAlloc((void**)&p->h_mask, (size_t)B * hw, cudaHostAllocDefault));
+            p->h_mask_cap = (size_t)B * hw;
         }
-    } joiner{fillers};
-    for (int f = 0; f < kFillers; ++f)
-        fillers[f] = std::thread([=]() {
-            for (int b = f; b < B; b += kFillers) {
-                fill_plane(back_flow_host + ((size_t)b * 2 + 1) * hw, hw, 0.0f);
-                if (flow_host) fill_plane(flow_host + ((size_t)b * 2 + 1) * hw, hw, -0.0f);
+        while ((int)p->ev.size() < K) {
+            cudaEvent_t e;
+            OFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->ev.push_back(e);
+        }
+    }
+    std::atomic<int> issued{0};      // chunks whose event has been recorded in THIS run
+    std::atomic<bool> abort_run{false};
+    std::vector<std::thread> workers((size_t)kWorkers);
+    struct Joiner {
+        std::vector<std::thread>& t;
+        std::atomic<bool>& abort_run;
+        bool ok = false;
+        ~Joiner() {
+            if (!ok) abort_run = true;
+            for (auto& th : t)
+                if (th.joinable()) th.join();
+        }
+    } joiner{workers, abort_run};
+    const int chunk = p->chunk, device = p->device;
+    const unsigned char* h_mask = p->h_mask;
+    const cudaEvent_t* ev = p->ev.data();
+    for (int t = 0; t < kWorkers; ++t)
+        workers[(size_t)t] = std::thread([=, &issued, &abort_run]() {
+            if (mask_bytes) cudaSetDevice(device);
+            for (int k = 0; k < K; ++k) {
+                const int b0 = k * chunk, n = (B - b0) < chunk ? (B - b0) : chunk;
+                for (int b = b0 + t; b < b0 + n; b += kWorkers) {
+                    fill_plane(back_flow_host + ((size_t)b * 2 + 1) * hw, hw, 0.0f);
+                    if (flow_host) fill_plane(flow_host + ((size_t)b * 2 + 1) * hw, hw, -0.0f);
+                }
+                if (!mask_bytes) continue;
+                while (issued.load(std::memory_order_acquire) <= k) {
+                    if (abort_run.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                if (cudaEventSynchronize(ev[k]) != cudaSuccess) return;  // the main thread reports the stream's error
+                // this worker's 16-pixel-aligned share of the chunk
+                const size_t len = (size_t)n * hw, per = ((len + kWorkers - 1) / kWorkers + 15) & ~(size_t)15;
+                const size_t lo = per * t < len ? per * t : len, hi = lo + per < len ? lo + per : len;
+                if (hi > lo) {
+                    const size_t o = (size_t)b0 * hw + lo;
+                    expand_plane(h_mask + o, hi - lo, 0, valid_host + o);
+                    if (collision_host) expand_plane(h_mask + o, hi - lo, 1, collision_host + o);
+                }
             }
         });
-    int k = 0;
-    for (int b0 = 0; b0 < B; b0 += p->chunk, ++k) {
+    for (int k = 0, b0 = 0; b0 < B; b0 += p->chunk, ++k) {
         const int s = k % ofd_pair_pipeline::NSLOT;
         const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
         cudaStream_t st = p->st[s];
@@ -141,18 +236,31 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[s], (int)n, p->H, p->W, o_img, o_dep, o_bf,
                                     flow_host ? o_fl : nullptr, o_val, collision_host ? o_col : nullptr, nullptr, st);
         if (rc) return rc;
+        if (mask_bytes) {
+            pack_masks_kernel<<<296, 256, 0, st>>>((const float4*)o_val, collision_host ? (const float4*)o_col : nullptr,
+                                                   (uchar4*)p->d_u8[s], n * hw / 4);
+            rc = check_launch(fn);
+            if (rc) return rc;
+            // masks first: the host expansion of this chunk overlaps the float planes' copies
+            OFD_CUDA(cudaMemcpyAsync(p->h_mask + (size_t)b0 * hw, p->d_u8[s], n * hw, cudaMemcpyDeviceToHost, st));
+            OFD_CUDA(cudaEventRecord(p->ev[(size_t)k], st));
+            issued.store(k + 1, std::memory_order_release);
+        }
         OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
         OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
         // x planes only: plane 0 of every [2,H,W] frame (pitch 2*hw floats on both sides)
         OFD_CUDA(cudaMemcpy2DAsync(back_flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_bf, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
         if (flow_host)
             OFD_CUDA(cudaMemcpy2DAsync(flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_fl, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
-        OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
-        if (collision_host)
-            OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+        if (!mask_bytes) {
+            OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
+            if (collision_host)
+                OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+        }
     }
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
-    return OFD_OK;  // ~Joiner waits for the host fills
+    joiner.ok = true;
+    return OFD_OK;  // ~Joiner waits for the host fills and mask expansions
 }
 
 // Compact transport of the same pipeline: colour and masks as uint8, the two constant planes (flow.y == -0.0,
