@@ -259,7 +259,7 @@ def run_ours(args):
                    "frames_per_step_per_gpu": F, "H": H, "W": W, "parallelism": f"frames sharded by image index over {world} GPU(s), no collective on the hot path",
                    "l2": f"inputs {F * 4 * H * W * 4 / 1e6:.0f} MB + outputs {F * 10 * H * W * 4 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)"},
         "gpu_launches": K,
-        "roofline": {"bound": "hbm", "kernel": "pair_rows_persistent<float,2,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pair_rows_persistent<float,2,PAIR_ROW>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_px": PAIR_BYTES_PER_PX, "bytes_per_launch": PAIR_BYTES_PER_PX * H * W * F},
@@ -331,7 +331,8 @@ def run_ours(args):
                     im, dp = synthetic.redweb_frame(k, hh, ww)
                     r_img.append(torch.from_numpy(im).to(dev)[None])
                     r_dep.append(torch.from_numpy(dp).to(dev)[None])
-                r_s = [torch.tensor([47.0], device=dev) for _ in sizes]
+                r_s = torch.full((len(sizes),), 47.0, device=dev)
+                r_img_packed = torch.cat([im.reshape(-1) for im in r_img])  # [3,H_i,W_i] blocks at 3 * pixel offset
                 mpx = sum(hh * ww for hh, ww in sizes) / 1e6
 
                 def cfg2_filter():
@@ -339,20 +340,29 @@ def run_ours(args):
                                                                 normalize=True)
 
                 def cfg2_step():
-                    fd = cfg2_filter()
-                    for im, d, sv in zip(r_img, fd, r_s):
-                        ops.disparity_pair(im, d[None, None], sv)
+                    fd, shp, offs = bfm.sparse_bilateral_filtering_batch([d[0, 0] for d in r_dep], [7, 7, 5, 5, 5], depth_threshold=0.04,
+                                                                         num_iter=5, normalize=True, return_packed=True)
+                    ops.disparity_pair_ragged(r_img_packed, fd, r_s, shp, offs)
+
+                def cfg2_pairs_only():
+                    ops.disparity_pair_ragged(r_img_packed, cfg2_fd[0], r_s, cfg2_fd[1], cfg2_fd[2])
+
+                cfg2_fd = bfm.sparse_bilateral_filtering_batch([d[0, 0] for d in r_dep], [7, 7, 5, 5, 5], depth_threshold=0.04,
+                                                               num_iter=5, normalize=True, return_packed=True)
 
                 t_f = timed(cfg2_filter, 10, 3, sync, barrier) / 10
                 t_all = timed(cfg2_step, 10, 3, sync, barrier) / 10
+                t_p = timed(cfg2_pairs_only, 10, 3, sync, barrier) / 10
                 d2 = depth[0, 0].contiguous()
                 tbil = timed(lambda: bfm.sparse_bilateral_filtering(d2, None, [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5), 10, 3, sync, barrier) / 10
                 extras["cfg2_redweb_ragged_b16"] = {"frames_per_s": len(sizes) / t_all, "ms_per_step": 1e3 * t_all, "frames_per_step": len(sizes),
                                                     "megapixels_per_step": mpx, "Mpx_per_s": mpx / t_all,
                                                     "bilateral_5iter_ms": 1e3 * t_f, "bilateral_Mpx_per_s_per_iter": 5 * mpx / t_f,
-                                                    "launches_per_step": 3 + 5 + len(sizes),
+                                                    "pairs_ms": 1e3 * t_p, "pairs_GBps": 56e6 * mpx / t_p / 1e9, "pairs_frac_of_measured_peak": 56e6 * mpx / t_p / 1e9 / peak,
+                                                    "launches_per_step": 3 + 5 + 1,
                                                     "what": "16 mixed-resolution frames (0.3-2 MP): normalize_depth (ofd_normalize_depth_ragged: 3 launches), 5 bilateral iterations "
-                                                            "(ofd_bilateral_iter_batch: 1 launch/iteration for the whole ragged batch), fused disparity pair (1 launch/frame)"}
+                                                            "(ofd_bilateral_iter_batch: 1 launch/iteration for the whole ragged batch), fused disparity pairs of all frames in one persistent launch "
+                                                            "(ofd_disparity_pair_ragged)"}
                 extras["cfg2_bilateral_480x640_5iter"] = {"ms_per_frame": 1e3 * tbil, "frames_per_s": 1.0 / tbil, "launches": 5}
             except Exception as e:
                 extras["cfg2_redweb_ragged_b16"] = {"error": repr(e)}

@@ -120,6 +120,19 @@ int ofd_disparity_pair(const float* img0, const void* depth0, int depth_dtype, c
                        float* collision, uint64_t* counters, ofd_stream_t stream);
 
 /*
+ * ofd_disparity_pair_ragged — ofd_disparity_pair over a RAGGED batch (BASELINE config 2: mixed-resolution frames, every frame
+ * synthesised exactly as the single-frame call would): image i is H_host[i] x W_host[i] and starts at PIXEL offset
+ * offset_host[i] of the packed buffers - a C-channel tensor stores it densely as [C,H_i,W_i] at element C * offset_host[i]
+ * (depth0 / depth1 / valid / collision: C = 1, img0 / img1: 3, back_flow / flow: 2); sBf[n_images] on the device.
+ * One persistent launch per 96 frames when every frame has H*W and its offset a multiple of 4 pixels (any W: work units may
+ * start on any pixel) and W <= ~2890; otherwise one launch per frame.  H_host / W_host / offset_host are HOST arrays.
+ */
+int ofd_disparity_pair_ragged(const float* img0, const void* depth0, int depth_dtype, const float* sBf, int n_images,
+                              const int* H_host, const int* W_host, const size_t* offset_host, float* img1, float* depth1,
+                              float* back_flow, float* flow /*nullable*/, float* valid, float* collision /*nullable*/,
+                              uint64_t* counters, ofd_stream_t stream);
+
+/*
  * ofd_reproject_flow — Convert.depth_to_random_flow (preprocess.py:265-298) = geometry.BackprojectDepth.forward
  * (geometry.py:37-42) + geometry.Project3D.forward (geometry.py:56-67) + de-normalisation, per pixel, fused:
  *   ray = invK3 (x,y,1);  X = depth*ray (float32);  c = P (X,1);  u = c.x/(c.z+eps), v = c.y/(c.z+eps);

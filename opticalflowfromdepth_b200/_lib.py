@@ -29,6 +29,7 @@ SIGNATURES = {
     "ofd_splat_flow": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
     "ofd_disparity_flow": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "ofd_disparity_pair": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ofd_disparity_pair_ragged": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ofd_reproject_flow": (_i, [_p, _i, _p, _f, _i, _i, _i, _p, _p]),
     "ofd_backproject": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "ofd_project": (_i, [_p, _p, _f, _i, _i, _i, _p, _p, _p]),

@@ -56,16 +56,17 @@ def sparse_bilateral_filtering(depth, image, filter_size, sigma_r=0.5, sigma_s=4
     return cur.cpu().numpy() if is_numpy else cur
 
 
-def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, num_iter=None, normalize=False):
+def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, num_iter=None, normalize=False, return_packed=False):
     """sparse_bilateral_filtering for a RAGGED batch of CUDA depth maps (BASELINE config 2: mixed-resolution frames): every
     depths[i] is an [H_i, W_i] tensor of one dtype and device, filtered independently exactly as the single-image call
     would, but each iteration is ONE launch over all images (ofd_bilateral_iter_batch).  Returns a list of tensors that are
     views into one packed buffer.  normalize=True first applies utils.normalize_depth to every image (one ragged launch
-    triple, ofd_normalize_depth_ragged) - the cfg2 front end `normalize_depth -> bilateral` without per-image launches."""
+    triple, ofd_normalize_depth_ragged) - the cfg2 front end `normalize_depth -> bilateral` without per-image launches.
+    return_packed=True returns (packed buffer, shapes, pixel offsets) instead - the layout ops.disparity_pair_ragged takes."""
     if num_iter is None:
         raise TypeError("'NoneType' object cannot be interpreted as an integer")
     if not depths:
-        return []
+        return (torch.empty(0), [], []) if return_packed else []
     dev, dt = depths[0].device, depths[0].dtype
     shapes = [tuple(d.shape) for d in depths]
     if any(len(s_) != 2 for s_ in shapes) or any(d.device != dev or d.dtype != dt for d in depths):
@@ -83,4 +84,6 @@ def sparse_bilateral_filtering_batch(depths, filter_size, depth_threshold=0.04, 
             cur = ops.bilateral_iter_batch(cur, packed0, shapes, offsets, int(filter_size[i]), float(depth_threshold))
     if num_iter == 0:
         cur = packed0.clone()
+    if return_packed:
+        return cur, shapes, offsets
     return [cur[o:o + n].view(h, w) for (h, w), o, n in zip(shapes, offsets, sizes)]

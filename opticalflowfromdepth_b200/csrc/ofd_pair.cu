@@ -233,13 +233,39 @@ struct PairPlan {
     }
 };
 
-template <typename DT, int NITER, bool GROUPED>
+// Ragged batches (BASELINE config 2: mixed-resolution frames): image i is H x W, its planes start at pixel offset `off` of the
+// packed buffers (a C-channel tensor stores it densely at element C * off), it is cut into units of G rows and its first unit has
+// the batch-wide index unit0.  The table travels in the kernel's parameter space: every thread of a CTA reads the same entry.
+constexpr int kPairRaggedMax = 96;  // images per launch
+struct PairRaggedImg {
+    int H, W, G, unit0;
+    unsigned long long off;
+};
+struct PairRaggedTable {
+    int n, total_units;
+    PairRaggedImg img[kPairRaggedMax + 1];  // img[n].unit0 == total_units (sentinel)
+};
+struct PairNoTable {};
+enum { PAIR_ROW = 0, PAIR_GROUPED = 1, PAIR_RAGGED = 2 };
+template <int MODE>
+struct PairTab {
+    typedef PairNoTable type;
+};
+template <>
+struct PairTab<PAIR_RAGGED> {
+    typedef PairRaggedTable type;
+};
+
+template <typename DT, int NITER, int MODE>
 __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __restrict__ img0, const DT* __restrict__ depth0,
                                                            const float* __restrict__ sBf, float* __restrict__ img1,
                                                            float* __restrict__ depth1, float* __restrict__ back_flow,
                                                            float* __restrict__ flow, float* __restrict__ valid,
                                                            float* __restrict__ collision, uint64_t* __restrict__ counters,
-                                                           int B, int H, int W, int G, int in_stages_rt, int out_stages_rt) {
+                                                           int B, int H, int W, int G, int in_stages_rt, int out_stages_rt,
+                                                           const __grid_constant__ typename PairTab<MODE>::type tab) {
+    constexpr bool GROUPED = MODE != PAIR_ROW;
+    constexpr bool RAGGED = MODE == PAIR_RAGGED;  // H is unused, W = the widest unit of the batch (shared-memory row stride), G = 1
     // A work unit is G consecutive rows of one frame, handled as ONE virtual row of VW = G * W pixels: the rows are contiguous in
     // every plane, so each plane still moves with one bulk copy per unit; sources stay in their row, so the row-local z-buffer
     // only needs the virtual target index r * W + tx.  G > 1 (a) makes narrow rows long enough to amortise the per-unit barrier /
@@ -254,9 +280,30 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t hw = (size_t)H * W;
     // GROUPED = false is the G == 1 specialisation: the index arithmetic below folds back to the one-row form
-    const int VW = GROUPED ? G * W : W;
-    const int upf = GROUPED ? (H + G - 1) / G : H;  // units per frame
-    const int total_rows = B * upf;                 // work units
+    const int VW = (GROUPED && !RAGGED) ? G * W : W;
+    const int upf = RAGGED ? 1 : (GROUPED ? (H + G - 1) / G : H);  // units per frame
+    int total_rows = B * upf;                                     // work units
+    if constexpr (RAGGED) total_rows = tab.total_units;
+    // where a unit lives: frame, first row, pixels, row width, pixel offset and plane size of its frame
+    struct Unit {
+        int b, j, NV, W;
+        size_t off, hw;
+    };
+    auto locate = [&](int row, int& cur) -> Unit {
+        Unit u;
+        if constexpr (RAGGED) {
+            while (row >= tab.img[cur + 1].unit0) ++cur;  // a CTA's units only move forward
+            const PairRaggedImg& t = tab.img[cur];
+            u.b = cur, u.W = t.W, u.j = (row - t.unit0) * t.G;
+            u.NV = ((t.H - u.j) < t.G ? (t.H - u.j) : t.G) * t.W;
+            u.off = (size_t)t.off, u.hw = (size_t)t.H * t.W;
+        } else {
+            u.b = row / upf, u.j = GROUPED ? (row - u.b * upf) * G : row - u.b * upf;
+            u.W = W, u.NV = GROUPED ? ((H - u.j) < G ? (H - u.j) : G) * W : W;
+            u.hw = hw, u.off = (size_t)u.b * hw;
+        }
+        return u;
+    };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stage][0 depth, 1 colour]
     float* base = reinterpret_cast<float*>(smem_raw + 128);
     typedef PairPlan<DT> Plan;
@@ -280,24 +327,41 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     fence_async_smem();
     __syncthreads();
     // the thread's pixels are the same virtual indices in every unit: row-in-unit and column are computed once
+    // (ragged batches: recomputed whenever the CTA moves on to another frame)
     int vr[NITER], vi[NITER];
 #pragma unroll
     for (int k = 0; k < NITER; ++k) {
         const int v = tid + k * nt;
-        vr[k] = GROUPED ? v / W : 0;
-        vi[k] = GROUPED ? v - vr[k] * W : v;
+        vr[k] = (GROUPED && !RAGGED) ? v / W : 0;
+        vi[k] = (GROUPED && !RAGGED) ? v - vr[k] * W : v;
     }
 
+    constexpr int kDPer = 16 / (int)sizeof(DT);  // depth elements per 16 bytes
+    int cur_ld = 0, cur = 0, cur_w = -1;  // table cursors of the loader / of the CTA, frame the vr / vi are valid for
     auto issue_loads = [&](int row, int s) {  // one thread (the loader)
-        const int b = row / upf, j = GROUPED ? (row - b * upf) * G : row - b * upf;
-        const int n = GROUPED ? ((H - j) < G ? (H - j) : G) * W : W;  // pixels of this unit
+        const Unit u = locate(row, cur_ld);
+        const int n = u.NV;  // pixels of this unit
         DT* sraw = reinterpret_cast<DT*>(in_stage(s));
         float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)VW;
-        mbar_expect_tx(&bars[2 * s], (unsigned)(n * sizeof(DT)));
-        bulk_g2s(sraw, depth0 + (size_t)b * hw + (size_t)j * W, (unsigned)(n * sizeof(DT)), &bars[2 * s]);
-        mbar_expect_tx(&bars[2 * s + 1], (unsigned)(3 * n * 4));
-        const float* g = img0 + (size_t)b * 3 * hw + (size_t)j * W;
-        for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * VW, g + c * hw, (unsigned)(n * 4), &bars[2 * s + 1]);
+        // ragged units may start anywhere: the copy covers the 16-byte-aligned superset of the unit (the extra elements belong to
+        // the neighbouring rows of the same plane: plane sizes and offsets are multiples of 4 pixels), pixel i sits at [i + shift]
+        if constexpr (RAGGED) {
+            const size_t e0 = u.off + (size_t)u.j * u.W;
+            const int a = (int)(e0 & 3), ad = (int)(e0 & (kDPer - 1));
+            const unsigned dbytes = (unsigned)(((ad + n + kDPer - 1) & ~(kDPer - 1)) * sizeof(DT));
+            const unsigned cbytes = (unsigned)(((a + n + 3) & ~3) * 4);
+            mbar_expect_tx(&bars[2 * s], dbytes);
+            bulk_g2s(sraw, depth0 + e0 - ad, dbytes, &bars[2 * s]);
+            mbar_expect_tx(&bars[2 * s + 1], 3 * cbytes);
+            const float* g = img0 + 3 * u.off + (size_t)u.j * u.W - a;
+            for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * VW, g + c * u.hw, cbytes, &bars[2 * s + 1]);
+        } else {
+            mbar_expect_tx(&bars[2 * s], (unsigned)(n * sizeof(DT)));
+            bulk_g2s(sraw, depth0 + u.off + (size_t)u.j * u.W, (unsigned)(n * sizeof(DT)), &bars[2 * s]);
+            mbar_expect_tx(&bars[2 * s + 1], (unsigned)(3 * n * 4));
+            const float* g = img0 + 3 * u.off + (size_t)u.j * u.W;
+            for (int c = 0; c < 3; ++c) bulk_g2s(simg + (size_t)c * VW, g + c * u.hw, (unsigned)(n * 4), &bars[2 * s + 1]);
+        }
     };
 
     int row = blockIdx.x;
@@ -312,8 +376,27 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     unsigned ph = 0;
     for (; row < total_rows; row += gridDim.x, s = (s + 1 == kInStages ? 0 : s + 1), so = (so + 1 == kOutStages ? 0 : so + 1),
                              s_fill = (s_fill + 1 == kInStages ? 0 : s_fill + 1), ph ^= (s == 0 ? 1u : 0u)) {
-        const int b = row / upf, j = GROUPED ? (row - b * upf) * G : row - b * upf;
-        const int NV = GROUPED ? ((H - j) < G ? (H - j) : G) * W : W;  // pixels of this unit (the last unit of a frame may be shorter)
+        const Unit u = locate(row, cur);
+        const int b = u.b, j = u.j;
+        const int NV = u.NV;  // pixels of this unit (the last unit of a frame may be shorter)
+        const int Wu = u.W;
+        int a = 0, ad = 0;  // ragged units: shift of the float rows / of the raw depth row in shared memory (see issue_loads)
+        if constexpr (RAGGED) {
+            const size_t e0 = u.off + (size_t)j * Wu;  // first pixel of the unit in its planes
+            a = (int)(e0 & 3), ad = (int)(e0 & (kDPer - 1));
+        }
+        const int as = sizeof(DT) == 4 ? a : 0;  // shift of the float depth row (sdepth32 is unshifted)
+        if constexpr (RAGGED) {
+            if (b != cur_w) {
+                cur_w = b;
+#pragma unroll
+                for (int k = 0; k < NITER; ++k) {
+                    const int v = tid + k * nt;
+                    vr[k] = v / Wu;
+                    vi[k] = v - vr[k] * Wu;
+                }
+            }
+        }
         const DT* sraw = reinterpret_cast<const DT*>(in_stage(s));
         const float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)VW;
         const float* sdep = sizeof(DT) == 4 ? reinterpret_cast<const float*>(sraw) : sdepth32;
@@ -355,15 +438,15 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
             tx[k] = T_DROPPED;
             hi[k] = 0;
             if (i < NV) {
-                const DT d = sraw[i];
+                const DT d = sraw[i + ad];
                 const DT fx = (sc / d) * (DT)-1.0;
                 DT px = (DT)(float)vi[k] + fx;
                 if (px == px) {
                     px = px < (DT)0 ? (DT)0 : px;
-                    px = px > (DT)(W - 1) ? (DT)(W - 1) : px;
-                    tx[k] = GROUPED ? (uint32_t)(vr[k] * W + (int)px) : (uint32_t)(int)px;
+                    px = px > (DT)(Wu - 1) ? (DT)(Wu - 1) : px;
+                    tx[k] = GROUPED ? (uint32_t)(vr[k] * Wu + (int)px) : (uint32_t)(int)px;
                 }
-                o_flx[i] = (float)fx;
+                o_flx[i + a] = (float)fx;
                 if (sizeof(DT) == 8) sdepth32[i] = (float)d;
                 hi[k] = depth_hi((float)d);
                 if (tx[k] != T_DROPPED)
@@ -391,19 +474,19 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                 const float v = hit ? 1.0f : 0.0f;
                 float r = 0.f, g = 0.f, bl = 0.f, dd = 0.f, bx = 0.f;
                 if (win) {
-                    r = simg[src];
-                    g = simg[VW + src];
-                    bl = simg[2 * VW + src];
-                    dd = sdep[src];
-                    bx = o_flx[src] * -1.0f;
+                    r = simg[src + a];
+                    g = simg[VW + src + a];
+                    bl = simg[2 * VW + src + a];
+                    dd = sdep[src + as];
+                    bx = o_flx[src + a] * -1.0f;
                 }
-                o_img[t] = r * v;
-                o_img[VW + t] = g * v;
-                o_img[2 * VW + t] = bl * v;
-                o_dep[t] = fix_depth(dd * v);
-                o_bfx[t] = bx * v;
-                o_val[t] = v;
-                o_col[t] = (hit && !win) ? 1.0f : 0.0f;
+                o_img[t + a] = r * v;
+                o_img[VW + t + a] = g * v;
+                o_img[2 * VW + t + a] = bl * v;
+                o_dep[t + a] = fix_depth(dd * v);
+                o_bfx[t + a] = bx * v;
+                o_val[t + a] = v;
+                o_col[t + a] = (hit && !win) ? 1.0f : 0.0f;
                 n_px++;
                 n_hit += hit;
                 n_col += (hit && !win);
@@ -416,23 +499,71 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         }
         fence_async_smem();  // generic-proxy writes of the staging rows -> visible to the TMA engine
         __syncthreads();
-        if (tid == 0) {
-            const size_t r1 = (size_t)b * hw + (size_t)j * W;
-            const unsigned rb = (unsigned)(NV * 4);
-            float* gi = img1 + (size_t)b * 3 * hw + (size_t)j * W;
-            for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * hw, o_img + (size_t)c * VW, rb);
-            bulk_s2g(depth1 + r1, o_dep, rb);
-            float* gb = back_flow + (size_t)b * 2 * hw + (size_t)j * W;
-            bulk_s2g(gb, o_bfx, rb);
-            bulk_s2g(gb + hw, zero_row, rb);
-            if (flow) {
-                float* gf = flow + (size_t)b * 2 * hw + (size_t)j * W;
-                bulk_s2g(gf, o_flx, rb);
-                bulk_s2g(gf + hw, negzero_row, rb);
+        if constexpr (!RAGGED) {
+            if (tid == 0) {
+                const size_t r1 = u.off + (size_t)j * Wu;
+                const unsigned rb = (unsigned)(NV * 4);
+                float* gi = img1 + 3 * u.off + (size_t)j * Wu;
+                for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * u.hw, o_img + (size_t)c * VW, rb);
+                bulk_s2g(depth1 + r1, o_dep, rb);
+                float* gb = back_flow + 2 * u.off + (size_t)j * Wu;
+                bulk_s2g(gb, o_bfx, rb);
+                bulk_s2g(gb + u.hw, zero_row, rb);
+                if (flow) {
+                    float* gf = flow + 2 * u.off + (size_t)j * Wu;
+                    bulk_s2g(gf, o_flx, rb);
+                    bulk_s2g(gf + u.hw, negzero_row, rb);
+                }
+                bulk_s2g(valid + r1, o_val, rb);
+                if (collision) bulk_s2g(collision + r1, o_col, rb);
+                bulk_commit();
             }
-            bulk_s2g(valid + r1, o_val, rb);
-            if (collision) bulk_s2g(collision + r1, o_col, rb);
-            bulk_commit();
+        }
+        if constexpr (RAGGED) {
+            // bulk stores cover the 16-byte-aligned interior of the unit: `head` pixels before it and `tail` pixels after it (at
+            // most 3 each) are written by ordinary stores of the first threads
+            const int head = ((4 - a) & 3) < NV ? ((4 - a) & 3) : NV;
+            const int mid = (NV - head) & ~3;
+            const int tail = NV - head - mid;
+            if (tid == 0) {
+                if (mid > 0) {
+                    const size_t r1 = u.off + (size_t)j * Wu + head;
+                    const int sh = a + head;  // aligned: a + head is 0 or 4
+                    const unsigned rb = (unsigned)(mid * 4);
+                    float* gi = img1 + 3 * u.off + (size_t)j * Wu + head;
+                    for (int c = 0; c < 3; ++c) bulk_s2g(gi + c * u.hw, o_img + (size_t)c * VW + sh, rb);
+                    bulk_s2g(depth1 + r1, o_dep + sh, rb);
+                    float* gb = back_flow + 2 * u.off + (size_t)j * Wu + head;
+                    bulk_s2g(gb, o_bfx + sh, rb);
+                    bulk_s2g(gb + u.hw, zero_row, rb);
+                    if (flow) {
+                        float* gf = flow + 2 * u.off + (size_t)j * Wu + head;
+                        bulk_s2g(gf, o_flx + sh, rb);
+                        bulk_s2g(gf + u.hw, negzero_row, rb);
+                    }
+                    bulk_s2g(valid + r1, o_val + sh, rb);
+                    if (collision) bulk_s2g(collision + r1, o_col + sh, rb);
+                }
+                bulk_commit();  // a unit without an aligned interior still commits its (empty) group: the ring counts groups
+            }
+            if ((head | tail) != 0 && tid < 60) {
+                const int pl = tid / 6, sl = tid - pl * 6;  // plane 0-9, slot: 0-2 head, 3-5 tail
+                const int t = sl < 3 ? (sl < head ? sl : -1) : (sl - 3 < tail ? head + mid + sl - 3 : -1);
+                if (t >= 0) {
+                    const size_t px = (size_t)j * Wu + t;
+                    float* dst;
+                    float val;
+                    if (pl < 3) dst = img1 + 3 * u.off + pl * u.hw + px, val = o_img[(size_t)pl * VW + t + a];
+                    else if (pl == 3) dst = depth1 + u.off + px, val = o_dep[t + a];
+                    else if (pl == 4) dst = back_flow + 2 * u.off + px, val = o_bfx[t + a];
+                    else if (pl == 5) dst = back_flow + 2 * u.off + u.hw + px, val = 0.0f;
+                    else if (pl == 6) dst = flow ? flow + 2 * u.off + px : nullptr, val = o_flx[t + a];
+                    else if (pl == 7) dst = flow ? flow + 2 * u.off + u.hw + px : nullptr, val = -0.0f;
+                    else if (pl == 8) dst = valid + u.off + px, val = o_val[t + a];
+                    else dst = collision ? collision + u.off + px : nullptr, val = o_col[t + a];
+                    if (dst) *dst = val;
+                }
+            }
         }
     }
     if (tid == 0) bulk_wait_all();
@@ -492,12 +623,12 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
     while ((VW + niter - 1) / niter > 1024) niter *= 2;
     if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
     int threads = ((VW + niter - 1) / niter + 31) / 32 * 32;
-    auto kern = G == 1 ? (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, false>
-                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, false>
-                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, false>))
-                       : (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, true>
-                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, true>
-                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, true>));
+    auto kern = G == 1 ? (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_ROW>
+                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_ROW>
+                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_ROW>))
+                       : (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_GROUPED>
+                                                  : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_GROUPED>
+                                                                                 : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_GROUPED>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     int dev = 0, sms = 0, per_sm = 0;
@@ -512,7 +643,75 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
         fprintf(stderr, "[ofd] %s: persistent pair kernel: G=%d rows/unit in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM x %d SMs -> grid %lld\n",
                 fn, G, in_stages, out_stages, niter, threads, smem, per_sm, sms, grid);
     kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, B, H, W, G,
-                                                in_stages, out_stages);
+                                                in_stages, out_stages, PairNoTable{});
+    *handled = true;
+    return check_launch(fn);
+}
+
+// One launch for a ragged batch (up to kPairRaggedMax frames): every frame is cut into units of G_i rows with G_i * W_i <= the
+// batch's unit width, and the persistent CTAs walk the concatenated unit list.  *handled stays false when a frame does not fit
+// the TMA alignment rules (the caller then launches frame by frame).
+template <typename DT>
+static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth0, const float* sBf, int n, const int* Hs,
+                              const int* Ws, const size_t* offs, float* img1, float* depth1, float* back_flow, float* flow,
+                              float* valid, float* collision, uint64_t* counters, cudaStream_t st, bool* handled) {
+    *handled = false;
+    PairRaggedTable tab;
+    // units may start at any pixel (shifted shared-memory rows, scalar head / tail stores), so rows need no alignment groups;
+    // the planes themselves must start on 16-byte boundaries: every H*W and offset a multiple of 4 pixels
+    for (int i = 0; i < n; ++i)
+        if (((size_t)Hs[i] * Ws[i]) % 4 != 0 || offs[i] % 4 != 0) return OFD_OK;
+    const int vwmax = 2048;  // pixels per unit (1024 threads x 2); wider rows travel alone
+    long long units = 0;
+    int used = 0;  // widest unit actually formed
+    for (int i = 0; i < n; ++i) {
+        const int W = Ws[i], H = Hs[i];
+        int G = vwmax / W;
+        if (G < 1) G = 1;
+        if (G > H) G = H;
+        tab.img[i].H = H, tab.img[i].W = W, tab.img[i].G = G, tab.img[i].unit0 = (int)units;
+        tab.img[i].off = (unsigned long long)offs[i];
+        units += (H + G - 1) / G;
+        if (G * W > used) used = G * W;
+        if (units > 0x7FFFFFFFll) return OFD_OK;
+    }
+    tab.n = n, tab.total_units = (int)units;
+    tab.img[n].H = tab.img[n].W = tab.img[n].G = 1, tab.img[n].unit0 = (int)units, tab.img[n].off = 0;
+    const int VW = ((used + 3) & ~3) + 8;  // shared-memory row stride: room for the alignment shift and the rounded-up copy size
+    static const int plans[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}, {2, 1}};
+    int in_stages = 0, out_stages = 0;
+    size_t smem = 0;
+    for (int pass = 0; pass < 2 && !in_stages; ++pass)
+        for (const auto& pl : plans) {
+            const size_t need = PairPlan<DT>::bytes(VW, pl[0], pl[1]);
+            if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
+                in_stages = pl[0], out_stages = pl[1], smem = need;
+                break;
+            }
+        }
+    if (!in_stages) return OFD_OK;
+    int niter = OFD_PAIR_NITER;
+    while ((used + niter - 1) / niter > 1024) niter *= 2;
+    if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
+    int threads = ((used + niter - 1) / niter + 31) / 32 * 32;
+    if (threads < 64) threads = 64;  // 60 threads write the unaligned head / tail pixels
+    auto kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_RAGGED>
+                                        : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_RAGGED>
+                                                                       : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_RAGGED>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
+    long long grid = (long long)sms * per_sm;
+    if (grid > units) grid = units;
+    if (std::getenv("OFD_DEBUG"))
+        fprintf(stderr, "[ofd] %s: ragged persistent pair kernel: %d frames, %lld units of <= %d px, in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM -> grid %lld\n",
+                fn, n, units, VW, in_stages, out_stages, niter, threads, smem, per_sm, grid);
+    kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, n, 0, VW, 1,
+                                                in_stages, out_stages, tab);
     *handled = true;
     return check_launch(fn);
 }
@@ -573,6 +772,33 @@ __global__ void __launch_bounds__(256) disparity_flow_kernel(const DT* __restric
 
 using namespace ofd;
 
+template <typename DT>
+static int pair_ragged(const char* fn, const float* img0, const DT* depth0, const float* sBf, int n_images, const int* Hs,
+                       const int* Ws, const size_t* offs, float* img1, float* depth1, float* back_flow, float* flow, float* valid,
+                       float* collision, uint64_t* counters, cudaStream_t st) {
+    const bool aligned = (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 | (uintptr_t)back_flow |
+                           (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
+    for (int i0 = 0; i0 < n_images; i0 += kPairRaggedMax) {
+        const int n = (n_images - i0) < kPairRaggedMax ? (n_images - i0) : kPairRaggedMax;
+        bool handled = false;
+        if (aligned) {
+            // sBf is indexed by the frame's position in the launch: pass the chunk's slice, offsets stay batch-wide
+            int rc = launch_pair_ragged<DT>(fn, img0, depth0, sBf + i0, n, Hs + i0, Ws + i0, offs + i0, img1, depth1, back_flow, flow,
+                                            valid, collision, counters, st, &handled);
+            if (rc) return rc;
+        }
+        if (handled) continue;
+        for (int i = i0; i < i0 + n; ++i) {  // frames outside the TMA alignment rules: one launch per frame
+            const size_t o = offs[i];
+            int rc = launch_pair<DT>(fn, img0 + 3 * o, depth0 + o, sBf + i, 1, Hs[i], Ws[i], img1 + 3 * o, depth1 + o,
+                                     back_flow + 2 * o, flow ? flow + 2 * o : nullptr, valid + o, collision ? collision + o : nullptr,
+                                     counters, st);
+            if (rc) return rc;
+        }
+    }
+    return OFD_OK;
+}
+
 extern "C" {
 
 int ofd_disparity_pair(const float* img0, const void* depth0, int depth_dtype, const float* sBf, int B, int H, int W,
@@ -591,6 +817,29 @@ int ofd_disparity_pair(const float* img0, const void* depth0, int depth_dtype, c
                                   collision, counters, st);
     return launch_pair<double>(fn, img0, (const double*)depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid,
                                collision, counters, st);
+}
+
+int ofd_disparity_pair_ragged(const float* img0, const void* depth0, int depth_dtype, const float* sBf, int n_images,
+                              const int* H_host, const int* W_host, const size_t* offset_host, float* img1, float* depth1,
+                              float* back_flow, float* flow, float* valid, float* collision, uint64_t* counters,
+                              ofd_stream_t stream) {
+    const char* fn = "ofd_disparity_pair_ragged";
+    if (depth_dtype != OFD_F32 && depth_dtype != OFD_F64) return fail(OFD_E_DTYPE, "%s: bad depth dtype %d", fn, depth_dtype);
+    if (n_images < 0) return fail(OFD_E_SHAPE, "%s: negative n_images", fn);
+    if (n_images == 0) return OFD_OK;
+    if (!H_host || !W_host || !offset_host) return fail(OFD_E_NULL, "%s: NULL shape table", fn);
+    if (!img0 || !depth0 || !sBf || !img1 || !depth1 || !back_flow || !valid)
+        return fail(OFD_E_NULL, "%s: NULL tensor pointer", fn);
+    for (int i = 0; i < n_images; ++i) {
+        if (H_host[i] <= 0 || W_host[i] <= 0) return fail(OFD_E_SHAPE, "%s: image %d has a non-positive dimension", fn, i);
+        if ((size_t)H_host[i] * (size_t)W_host[i] >= ((size_t)1 << 31)) return fail(OFD_E_SHAPE, "%s: image %d: H*W must be < 2^31", fn, i);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (depth_dtype == OFD_F32)
+        return pair_ragged<float>(fn, img0, (const float*)depth0, sBf, n_images, H_host, W_host, offset_host, img1, depth1,
+                                  back_flow, flow, valid, collision, counters, st);
+    return pair_ragged<double>(fn, img0, (const double*)depth0, sBf, n_images, H_host, W_host, offset_host, img1, depth1,
+                               back_flow, flow, valid, collision, counters, st);
 }
 
 int ofd_disparity_flow(const void* depth, int depth_dtype, const float* sBf, int B, int H, int W, void* flow,

@@ -161,6 +161,43 @@ def disparity_pair(img0, depth0, sBf, want_flow=True, want_collision=True, count
     return img1, depth1, back, flow, valid, coll
 
 
+def disparity_pair_ragged(img0, depth0, sBf, shapes, offsets, want_flow=True, want_collision=True, counters=None, out=None):
+    """disparity_pair over a ragged batch in one launch (ofd_disparity_pair_ragged): img0 / depth0 are 1-D packed CUDA buffers,
+    image i is shapes[i] = (H_i, W_i) and starts at PIXEL offset offsets[i] - a C-channel tensor holds it densely as
+    [C,H_i,W_i] at element C * offsets[i] (img0: 3 * total pixels, depth0: total pixels, float32 or float64); sBf[n] float32.
+
+    Returns packed (img1[3P], depth1[P], back_flow[2P], flow[2P]|None, valid[P], collision[P]|None), P = depth0.numel();
+    `ragged_views(packed, C, shapes, offsets)` turns one of them into per-image [C,H_i,W_i] views."""
+    _check("depth0", depth0, dtype=(torch.float32, torch.float64))
+    P = depth0.numel()
+    _check("img0", img0, dtype=torch.float32, shape=(3 * P,))
+    n = len(shapes)
+    _check("sBf", sBf, dtype=torch.float32, shape=(n,))
+    if len(offsets) != n or any(off < 0 or off + h * w > P for (h, w), off in zip(shapes, offsets)):
+        raise ValueError("an image extends past the end of the packed buffer")
+    dev = depth0.device
+    if out is None:
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = (torch.empty(3 * P, **f32), torch.empty(P, **f32), torch.empty(2 * P, **f32),
+               torch.empty(2 * P, **f32) if want_flow else None, torch.empty(P, **f32), torch.empty(P, **f32) if want_collision else None)
+    else:
+        for nm, t, c in zip(("img1", "depth1", "back_flow", "flow", "valid", "collision"), out, (3, 1, 2, 2, 1, 1)):
+            if t is not None:
+                _check(nm, t, dtype=torch.float32, shape=(c * P,))
+    img1, depth1, back, flow, valid, coll = out
+    Hs = (C.c_int * n)(*[int(h) for h, _ in shapes])
+    Ws = (C.c_int * n)(*[int(w) for _, w in shapes])
+    offs = (C.c_size_t * n)(*[int(o) for o in offsets])
+    _lib.call("ofd_disparity_pair_ragged", _ptr(img0), _ptr(depth0), _DT[depth0.dtype], _ptr(sBf), n, Hs, Ws, offs, _ptr(img1),
+              _ptr(depth1), _ptr(back), _ptr(flow), _ptr(valid), _ptr(coll), _ptr(counters), _stream(dev))
+    return img1, depth1, back, flow, valid, coll
+
+
+def ragged_views(packed, channels: int, shapes, offsets):
+    """Per-image [C,H_i,W_i] views into a packed ragged buffer (layout of disparity_pair_ragged)."""
+    return [packed[channels * o:channels * (o + h * w)].view(channels, h, w) for (h, w), o in zip(shapes, offsets)]
+
+
 def reproject_flow(depth, cam, eps=1e-7):
     """Convert.depth_to_random_flow (preprocess.py:265-298) fused: depth[B,1,H,W] f32|f64, cam[B,21] f32 -> flow[B,2,H,W]."""
     _check("depth", depth, dtype=(torch.float32, torch.float64))

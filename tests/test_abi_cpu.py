@@ -46,6 +46,9 @@ def test_version_and_workspace_bytes():
     ("ofd_disparity_pair", (1, 1, 0, 1, 1, 65536, 32768, 1, 1, 1, 1, 1, 1, None, None), -2),                   # H*W = 2^31
     ("ofd_augment_pairs", (1, 1, 1, 1, 1, 1, None, None, 2, 8, 8) + (1,) * 15 + (None, 8, 1 << 20, None), -1), # NULL kinds
     ("ofd_bilateral_iter_batch", (1, 1, 0, 1, None, None, None, 5, 0.04, 1, None), -1),                        # NULL tables
+    ("ofd_disparity_pair_ragged", (1, 1, 0, 1, 2, None, None, None, 1, 1, 1, 1, 1, 1, None, None), -1),        # NULL shape tables
+    ("ofd_disparity_pair_ragged", (1, 1, 0, 1, -1, None, None, None, 1, 1, 1, 1, 1, 1, None, None), -2),       # negative n_images
+    ("ofd_disparity_pair_ragged", (1, 1, 7, 1, 1, None, None, None, 1, 1, 1, 1, 1, 1, None, None), -3),        # bad depth dtype
     ("ofd_bilateral_iter_masked", (1, 1, 1, 0, 0, 8, 8, 9, 0.04, 1, None), -4),                                # window 9 with a mask
     ("ofd_bilateral_iter_masked", (1, 1, None, 0, 0, 8, 8, 5, 0.04, 1, None), -1),                             # NULL mask
     ("ofd_depth_from_png", (1, 12, 0, 16, 1, 1, None), -3),                                                    # 12-bit source

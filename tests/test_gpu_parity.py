@@ -284,6 +284,53 @@ def test_disparity_pair_float64_depth(pkg):
     assert f.dtype == torch.float64 and eq(f[0], flow64)
 
 
+def _ragged_pair_case(pkg, sizes, seed, dtype=np.float32):
+    rng = np.random.default_rng(seed)
+    imgs = [rng.integers(0, 256, (3, h, w)).astype(np.float32) for h, w in sizes]
+    deps = [rng.integers(1, 60, (1, h, w)).astype(dtype) if dtype == np.float32 else rng.uniform(1, 99, (1, h, w)) for h, w in sizes]
+    sBf = torch.from_numpy(rng.uniform(40, 55, len(sizes)).astype(np.float32)).to(DEV)
+    offs = [0]
+    for h, w in sizes[:-1]:
+        offs.append(offs[-1] + h * w)
+    img_p = torch.cat([cu(i).reshape(-1) for i in imgs])
+    dep_p = torch.cat([cu(d).reshape(-1) for d in deps])
+    cnt_r = torch.zeros(8, dtype=torch.int64, device=DEV)
+    cnt_f = torch.zeros(8, dtype=torch.int64, device=DEV)
+    got = pkg.ops.disparity_pair_ragged(img_p, dep_p, sBf, sizes, offs, counters=cnt_r)
+    views = [pkg.ops.ragged_views(t, c, sizes, offs) for t, c in zip(got, (3, 1, 2, 2, 1, 1))]
+    for i, (h, w) in enumerate(sizes):
+        want = pkg.ops.disparity_pair(cu(imgs[i])[None], cu(deps[i])[None], sBf[i:i + 1], counters=cnt_f)
+        for k in range(6):
+            assert torch.equal(views[k][i], want[k][0]), (i, (h, w), k)
+    assert torch.equal(cnt_r, cnt_f)
+    return imgs, deps, sBf, views
+
+
+def test_disparity_pair_ragged_equals_per_frame_and_oracle(pkg, capfd, monkeypatch):
+    """ofd_disparity_pair_ragged (BASELINE config 2: mixed resolutions, one persistent launch) == the single-frame call on
+    every frame, bit for bit, counters included; small frames also against the oracle.  Units that start on every 16-byte phase
+    (W % 4 == 0 / 2 / odd with one or an odd number of rows per unit: shifted shared-memory rows, scalar head / tail stores),
+    frames smaller than a unit, rows wider than 2048 pixels (4 pixels per thread), float64 depth, more frames than one launch's table."""
+    monkeypatch.setenv("OFD_DEBUG", "1")
+    sizes = [(48, 64), (30, 50), (36, 33), (2, 8), (4, 2500), (64, 512), (12, 1022), (10, 1026), (8, 1025), (12, 682), (40, 100), (4, 7)]
+    imgs, deps, sBf, views = _ragged_pair_case(pkg, sizes, 31)
+    assert "ragged persistent pair kernel: 12 frames" in capfd.readouterr().err  # the one-launch path really ran
+    for i in (0, 1, 2, 3, 11):
+        want = oracle.disparity_pair(imgs[i][None], deps[i][None], sBf[i:i + 1].cpu().numpy())
+        for k in range(6):
+            assert eq(views[k][i], want[k][0])
+    # float64 depth (dataset path): the raw depth row has its own 16-byte phase
+    _ragged_pair_case(pkg, [(20, 36), (16, 130), (32, 42), (8, 1025), (10, 1026), (6, 1366)], 32, dtype=np.float64)
+    assert "ragged persistent pair kernel: 6 frames" in capfd.readouterr().err
+    # more frames than one launch's table holds (96)
+    _ragged_pair_case(pkg, [(4 + 2 * (i % 3), 8 + 4 * (i % 5)) for i in range(200)], 33)
+    assert "ragged persistent pair kernel: 8 frames" in capfd.readouterr().err  # 96 + 96 + 8
+    # frames outside the rules (H*W % 4 != 0, or a row too wide for shared memory) send the batch down the frame-by-frame path
+    _ragged_pair_case(pkg, [(7, 10), (12, 16), (5, 9)], 34)
+    _ragged_pair_case(pkg, [(8, 4200), (16, 32)], 35)
+    assert "ragged persistent" not in capfd.readouterr().err
+
+
 def test_pair_equals_general_splat_path(pkg):
     """Row-local shared-memory z-buffer == packed-key global z-buffer on the same inputs (480x640)."""
     img, depth = _cfg1_inputs(pkg, 4)
@@ -326,6 +373,30 @@ def test_pair_pipeline_host_front_end(pkg):
     pipe.close()
     for o, wnt in zip(outs2, (want[0], want[1], want[2], want[4])):
         assert np.array_equal(o.numpy(), wnt)
+
+
+def test_pair_pipeline_mask_bytes_edge_cases(pkg):
+    """The float32 host pipeline sends valid / collision as packed bytes and expands them on the host: growing batches on one
+    pipeline (staging buffer and events regrow), host planes that are only 4-byte aligned (scalar head / tail of the
+    non-temporal expansion), and H*W not a multiple of 4 (float-plane fallback) all land the oracle's planes bit for bit."""
+    rng = np.random.default_rng(14)
+    for h, w, Bs in ((40, 52, (2, 9, 5)), (15, 21, (4,))):
+        pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=2)
+        for B in Bs:
+            img = torch.from_numpy(rng.integers(0, 256, (B, 3, h, w)).astype(np.float32)).pin_memory()
+            depth = torch.from_numpy(rng.integers(1, 40, (B, 1, h, w)).astype(np.float32)).pin_memory()
+            depth[:, 0, 3, 5:9] = 1000.0  # sources that hit but cannot win: the collision plane is not empty
+            sBf = torch.from_numpy(rng.uniform(40, 55, B).astype(np.float32))
+            outs = []
+            for c, off in zip((3, 1, 2, 2, 1, 1), (0, 1, 2, 3, 1, 3)):  # odd element offsets into page-locked slabs
+                slab = torch.full((B * c * h * w + 8,), 7.0).pin_memory()
+                outs.append(slab[off:off + B * c * h * w].view(B, c, h, w))
+            pipe.run(img, depth, sBf, *outs)
+            want = oracle.disparity_pair(img.numpy(), depth.numpy(), sBf.numpy())
+            for o, wnt in zip(outs, want):
+                assert np.array_equal(o.numpy(), wnt)
+            assert not want[4].all() and want[4].any()  # both mask values occur
+        pipe.close()
 
 
 def test_pair_pipeline_compact_u8_transport(pkg):
