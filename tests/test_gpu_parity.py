@@ -331,6 +331,38 @@ def test_disparity_pair_ragged_equals_per_frame_and_oracle(pkg, capfd, monkeypat
     assert "ragged persistent" not in capfd.readouterr().err
 
 
+def test_disparity_pair_ragged_writes_only_its_frames(pkg):
+    """Guard bands between the frames of a ragged batch (offsets need not be contiguous) stay untouched in every result plane:
+    the aligned-superset loads never turn into stores, head / tail pixels are written exactly."""
+    rng = np.random.default_rng(41)
+    sizes = [(8, 1025), (6, 10), (10, 1026), (12, 682), (4, 7), (2, 2), (16, 36)]
+    gap = 8
+    offs, P = [], gap
+    for h, w in sizes:
+        offs.append(P)
+        P += h * w + gap
+    img_p = torch.zeros(3 * P, device=DEV)
+    dep_p = torch.ones(P, device=DEV)
+    imgs, deps = [], []
+    for (h, w), o in zip(sizes, offs):
+        im, dp = rng.integers(0, 256, (3, h, w)).astype(np.float32), rng.integers(1, 60, (1, h, w)).astype(np.float32)
+        imgs.append(im), deps.append(dp)
+        img_p[3 * o:3 * (o + h * w)] = cu(im).reshape(-1)
+        dep_p[o:o + h * w] = cu(dp).reshape(-1)
+    sBf = torch.from_numpy(rng.uniform(40, 55, len(sizes)).astype(np.float32)).to(DEV)
+    out = tuple(torch.full((c * P,), 777.0, device=DEV) for c in (3, 1, 2, 2, 1, 1))
+    got = pkg.ops.disparity_pair_ragged(img_p, dep_p, sBf, sizes, offs, out=out)
+    for t, c in zip(got, (3, 1, 2, 2, 1, 1)):
+        inside = torch.zeros(c * P, dtype=torch.bool, device=DEV)
+        for (h, w), o in zip(sizes, offs):
+            inside[c * o:c * (o + h * w)] = True
+        assert bool((t[~inside] == 777.0).all()), c
+    for i in range(len(sizes)):
+        want = oracle.disparity_pair(imgs[i][None], deps[i][None], sBf[i:i + 1].cpu().numpy())
+        for k, c in enumerate((3, 1, 2, 2, 1, 1)):
+            assert eq(pkg.ops.ragged_views(got[k], c, sizes, offs)[i], want[k][0]), (i, k)
+
+
 def test_pair_equals_general_splat_path(pkg):
     """Row-local shared-memory z-buffer == packed-key global z-buffer on the same inputs (480x640)."""
     img, depth = _cfg1_inputs(pkg, 4)

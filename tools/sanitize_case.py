@@ -42,5 +42,23 @@ for (B, H, W) in ((2, 24, 40), (3, 17, 33)):
     pj = geometry.Project3D(B, H, W)
     pj(bp(depth, invK.repeat(B, 1, 1).to(dev)), K.repeat(B, 1, 1).to(dev), T1.repeat(B, 1, 1).to(dev))
     synthesis.fix_warped_depth(depth.clone())
+# ragged batch through the one-launch pair kernel: units on every 16-byte phase, head / tail scalar stores, float64 depth
+sizes = [(8, 1025), (10, 1026), (12, 682), (4, 7), (16, 32), (2, 2)]
+offs = [0]
+for h, w in sizes[:-1]:
+    offs.append(offs[-1] + h * w)
+P = offs[-1] + sizes[-1][0] * sizes[-1][1]
+rimg = torch.randint(0, 256, (3 * P,), device=dev).float()
+rdep = torch.randint(1, 60, (P,), device=dev).float()
+rs = torch.full((len(sizes),), 47.0, device=dev)
+ops.disparity_pair_ragged(rimg, rdep, rs, sizes, offs, counters=cnt)
+ops.disparity_pair_ragged(rimg, rdep.double(), rs, sizes, offs)
+# host pipeline with byte-packed masks
+pipe = ops.PairPipeline(0, 24, 40, chunk_frames=2)
+himg = torch.randint(0, 256, (5, 3, 24, 40)).float().pin_memory()
+hdep = torch.randint(1, 60, (5, 1, 24, 40)).float().pin_memory()
+houts = [torch.empty((5, c, 24, 40)).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+pipe.run(himg, hdep, torch.full((5,), 47.0), *houts)
+pipe.close()
 torch.cuda.synchronize()
 print("sanitize_case ok", cnt.tolist())

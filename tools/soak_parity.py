@@ -49,6 +49,37 @@ def trial_pair(rng):
     return ok, f"pair {b}x{h}x{w}"
 
 
+def trial_pair_ragged(rng):
+    """Mixed-resolution batch through the one-launch ragged kernel (every H*W a multiple of 4: any W, units on every 16-byte phase),
+    float32 or float64 depth, each frame against the oracle."""
+    n = int(rng.integers(1, 7))
+    sizes = []
+    for _ in range(n):
+        w = int(rng.choice([rng.integers(1, 2400), rng.integers(1, 80), 2 * rng.integers(1, 700)]))
+        q = 4 // np.gcd(w, 4)
+        sizes.append((int(q * rng.integers(1, max(2, 40 // q))), w))
+    f64 = rng.random() < 0.3
+    imgs = [rng.integers(0, 256, (3, h, w)).astype(np.float32) for h, w in sizes]
+    deps = [depth_field(rng, h, w, rng.random() < 0.5)[None] for h, w in sizes]
+    if f64:
+        deps = [d.astype(np.float64) + rng.uniform(0, 1e-3, d.shape) for d in deps]
+    sBf = rng.uniform(40, 55, n).astype(np.float32)
+    offs = [0]
+    for h, w in sizes[:-1]:
+        offs.append(offs[-1] + h * w)
+    got = ops.disparity_pair_ragged(torch.cat([cu(i).reshape(-1) for i in imgs]), torch.cat([cu(d).reshape(-1) for d in deps]),
+                                    cu(sBf), sizes, offs)
+    views = [ops.ragged_views(t, c, sizes, offs) for t, c in zip(got, (3, 1, 2, 2, 1, 1))]
+    ok = True
+    for i in range(n):
+        if f64:  # the oracle's pair is float32: compare with the single-frame float64 kernel path (itself pinned by the tests)
+            want = [t[0].cpu().numpy() for t in ops.disparity_pair(cu(imgs[i])[None], cu(deps[i])[None], cu(sBf[i:i + 1]))]
+        else:
+            want = [t[0] for t in oracle.disparity_pair(imgs[i][None], deps[i][None], sBf[i:i + 1], nthreads=4)]
+        ok = ok and all(eq(views[k][i], want[k]) for k in range(6))
+    return ok, f"pair_ragged {sizes} f64={f64}"
+
+
 def trial_splat(rng):
     h, w, b, c = int(rng.integers(1, 70)), int(rng.integers(1, 200)), int(rng.integers(1, 4)), int(rng.integers(1, 9))
     obj = rng.normal(0, 50, (b, c, h, w)).astype(np.float32)
@@ -166,7 +197,7 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, counts, fails = time.time(), {}, []
-    trials = (trial_pair, trial_splat, trial_bilateral, trial_bilateral_masked, trial_reproject_pair, trial_augment)
+    trials = (trial_pair, trial_pair_ragged, trial_splat, trial_bilateral, trial_bilateral_masked, trial_reproject_pair, trial_augment)
     k = 0
     while time.time() - t0 < budget:
         fn = trials[k % len(trials)]
