@@ -240,7 +240,7 @@ def test_against_the_reference_kernel_itself(pkg):
 # sizes: TMA row groups of 1 / 2 / 4 rows (W % 4 == 0 / 2 / odd), frames that end inside a unit, the one-row fallback (H not a
 # multiple of the alignment group), a unit wider than 1024 threads x 2 pixels, degenerate frames
 @pytest.mark.parametrize("h,w", [(480, 640), (37, 53), (64, 4), (5, 130), (1, 1), (36, 53), (38, 130), (7, 640), (96, 642),
-                                 (8, 333), (12, 2561), (33, 496), (368, 496)])
+                                 (8, 333), (12, 2561), (33, 496), (368, 496), (375, 1242)])  # last: the reference's KITTI stereo shape (utils.py:31)
 def test_disparity_pair_vs_oracle(pkg, h, w):
     rng = np.random.default_rng(h * 1000 + w)
     B = 3
