@@ -267,3 +267,19 @@ def test_bench_reference_arm_prints_the_contract_line():
                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=str(ROOT),
                         env={**__import__("os").environ, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_ragged_views_and_argument_checks_of_the_ragged_pair():
+    """Packed ragged layout of ops.disparity_pair_ragged: a C-channel tensor holds frame i as [C,H_i,W_i] at element C * offset_i;
+    the wrapper refuses CPU tensors and tables that run past the buffer before anything reaches the library."""
+    from opticalflowfromdepth_b200 import ops
+    shapes, offs = [(2, 3), (4, 2), (1, 5)], [0, 8, 16]
+    P = 24
+    packed = torch.arange(3 * P, dtype=torch.float32)
+    views = ops.ragged_views(packed, 3, shapes, offs)
+    assert [tuple(v.shape) for v in views] == [(3, 2, 3), (3, 4, 2), (3, 1, 5)]
+    assert views[1][0, 0, 0] == 3 * 8 and views[1][2, 3, 1] == 3 * 8 + 3 * 8 - 1 and views[2][1, 0, 0] == 3 * 16 + 5
+    views[0][1, 1, 2] = -1.0  # views, not copies
+    assert packed[3 * 0 + 6 + 5] == -1.0
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ops.disparity_pair_ragged(torch.zeros(3 * P), torch.zeros(P), torch.zeros(3), shapes, offs)
