@@ -661,7 +661,11 @@ static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth
     // the planes themselves must start on 16-byte boundaries: every H*W and offset a multiple of 4 pixels
     for (int i = 0; i < n; ++i)
         if (((size_t)Hs[i] * Ws[i]) % 4 != 0 || offs[i] % 4 != 0) return OFD_OK;
-    const int vwmax = 2048;  // pixels per unit (1024 threads x 2); wider rows travel alone
+    int vwmax = 2048;  // pixels per unit (1024 threads x 2); wider rows travel alone
+    if (const char* e = std::getenv("OFD_PAIR_RAGGED_UNIT")) {  // tuning knob
+        const int v = std::atoi(e);
+        if (v >= 64 && v <= 2880) vwmax = v;
+    }
     long long units = 0;
     int used = 0;  // widest unit actually formed
     for (int i = 0; i < n; ++i) {
