@@ -731,9 +731,36 @@ static int launch_pair(const char* fn, const float* img0, const DT* depth0, cons
                            (uintptr_t)back_flow | (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
     if (aligned) {
         bool handled = false;
-        int rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,
+        int rc = OFD_OK;
+        // odd widths would need 4-row alignment groups (units of 4 W pixels: 74 % of the HBM peak at 480x641); the shift-capable
+        // ragged kernel cuts them into ~2000-pixel units that start on any pixel (84 %) - tried first when the planes allow it
+        const bool ragged_first = (W % 2 == 1) && (((size_t)H * W) % 4 == 0) && std::getenv("OFD_PAIR_GROUP") == nullptr;
+        if (!ragged_first) {
+            rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,
                                             counters, st, &handled);
-        if (rc || handled) return rc;
+            if (rc || handled) return rc;
+        }
+        // also: rows too wide for an alignment group (W % 4 != 0 and 2 or 4 rows do not fit in shared memory) travel one row per
+        // unit through the same kernel, as a batch of B equal frames
+        if (((size_t)H * W) % 4 == 0) {
+            const size_t hw4 = (size_t)H * W;
+            for (int b0 = 0; b0 < B; b0 += kPairRaggedMax) {
+                const int n = (B - b0) < kPairRaggedMax ? (B - b0) : kPairRaggedMax;
+                int Hs[kPairRaggedMax], Ws[kPairRaggedMax];
+                size_t offs[kPairRaggedMax];
+                for (int i = 0; i < n; ++i) Hs[i] = H, Ws[i] = W, offs[i] = (size_t)(b0 + i) * hw4;
+                rc = launch_pair_ragged<DT>(fn, img0, depth0, sBf + b0, n, Hs, Ws, offs, img1, depth1, back_flow, flow, valid, collision,
+                                            counters, st, &handled);
+                if (rc) return rc;
+                if (!handled) break;  // (only possible on the first chunk: every chunk has the same shape)
+            }
+            if (handled) return OFD_OK;
+        }
+        if (ragged_first) {
+            rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,
+                                            counters, st, &handled);
+            if (rc || handled) return rc;
+        }
     }
     const size_t smem = PairSmem<DT>::bytes(W);
     if (smem > 227 * 1024) return fail(OFD_E_SHAPE, "%s: W=%d needs %zu B of shared memory per row (max 227 KB)", fn, W, smem);

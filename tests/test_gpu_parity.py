@@ -240,7 +240,8 @@ def test_against_the_reference_kernel_itself(pkg):
 # sizes: TMA row groups of 1 / 2 / 4 rows (W % 4 == 0 / 2 / odd), frames that end inside a unit, the one-row fallback (H not a
 # multiple of the alignment group), a unit wider than 1024 threads x 2 pixels, degenerate frames
 @pytest.mark.parametrize("h,w", [(480, 640), (37, 53), (64, 4), (5, 130), (1, 1), (36, 53), (38, 130), (7, 640), (96, 642),
-                                 (8, 333), (12, 2561), (33, 496), (368, 496), (375, 1242)])  # last: the reference's KITTI stereo shape (utils.py:31)
+                                 (8, 333), (12, 2561), (33, 496), (368, 496), (375, 1242),  # the reference's KITTI stereo shape (utils.py:31)
+                                 (8, 1918), (8, 1001)])  # unaligned rows too wide for a row group: one-row units of the ragged kernel
 def test_disparity_pair_vs_oracle(pkg, h, w):
     rng = np.random.default_rng(h * 1000 + w)
     B = 3
@@ -263,6 +264,21 @@ def test_disparity_pair_vs_oracle(pkg, h, w):
         _, _, _, w_map, _ = oracle.fw_forward(obj, want[3][b], depth[b])
         ties += expected_ties(want[3][b], depth[b], w_map)
     assert cn[4] == ties, "tie census of the fused pair kernel differs from the oracle"
+
+
+@pytest.mark.parametrize("h,w,g", [(36, 53, 4), (8, 333, 4), (8, 333, 8), (12, 130, 2)])
+def test_disparity_pair_forced_row_groups_vs_oracle(pkg, monkeypatch, h, w, g):
+    """Odd widths normally take the shift-capable ragged kernel; OFD_PAIR_GROUP forces the aligned row-group specialisation
+    (4-row groups for odd W, 2-row groups for W % 4 == 2), which must give the same bits."""
+    monkeypatch.setenv("OFD_PAIR_GROUP", str(g))
+    rng = np.random.default_rng(h * 100 + w)
+    img = rng.integers(0, 256, (2, 3, h, w)).astype(np.float32)
+    depth = rng.integers(1, 60, (2, 1, h, w)).astype(np.float32)
+    sBf = rng.uniform(40, 55, 2).astype(np.float32)
+    got = pkg.ops.disparity_pair(cu(img), cu(depth), cu(sBf))
+    want = oracle.disparity_pair(img, depth, sBf, nthreads=2)
+    for gt, wt in zip(got, want):
+        assert eq(gt, wt)
 
 
 def test_disparity_pair_float64_depth(pkg):
