@@ -124,8 +124,9 @@ int ofd_disparity_pair(const float* img0, const void* depth0, int depth_dtype, c
  * synthesised exactly as the single-frame call would): image i is H_host[i] x W_host[i] and starts at PIXEL offset
  * offset_host[i] of the packed buffers - a C-channel tensor stores it densely as [C,H_i,W_i] at element C * offset_host[i]
  * (depth0 / depth1 / valid / collision: C = 1, img0 / img1: 3, back_flow / flow: 2); sBf[n_images] on the device.
- * One persistent launch per 96 frames when every frame has H*W and its offset a multiple of 4 pixels (any W: work units may
- * start on any pixel) and W <= ~2890; otherwise one launch per frame.  H_host / W_host / offset_host are HOST arrays.
+ * One persistent launch per 96 frames for any H, W <= ~2890 and offsets (work units may start on any pixel, every plane on any
+ * 16-byte phase; the buffers themselves must be 16-byte aligned); only the frame that ends the buffers on an odd 16-byte
+ * boundary, and rows wider than that, take one launch per frame.  H_host / W_host / offset_host are HOST arrays.
  */
 int ofd_disparity_pair_ragged(const float* img0, const void* depth0, int depth_dtype, const float* sBf, int n_images,
                               const int* H_host, const int* W_host, const size_t* offset_host, float* img1, float* depth1,

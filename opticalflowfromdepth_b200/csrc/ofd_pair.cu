@@ -246,13 +246,19 @@ struct PairRaggedTable {
     PairRaggedImg img[kPairRaggedMax + 1];  // img[n].unit0 == total_units (sentinel)
 };
 struct PairNoTable {};
-enum { PAIR_ROW = 0, PAIR_GROUPED = 1, PAIR_RAGGED = 2 };
+// PAIR_RAGGED: every frame's H*W and offset are multiples of 4 pixels (all planes of a unit share one 16-byte phase);
+// PAIR_RAGGED_ANY: no such rule, every plane has its own phase (more registers and per-plane store bookkeeping: only when needed)
+enum { PAIR_ROW = 0, PAIR_GROUPED = 1, PAIR_RAGGED = 2, PAIR_RAGGED_ANY = 3 };
 template <int MODE>
 struct PairTab {
     typedef PairNoTable type;
 };
 template <>
 struct PairTab<PAIR_RAGGED> {
+    typedef PairRaggedTable type;
+};
+template <>
+struct PairTab<PAIR_RAGGED_ANY> {
     typedef PairRaggedTable type;
 };
 
@@ -265,7 +271,8 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                                                            int B, int H, int W, int G, int in_stages_rt, int out_stages_rt,
                                                            const __grid_constant__ typename PairTab<MODE>::type tab) {
     constexpr bool GROUPED = MODE != PAIR_ROW;
-    constexpr bool RAGGED = MODE == PAIR_RAGGED;  // H is unused, W = the widest unit of the batch (shared-memory row stride), G = 1
+    constexpr bool RAGGED = MODE >= PAIR_RAGGED;  // H is unused, W = the widest unit of the batch (shared-memory row stride), G = 1
+    constexpr bool ANY = MODE == PAIR_RAGGED_ANY;
     // A work unit is G consecutive rows of one frame, handled as ONE virtual row of VW = G * W pixels: the rows are contiguous in
     // every plane, so each plane still moves with one bulk copy per unit; sources stay in their row, so the row-local z-buffer
     // only needs the virtual target index r * W + tx.  G > 1 (a) makes narrow rows long enough to amortise the per-unit barrier /
@@ -345,7 +352,21 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         float* simg = in_stage(s) + (sizeof(DT) / 4) * (size_t)VW;
         // ragged units may start anywhere: the copy covers the 16-byte-aligned superset of the unit (the extra elements belong to
         // the neighbouring rows of the same plane: plane sizes and offsets are multiples of 4 pixels), pixel i sits at [i + shift]
-        if constexpr (RAGGED) {
+        if constexpr (ANY) {
+            // every plane has its own 16-byte phase (a frame's planes are H*W elements apart, not necessarily a multiple of 4)
+            const size_t q0 = (size_t)u.j * u.W, e1 = u.off + q0, e3 = 3 * u.off + q0;
+            const int ad = (int)(e1 & (kDPer - 1));
+            const unsigned dbytes = (unsigned)(((ad + n + kDPer - 1) & ~(kDPer - 1)) * sizeof(DT));
+            mbar_expect_tx(&bars[2 * s], dbytes);
+            bulk_g2s(sraw, depth0 + e1 - ad, dbytes, &bars[2 * s]);
+            unsigned cb[3], total = 0;
+            for (int c = 0; c < 3; ++c) cb[c] = (unsigned)((((int)((e3 + c * u.hw) & 3) + n + 3) & ~3) * 4), total += cb[c];
+            mbar_expect_tx(&bars[2 * s + 1], total);
+            for (int c = 0; c < 3; ++c) {
+                const size_t e = e3 + c * u.hw;
+                bulk_g2s(simg + (size_t)c * VW, img0 + (e - (e & 3)), cb[c], &bars[2 * s + 1]);
+            }
+        } else if constexpr (RAGGED) {
             const size_t e0 = u.off + (size_t)u.j * u.W;
             const int a = (int)(e0 & 3), ad = (int)(e0 & (kDPer - 1));
             const unsigned dbytes = (unsigned)(((ad + n + kDPer - 1) & ~(kDPer - 1)) * sizeof(DT));
@@ -384,6 +405,13 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
         if constexpr (RAGGED) {
             const size_t e0 = u.off + (size_t)j * Wu;  // first pixel of the unit in its planes
             a = (int)(e0 & 3), ad = (int)(e0 & (kDPer - 1));
+        }
+        // per-plane shifts (PAIR_RAGGED_ANY; otherwise all equal to a): a3x colour plane x, a2x / a2y the x / y planes of the flows
+        int a30 = a, a31 = a, a32 = a, a2x = a, a2y = a;
+        if constexpr (ANY) {
+            const size_t q0 = (size_t)j * Wu;
+            a30 = (int)((3 * u.off + q0) & 3), a31 = (int)((3 * u.off + u.hw + q0) & 3), a32 = (int)((3 * u.off + 2 * u.hw + q0) & 3);
+            a2x = (int)((2 * u.off + q0) & 3), a2y = (int)((2 * u.off + u.hw + q0) & 3);
         }
         const int as = sizeof(DT) == 4 ? a : 0;  // shift of the float depth row (sdepth32 is unshifted)
         if constexpr (RAGGED) {
@@ -446,7 +474,7 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                     px = px > (DT)(Wu - 1) ? (DT)(Wu - 1) : px;
                     tx[k] = GROUPED ? (uint32_t)(vr[k] * Wu + (int)px) : (uint32_t)(int)px;
                 }
-                o_flx[i + a] = (float)fx;
+                o_flx[i + a2x] = (float)fx;
                 if (sizeof(DT) == 8) sdepth32[i] = (float)d;
                 hi[k] = depth_hi((float)d);
                 if (tx[k] != T_DROPPED)
@@ -474,17 +502,17 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                 const float v = hit ? 1.0f : 0.0f;
                 float r = 0.f, g = 0.f, bl = 0.f, dd = 0.f, bx = 0.f;
                 if (win) {
-                    r = simg[src + a];
-                    g = simg[VW + src + a];
-                    bl = simg[2 * VW + src + a];
+                    r = simg[src + a30];
+                    g = simg[VW + src + a31];
+                    bl = simg[2 * VW + src + a32];
                     dd = sdep[src + as];
-                    bx = o_flx[src + a] * -1.0f;
+                    bx = o_flx[src + a2x] * -1.0f;
                 }
-                o_img[t + a] = r * v;
-                o_img[VW + t + a] = g * v;
-                o_img[2 * VW + t + a] = bl * v;
+                o_img[t + a30] = r * v;
+                o_img[VW + t + a31] = g * v;
+                o_img[2 * VW + t + a32] = bl * v;
                 o_dep[t + a] = fix_depth(dd * v);
-                o_bfx[t + a] = bx * v;
+                o_bfx[t + a2x] = bx * v;
                 o_val[t + a] = v;
                 o_col[t + a] = (hit && !win) ? 1.0f : 0.0f;
                 n_px++;
@@ -519,7 +547,49 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
                 bulk_commit();
             }
         }
-        if constexpr (RAGGED) {
+        if constexpr (ANY) {
+            // as below, but every plane has its own shift, hence its own head / interior / tail.
+            // plane p: 0-2 img1, 3 depth1, 4 back_flow.x, 5 back_flow.y, 6 flow.x, 7 flow.y, 8 valid, 9 collision
+            auto plane = [&](int p, float*& dst, const float*& src, int& sh) {
+                const size_t q0 = (size_t)j * Wu;
+                if (p < 3) dst = img1 + 3 * u.off + p * u.hw + q0, src = o_img + (size_t)p * VW, sh = p == 0 ? a30 : (p == 1 ? a31 : a32);
+                else if (p == 3) dst = depth1 + u.off + q0, src = o_dep, sh = a;
+                else if (p == 4) dst = back_flow + 2 * u.off + q0, src = o_bfx, sh = a2x;
+                else if (p == 5) dst = back_flow + 2 * u.off + u.hw + q0, src = nullptr, sh = a2y;
+                else if (p == 6) dst = flow ? flow + 2 * u.off + q0 : nullptr, src = o_flx, sh = a2x;
+                else if (p == 7) dst = flow ? flow + 2 * u.off + u.hw + q0 : nullptr, src = nullptr, sh = a2y;
+                else if (p == 8) dst = valid + u.off + q0, src = o_val, sh = a;
+                else dst = collision ? collision + u.off + q0 : nullptr, src = o_col, sh = a;
+            };
+            if (tid == 0) {
+#pragma unroll
+                for (int p = 0; p < 10; ++p) {
+                    float* dst;
+                    const float* src;
+                    int sh;
+                    plane(p, dst, src, sh);
+                    const int head = ((4 - sh) & 3) < NV ? ((4 - sh) & 3) : NV;
+                    const int mid = (NV - head) & ~3;
+                    if (dst && mid > 0) {
+                        const float* from = src ? src + sh + head : (p == 5 ? zero_row : negzero_row);  // sh + head is 0 or 4
+                        bulk_s2g(dst + head, from, (unsigned)(mid * 4));
+                    }
+                }
+                bulk_commit();  // a unit without an aligned interior still commits its (empty) group: the ring counts groups
+            }
+            if (tid >= 32 && tid < 92) {  // (warp 0 is busy issuing the bulk stores)
+                const int pl = (tid - 32) / 6, sl = (tid - 32) - pl * 6;  // plane 0-9, slot: 0-2 head, 3-5 tail
+                float* dst;
+                const float* src;
+                int sh;
+                plane(pl, dst, src, sh);
+                const int head = ((4 - sh) & 3) < NV ? ((4 - sh) & 3) : NV;
+                const int mid = (NV - head) & ~3;
+                const int tail = NV - head - mid;
+                const int t = sl < 3 ? (sl < head ? sl : -1) : (sl - 3 < tail ? head + mid + sl - 3 : -1);
+                if (t >= 0 && dst) dst[t] = src ? src[t + sh] : (pl == 5 ? 0.0f : -0.0f);
+            }
+        } else if constexpr (RAGGED) {
             // bulk stores cover the 16-byte-aligned interior of the unit: `head` pixels before it and `tail` pixels after it (at
             // most 3 each) are written by ordinary stores of the first threads
             const int head = ((4 - a) & 3) < NV ? ((4 - a) & 3) : NV;
@@ -654,12 +724,13 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
 template <typename DT>
 static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth0, const float* sBf, int n, const int* Hs,
                               const int* Ws, const size_t* offs, float* img1, float* depth1, float* back_flow, float* flow,
-                              float* valid, float* collision, uint64_t* counters, cudaStream_t st, bool* handled) {
+                              float* valid, float* collision, uint64_t* counters, cudaStream_t st, bool* handled, bool any = false) {
     *handled = false;
     PairRaggedTable tab;
-    // units may start at any pixel (shifted shared-memory rows, scalar head / tail stores), so rows need no alignment groups;
-    // the planes themselves must start on 16-byte boundaries: every H*W and offset a multiple of 4 pixels
-    for (int i = 0; i < n; ++i)
+    // units may start at any pixel (shifted shared-memory rows, scalar head / tail stores), so rows need no alignment groups.
+    // any == false: the planes themselves start on 16-byte boundaries - every H*W and offset is a multiple of 4 pixels;
+    // any == true (PAIR_RAGGED_ANY): no such rule, but the caller guarantees that the (at most 3) elements after every frame exist
+    for (int i = 0; i < n && !any; ++i)
         if (((size_t)Hs[i] * Ws[i]) % 4 != 0 || offs[i] % 4 != 0) return OFD_OK;
     int vwmax = 2048;  // pixels per unit (1024 threads x 2); wider rows travel alone
     if (const char* e = std::getenv("OFD_PAIR_RAGGED_UNIT")) {  // tuning knob
@@ -698,10 +769,14 @@ static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth
     while ((used + niter - 1) / niter > 1024) niter *= 2;
     if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
     int threads = ((used + niter - 1) / niter + 31) / 32 * 32;
-    if (threads < 64) threads = 64;  // 60 threads write the unaligned head / tail pixels
+    if (threads < 96) threads = 96;  // up to 60 threads (of the first three warps) write the unaligned head / tail pixels
     auto kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_RAGGED>
                                         : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_RAGGED>
                                                                        : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_RAGGED>);
+    if (any)
+        kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_RAGGED_ANY>
+                                       : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_RAGGED_ANY>
+                                                                      : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_RAGGED_ANY>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     int dev = 0, sms = 0, per_sm = 0;
@@ -712,8 +787,8 @@ static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth
     long long grid = (long long)sms * per_sm;
     if (grid > units) grid = units;
     if (std::getenv("OFD_DEBUG"))
-        fprintf(stderr, "[ofd] %s: ragged persistent pair kernel: %d frames, %lld units of <= %d px, in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM -> grid %lld\n",
-                fn, n, units, VW, in_stages, out_stages, niter, threads, smem, per_sm, grid);
+        fprintf(stderr, "[ofd] %s: ragged persistent pair kernel: %d frames%s, %lld units of <= %d px, in_stages=%d out_stages=%d niter=%d threads=%d smem=%zu B, %d CTAs/SM -> grid %lld\n",
+                fn, n, any ? " (per-plane phases)" : "", units, VW, in_stages, out_stages, niter, threads, smem, per_sm, grid);
     kern<<<(unsigned)grid, threads, smem, st>>>(img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, counters, n, 0, VW, 1,
                                                 in_stages, out_stages, tab);
     *handled = true;
@@ -729,6 +804,7 @@ static int launch_pair(const char* fn, const float* img0, const DT* depth0, cons
     // align_rows in launch_pair_persistent); rows that are not a multiple of 4 pixels travel in groups of 2 or 4 rows
     const bool aligned = (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 |
                            (uintptr_t)back_flow | (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
+    int done = 0;  // frames already synthesised (per-plane ragged kernel); the rest goes to the one-row kernel
     if (aligned) {
         bool handled = false;
         int rc = OFD_OK;
@@ -755,6 +831,24 @@ static int launch_pair(const char* fn, const float* img0, const DT* depth0, cons
                 if (!handled) break;  // (only possible on the first chunk: every chunk has the same shape)
             }
             if (handled) return OFD_OK;
+        } else {
+            // H*W not a multiple of 4 (e.g. 375x1242): the planes of a frame start on different 16-byte phases - the per-plane form
+            // of the ragged kernel.  Its loads read up to 3 elements past a frame, so the last frame is left to the one-row kernel
+            // when the batch does not end on a 16-byte boundary.
+            const size_t hw1 = (size_t)H * W;
+            const int Bp = ((size_t)B * hw1) % 4 == 0 ? B : B - 1;
+            for (int b0 = 0; b0 < Bp; b0 += kPairRaggedMax) {
+                const int n = (Bp - b0) < kPairRaggedMax ? (Bp - b0) : kPairRaggedMax;
+                int Hs[kPairRaggedMax], Ws[kPairRaggedMax];
+                size_t offs[kPairRaggedMax];
+                for (int i = 0; i < n; ++i) Hs[i] = H, Ws[i] = W, offs[i] = (size_t)(b0 + i) * hw1;
+                rc = launch_pair_ragged<DT>(fn, img0, depth0, sBf + b0, n, Hs, Ws, offs, img1, depth1, back_flow, flow, valid, collision,
+                                            counters, st, &handled, true);
+                if (rc) return rc;
+                if (!handled) break;
+                done = b0 + n;
+            }
+            if (done == B) return OFD_OK;
         }
         if (ragged_first) {
             rc = launch_pair_persistent<DT>(fn, img0, depth0, sBf, B, H, W, img1, depth1, back_flow, flow, valid, collision,
@@ -770,7 +864,7 @@ static int launch_pair(const char* fn, const float* img0, const DT* depth0, cons
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     const size_t hw = (size_t)H * W;
-    for (int b0 = 0; b0 < B; b0 += 65535) {
+    for (int b0 = done; b0 < B; b0 += 65535) {
         const int Bc = (B - b0) < 65535 ? (B - b0) : 65535;
         dim3 grid(H, Bc);
         kern<<<grid, threads, smem, st>>>(img0 + (size_t)b0 * 3 * hw, depth0 + (size_t)b0 * hw, sBf + b0,
@@ -809,25 +903,46 @@ static int pair_ragged(const char* fn, const float* img0, const DT* depth0, cons
                        float* collision, uint64_t* counters, cudaStream_t st) {
     const bool aligned = (((uintptr_t)img0 | (uintptr_t)depth0 | (uintptr_t)img1 | (uintptr_t)depth1 | (uintptr_t)back_flow |
                            (uintptr_t)flow | (uintptr_t)valid | (uintptr_t)collision) % 16 == 0);
-    for (int i0 = 0; i0 < n_images; i0 += kPairRaggedMax) {
-        const int n = (n_images - i0) < kPairRaggedMax ? (n_images - i0) : kPairRaggedMax;
-        bool handled = false;
-        if (aligned) {
-            // sBf is indexed by the frame's position in the launch: pass the chunk's slice, offsets stay batch-wide
-            int rc = launch_pair_ragged<DT>(fn, img0, depth0, sBf + i0, n, Hs + i0, Ws + i0, offs + i0, img1, depth1, back_flow, flow,
-                                            valid, collision, counters, st, &handled);
-            if (rc) return rc;
+    auto one_frame = [&](int i) {  // one launch for frame i alone (whatever kernel its shape allows)
+        const size_t o = offs[i];
+        return launch_pair<DT>(fn, img0 + 3 * o, depth0 + o, sBf + i, 1, Hs[i], Ws[i], img1 + 3 * o, depth1 + o, back_flow + 2 * o,
+                               flow ? flow + 2 * o : nullptr, valid + o, collision ? collision + o : nullptr, counters, st);
+    };
+    // frames [lo, hi) in launches of up to kPairRaggedMax; sBf is indexed by the frame's position in the launch, so each launch gets
+    // its slice of sBf while the offsets stay batch-wide
+    auto range = [&](int lo, int hi, bool any) {
+        for (int i0 = lo; i0 < hi; i0 += kPairRaggedMax) {
+            const int n = (hi - i0) < kPairRaggedMax ? (hi - i0) : kPairRaggedMax;
+            bool handled = false;
+            if (aligned) {
+                int rc = launch_pair_ragged<DT>(fn, img0, depth0, sBf + i0, n, Hs + i0, Ws + i0, offs + i0, img1, depth1, back_flow, flow,
+                                                valid, collision, counters, st, &handled, any);
+                if (rc) return rc;
+            }
+            if (handled) continue;
+            for (int i = i0; i < i0 + n; ++i) {  // a row too wide for shared memory, unaligned buffers: one launch per frame
+                int rc = one_frame(i);
+                if (rc) return rc;
+            }
         }
-        if (handled) continue;
-        for (int i = i0; i < i0 + n; ++i) {  // frames outside the TMA alignment rules: one launch per frame
-            const size_t o = offs[i];
-            int rc = launch_pair<DT>(fn, img0 + 3 * o, depth0 + o, sBf + i, 1, Hs[i], Ws[i], img1 + 3 * o, depth1 + o,
-                                     back_flow + 2 * o, flow ? flow + 2 * o : nullptr, valid + o, collision ? collision + o : nullptr,
-                                     counters, st);
-            if (rc) return rc;
-        }
+        return (int)OFD_OK;
+    };
+    bool uniform = true;  // every plane of every frame starts on a 16-byte boundary
+    int last = 0;         // the frame that ends the buffers
+    for (int i = 0; i < n_images; ++i) {
+        const size_t hw = (size_t)Hs[i] * Ws[i];
+        if (hw % 4 != 0 || offs[i] % 4 != 0) uniform = false;
+        if (offs[i] + hw > offs[last] + (size_t)Hs[last] * Ws[last]) last = i;
     }
-    return OFD_OK;
+    if (uniform) return range(0, n_images, false);
+    // per-plane phases: the aligned-superset loads read up to 3 elements past a frame; they exist for every frame but the one that
+    // ends the buffers (whose sizes are not known here) - it travels alone unless it ends on a 16-byte boundary
+    const bool last_alone = (offs[last] + (size_t)Hs[last] * Ws[last]) % 4 != 0;
+    if (!last_alone) return range(0, n_images, true);
+    int rc = range(0, last, true);
+    if (rc == OFD_OK) rc = range(last + 1, n_images, true);
+    if (rc == OFD_OK) rc = one_frame(last);
+    return rc;
 }
 
 extern "C" {

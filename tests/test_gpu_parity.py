@@ -341,18 +341,25 @@ def test_disparity_pair_ragged_equals_per_frame_and_oracle(pkg, capfd, monkeypat
     # more frames than one launch's table holds (96)
     _ragged_pair_case(pkg, [(4 + 2 * (i % 3), 8 + 4 * (i % 5)) for i in range(200)], 33)
     assert "ragged persistent pair kernel: 8 frames" in capfd.readouterr().err  # 96 + 96 + 8
-    # frames outside the rules (H*W % 4 != 0, or a row too wide for shared memory) send the batch down the frame-by-frame path
+    # H*W not a multiple of 4: every plane of a frame has its own 16-byte phase (PAIR_RAGGED_ANY); the frame that ends the buffers on
+    # an odd boundary is left to the single-frame path (the aligned-superset loads would read past the end)
     _ragged_pair_case(pkg, [(7, 10), (12, 16), (5, 9)], 34)
+    assert "ragged persistent pair kernel: 2 frames (per-plane phases)" in capfd.readouterr().err
+    _ragged_pair_case(pkg, [(7, 10), (5, 9), (3, 1025), (9, 13), (6, 1027), (375, 1242), (11, 30), (1, 1), (3, 2)], 36)
+    assert "ragged persistent pair kernel: 9 frames (per-plane phases)" in capfd.readouterr().err  # ends on a multiple of 4 pixels
+    _ragged_pair_case(pkg, [(5, 9), (3, 1025), (9, 13)], 37, dtype=np.float64)
+    assert "ragged persistent pair kernel: 2 frames (per-plane phases)" in capfd.readouterr().err
+    # a row too wide for shared memory sends its chunk down the frame-by-frame path
     _ragged_pair_case(pkg, [(8, 4200), (16, 32)], 35)
     assert "ragged persistent" not in capfd.readouterr().err
 
 
-def test_disparity_pair_ragged_writes_only_its_frames(pkg):
+@pytest.mark.parametrize("sizes,gap", [([(8, 1025), (6, 10), (10, 1026), (12, 682), (4, 7), (2, 2), (16, 36)], 8),
+                                       ([(7, 10), (5, 9), (3, 1025), (9, 13), (6, 1027), (11, 30), (1, 3)], 5)])
+def test_disparity_pair_ragged_writes_only_its_frames(pkg, sizes, gap):
     """Guard bands between the frames of a ragged batch (offsets need not be contiguous) stay untouched in every result plane:
     the aligned-superset loads never turn into stores, head / tail pixels are written exactly."""
     rng = np.random.default_rng(41)
-    sizes = [(8, 1025), (6, 10), (10, 1026), (12, 682), (4, 7), (2, 2), (16, 36)]
-    gap = 8
     offs, P = [], gap
     for h, w in sizes:
         offs.append(P)

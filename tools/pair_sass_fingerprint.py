@@ -31,7 +31,7 @@ def fingerprints():
     res = {}
     for name, ins in out.items():
         m = re.search(r"persistentI(.)Li(\d)ELi(\d)E", name)
-        key = f"pair_rows_persistent<{'float' if m.group(1) == 'f' else 'double'},{m.group(2)},{('PAIR_ROW', 'PAIR_GROUPED', 'PAIR_RAGGED')[int(m.group(3))]}>"
+        key = f"pair_rows_persistent<{'float' if m.group(1) == 'f' else 'double'},{m.group(2)},{('PAIR_ROW', 'PAIR_GROUPED', 'PAIR_RAGGED', 'PAIR_RAGGED_ANY')[int(m.group(3))]}>"
         res[key] = (len(ins), hashlib.sha256("\n".join(ins).encode()).hexdigest()[:16])
     return res
 

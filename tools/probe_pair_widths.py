@@ -27,7 +27,7 @@ def timeit(fn, n=20, warm=3):
 if __name__ == "__main__":
     targets = [int(a) for a in sys.argv[1:]] or [0]
     for (H, W, B) in ((480, 640, 256), (480, 642, 256), (480, 641, 256), (1080, 1920, 32), (1080, 1922, 32), (368, 496, 256),
-                      (300, 1000, 128), (300, 1002, 128), (512, 384, 256), (1080, 1001, 32), (1080, 2562, 16)):
+                      (300, 1000, 128), (300, 1002, 128), (512, 384, 256), (1080, 1001, 32), (1080, 2562, 16), (375, 1242, 64), (481, 641, 64)):
         img = torch.rand(B, 3, H, W, device=dev) * 255
         depth = torch.rand(B, 1, H, W, device=dev) * 98 + 1
         s = torch.full((B,), 47.0, device=dev)
