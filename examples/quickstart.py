@@ -47,6 +47,13 @@ smooth = bilateral_filter.sparse_bilateral_filtering(depth[0, 0], None, [7, 7, 5
 ragged = bilateral_filter.sparse_bilateral_filtering_batch([depth[0, 0], depth[1, 0, :100, :150].contiguous()], [7, 5], 0.04, 2)
 print("bilateral:", tuple(smooth.shape), [tuple(r.shape) for r in ragged])
 
+# 5b. mixed-resolution frames end to end: ragged normalize + bilateral, then every frame's virtual-stereo pair in ONE launch
+r_depths = [depth[0, 0], depth[1, 0, :100, :150].contiguous()]
+packed_depth, shapes, offsets = bilateral_filter.sparse_bilateral_filtering_batch(r_depths, [7, 5], 0.04, 2, return_packed=True)
+packed_img = torch.cat([img[0].reshape(-1), img[1, :, :100, :150].reshape(-1)])  # frame i as [3,H_i,W_i] at element 3 * offsets[i]
+packed = ops.disparity_pair_ragged(packed_img, packed_depth, torch.full((2,), 47.0, device=dev), shapes, offsets)
+print("ragged pairs:", [tuple(v.shape) for v in ops.ragged_views(packed[0], 3, shapes, offsets)])
+
 # 6. the reference's driver: 121 .npz files per frame, then read one sample back like the training loader does
 with tempfile.TemporaryDirectory() as tmp:
     driver = pp.PreprocessPlusAugment(dev, inpaint=None, quiet=True, compress=1, reader_compat=True)
