@@ -646,6 +646,26 @@ __global__ void __launch_bounds__(1024) pair_rows_persistent(const float* __rest
     }
 }
 
+// Ring depths for a shared-memory row stride of VW pixels, tuned on B200 (profiles/r1/tune_pair.txt): the deepest plan that still lets
+// two CTAs share an SM, else the deepest that fits one.  false: the row is too wide for shared memory.
+template <typename DT>
+static bool choose_pair_plan(int VW, int* in_stages, int* out_stages, size_t* smem) {
+#ifdef OFD_PAIR_IN_STAGES
+    static const int plans[][2] = {{OFD_PAIR_IN_STAGES, OFD_PAIR_OUT_STAGES}};
+#else
+    static const int plans[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}, {2, 1}};
+#endif
+    for (int pass = 0; pass < 2; ++pass)
+        for (const auto& pl : plans) {
+            const size_t need = PairPlan<DT>::bytes(VW, pl[0], pl[1]);
+            if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
+                *in_stages = pl[0], *out_stages = pl[1], *smem = need;
+                return true;
+            }
+        }
+    return false;
+}
+
 template <typename DT>
 static int launch_pair_persistent(const char* fn, const float* img0, const DT* depth0, const float* sBf, int B, int H, int W,
                                   float* img1, float* depth1, float* back_flow, float* flow, float* valid, float* collision,
@@ -671,23 +691,9 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
     }
     if (G > H) G = (H / align_rows) * align_rows;
     const int VW = G * W;
-    // ring depths, tuned on B200 (profiles/r1/tune_pair.txt): the deepest plan that still lets two CTAs share an SM
-#ifdef OFD_PAIR_IN_STAGES
-    static const int plans[][2] = {{OFD_PAIR_IN_STAGES, OFD_PAIR_OUT_STAGES}};
-#else
-    static const int plans[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}, {2, 1}};
-#endif
     int in_stages = 0, out_stages = 0;
     size_t smem = 0;
-    for (int pass = 0; pass < 2 && !in_stages; ++pass)
-        for (const auto& pl : plans) {
-            const size_t need = PairPlan<DT>::bytes(VW, pl[0], pl[1]);
-            if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
-                in_stages = pl[0], out_stages = pl[1], smem = need;
-                break;
-            }
-        }
-    if (!in_stages) return OFD_OK;  // row too wide for shared memory: fall back to the one-row kernel
+    if (!choose_pair_plan<DT>(VW, &in_stages, &out_stages, &smem)) return OFD_OK;  // row too wide: fall back to the one-row kernel
     // each thread owns NITER pixels of a (virtual) row; threads = ceil(VW / NITER) rounded up to a warp
     int niter = OFD_PAIR_NITER;
     while ((VW + niter - 1) / niter > 1024) niter *= 2;
@@ -753,18 +759,9 @@ static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth
     tab.n = n, tab.total_units = (int)units;
     tab.img[n].H = tab.img[n].W = tab.img[n].G = 1, tab.img[n].unit0 = (int)units, tab.img[n].off = 0;
     const int VW = ((used + 3) & ~3) + 8;  // shared-memory row stride: room for the alignment shift and the rounded-up copy size
-    static const int plans[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}, {2, 1}};
     int in_stages = 0, out_stages = 0;
     size_t smem = 0;
-    for (int pass = 0; pass < 2 && !in_stages; ++pass)
-        for (const auto& pl : plans) {
-            const size_t need = PairPlan<DT>::bytes(VW, pl[0], pl[1]);
-            if (need <= (pass == 0 ? (size_t)113 * 1024 : (size_t)227 * 1024)) {
-                in_stages = pl[0], out_stages = pl[1], smem = need;
-                break;
-            }
-        }
-    if (!in_stages) return OFD_OK;
+    if (!choose_pair_plan<DT>(VW, &in_stages, &out_stages, &smem)) return OFD_OK;
     int niter = OFD_PAIR_NITER;
     while ((used + niter - 1) / niter > 1024) niter *= 2;
     if (niter > 4 * OFD_PAIR_NITER) return OFD_OK;
