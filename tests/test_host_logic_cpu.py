@@ -283,3 +283,13 @@ def test_ragged_views_and_argument_checks_of_the_ragged_pair():
     assert packed[3 * 0 + 6 + 5] == -1.0
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         ops.disparity_pair_ragged(torch.zeros(3 * P), torch.zeros(P), torch.zeros(3), shapes, offs)
+
+
+def test_ragged_bilateral_batch_of_nothing():
+    """Empty ragged batches return empty results in both forms without touching the device."""
+    from opticalflowfromdepth_b200 import bilateral_filter
+    assert bilateral_filter.sparse_bilateral_filtering_batch([], [7, 5], 0.04, 2) == []
+    packed, shapes, offsets = bilateral_filter.sparse_bilateral_filtering_batch([], [7, 5], 0.04, 2, return_packed=True)
+    assert packed.numel() == 0 and shapes == [] and offsets == []
+    with pytest.raises(TypeError):
+        bilateral_filter.sparse_bilateral_filtering_batch([], [7, 5], 0.04)  # num_iter=None: range(None) in the reference
