@@ -32,6 +32,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W = 480, 640
+GROUP_BYTES_PER_PX = 56 + 64 + 56 + 2 * 40 + 12 + 2 * 60   # 388: SURVEY 8d rows of the 7 splats of one frame group
 PAIR_BYTES_PER_PX = 56          # img 3 + depth 1 in; img1 3, depth1 1, back_flow 2, flow 2, valid 1, collision 1 out
 FW_BYTES_PER_PX = lambda C: 4 * (2 * C + 5)  # noqa: E731  splat at the FW.forward boundary
 POOL = 16                       # distinct synthetic frames; the batch cycles through them
@@ -139,8 +140,8 @@ def run_reference(args):
     depth = np.stack([oflow.normalize_depth(torch.from_numpy(raw[k].copy())).numpy() for k in range(raw.shape[0])])
     idx = np.arange(frames) % img.shape[0]
     img, depth, sBf = np.ascontiguousarray(img[idx]), np.ascontiguousarray(depth[idx]), s_values(frames)
-    steps = min(args.steps, 10)
-    for _ in range(min(args.warmup, 2)):
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)   # exactly what the driver asked for; a step is a bounded sample
+    for _ in range(warm):
         oracle.disparity_pair(img, depth, sBf, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -150,7 +151,7 @@ def run_reference(args):
     sample = f"{frames} frames/step x {steps} steps of the same 480x640 workload, {cores} pthreads over frames"
     line = {
         "impl": "reference", "metric": "flow pairs/s @480x640", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg5 480x640 DIML-shaped frames: virtual-disparity flow pair (flow synthesis + C=6 z-buffered splat)",
                    "frames_per_step": frames, "H": H, "W": W},
@@ -194,12 +195,18 @@ def run_ours(args):
     if not (ROOT / "opticalflowfromdepth_b200" / "libofd_b200.so").exists():
         if rank == 0:
             ge.build()
+    from opticalflowfromdepth_b200 import sweep as sweep_mod
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cores_mine = sweep_mod.bind_rank_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    nccl_log = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("OFD_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the one JSON line, so NCCL's log (version banner, "comm ... nranks N" init lines) goes to a per-rank file
+        # and is replayed to stderr at the end - not silenced
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            nccl_log = f"/tmp/ofd_nccl_{os.getpid()}_r{rank}.log"
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
     from opticalflowfromdepth_b200 import _lib, geometry, ops, sweep, synthesis
 
@@ -269,8 +276,77 @@ def run_ours(args):
     if rank == 0:
         line["clocks"] = clk.summary()
 
-    # ---- secondary numbers, rank 0 only when N > 1 keeps the scaling runs short ------------------------------------------
+    def max_over_ranks(seconds):
+        tt = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     skip = set(filter(None, args.skip.split(",")))
+    # ---- cfg5 as stated (BASELINE config 5): the reference's 5-pair group per frame, sharded by image index over the ranks --------
+    # Both legs run at EVERY N (they are the sweep the scaling claim is about); values are whole-job aggregates, max time over ranks.
+    if "group" not in skip:
+        # (b2) the whole group on device-resident frames (preprocess.py:356-432 minus inpaint): 7 splats with fused producers /
+        #      epilogues = 13 launches per batch; >= 10 k frames per rank from the recycled pool
+        try:
+            Fq = min(F, args.group_frames)
+            Kq, invKq = synthesis.Plausible.K((H, W))
+            camsq = []
+            for k in range(Fq):
+                torch.manual_seed(12345 + int(my_idx[k]))
+                camsq.append(geometry.camera_constants(Kq, invKq, synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]))
+            camq = torch.cat(camsq).to(dev)
+            g_counters = ops.new_counters(dev)
+
+            def qstep():
+                synthesis.synthesize_group(img[:Fq], depth[:Fq], sBf[:Fq], camq)
+
+            nq = max(3, (args.group_total + Fq - 1) // Fq)
+            tq_rank = timed(qstep, nq, 3, sync, barrier)
+            tq = max_over_ranks(tq_rank) / nq
+            synthesis.synthesize_group(img[:Fq], depth[:Fq], sBf[:Fq], camq, counters=g_counters)  # one counted pass, untimed
+            g_counters[_lib.CNT_FRAMES] += Fq * nq
+            g_counters[_lib.CNT_PAIRS] += 5 * Fq * nq
+            gbytes = GROUP_BYTES_PER_PX * H * W * Fq
+            line["group_480x640"] = {"frames_per_s": world * Fq / tq, "pairs_per_s": 5 * world * Fq / tq, "ms_per_step": 1e3 * tq,
+                                     "frames_per_step_per_gpu": Fq, "steps": nq, "frames_per_rank": Fq * nq, "launches_per_step": 13,
+                                     "achieved_GBps_per_gpu": gbytes / tq / 1e9, "frac_of_measured_peak": gbytes / tq / 1e9 / peak,
+                                     "algorithmic_bytes_per_px": GROUP_BYTES_PER_PX,
+                                     "counters": sweep.reduce_counters(g_counters),
+                                     "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats); bytes = SURVEY 8d rows summed: "
+                                             "56 (0->1) + 64 (1->2) + 56 (0->3) + 2 x 40 (ConcatFlow) + 12 (flow13_valid * valid1) + 2 x 60 (C=7 frame splats)"}
+            del camq
+        except Exception as e:
+            line["group_480x640"] = {"error": repr(e)}
+    if "sweep" not in skip:
+        # (b4) cfg5 end to end: the sweep driver (per-image reseeding, host frames in, 44-channel group arrays out to pinned host
+        #      memory by strided DMA), inpaint and .npz writing excluded as SURVEY 8d says; this rank's shard = idx % world == rank
+        try:
+            n_sw, b_sw = args.sweep_frames, 32
+            shard = list(sweep.shard_strided(n_sw * world, world, rank))
+            pool_f = [(img_pool[k], raw_pool[k]) for k in range(POOL)]
+            sink = sweep.PinnedGroupSink()
+            # warm-up over three batches: page-locked staging (2 input slots, output slots of 1.7 GB) is allocated once
+            sweep.run_sweep(shard[:3 * b_sw], lambda i: pool_f[i % POOL], dev, batch=b_sw, dataset_len=n_sw * world, sink=sink)
+            sync()
+            sink.frames = sink.bytes = 0
+            barrier()
+            t0 = time.perf_counter()
+            sw_counters = sweep.run_sweep(shard, lambda i: pool_f[i % POOL], dev, batch=b_sw, dataset_len=n_sw * world, sink=sink)
+            sync()
+            ts = max_over_ranks(time.perf_counter() - t0)
+            line["cfg5_sweep_e2e"] = {"frames_per_s": world * n_sw / ts, "pairs_per_s": 5 * world * n_sw / ts, "frames_per_rank": n_sw, "batch": b_sw,
+                                      "seconds": ts, "d2h_bytes_per_frame": sink.bytes // max(sink.frames, 1), "h2d_bytes_per_frame": 4 * H * W * 4,
+                                      "d2h_GBps_per_gpu": sink.bytes / ts / 1e9, "pinned_output_buffers": sink.buffers_allocated,
+                                      "counters": sweep.reduce_counters(sw_counters),
+                                      "what": "sweep.run_sweep: host frames -> normalize_depth -> 5-pair group (reference RNG draw order per frame) -> "
+                                              "44-channel group array in pinned host memory (22 strided DMAs per batch, no concatenation on the device, "
+                                              "double-buffered); wall clock incl. host RNG, staging copy, H2D, D2H; max over ranks"}
+            del sink
+        except Exception as e:
+            line["cfg5_sweep_e2e"] = {"error": repr(e)}
+
+    # ---- secondary numbers, rank 0 only when N > 1 keeps the scaling runs short ------------------------------------------
     if world == 1 or args.extras:
         extras = {}
         if "general" not in skip:
@@ -396,76 +472,55 @@ def run_ours(args):
                                                              "per batch); *_reference_draw_order draws per sample in the reference's get_random order (host-bound)"}
             except Exception as e:
                 extras["cfg4_augment_368x496_b8"] = {"error": repr(e)}
-        if "group" not in skip:
-            # (b2) the reference's whole 5-pair group per frame (preprocess.py:356-432 minus inpaint): 7 splats with
-            #      fused producers/epilogues = 13 launches per batch
-            try:
-                Fq = min(F, args.group_frames)
-                Kq, invKq = synthesis.Plausible.K((H, W))
-                camsq = []
-                for k in range(Fq):
-                    torch.manual_seed(12345 + k)
-                    camsq.append(geometry.camera_constants(Kq, invKq, synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]))
-                camq = torch.cat(camsq).to(dev)
-
-                def qstep():
-                    synthesis.synthesize_group(img[:Fq], depth[:Fq], sBf[:Fq], camq)
-
-                tq = timed(qstep, 10, 3, sync, barrier) / 10
-                extras["group_480x640"] = {"frames_per_s": Fq / tq, "pairs_per_s": 5 * Fq / tq, "ms_per_step": 1e3 * tq, "frames_per_step": Fq,
-                                           "launches_per_step": 13, "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats)"}
-            except Exception as e:
-                extras["group_480x640"] = {"error": repr(e)}
-        if "sweep" not in skip:
-            # (b4) cfg5 end to end: the sweep driver (per-image reseeding, host frames in, 44-channel group tensors out to pinned
-            #      host memory), inpaint and .npz writing excluded as SURVEY 8d says
-            try:
-                n_sw, b_sw = 96, 32
-                pool_f = [(img_pool[k % POOL], raw_pool[k % POOL]) for k in range(n_sw)]
-                sink = sweep.PinnedGroupSink()
-                # warm-up over two batches: page-locked staging (2 input slots, 2 x 1.7 GB output slots) is allocated once
-                sweep.run_sweep(range(2 * b_sw), lambda i: pool_f[i], dev, batch=b_sw, dataset_len=n_sw, sink=sink)
-                sync()
-                sink.frames = sink.bytes = 0
-                t0 = time.perf_counter()
-                sweep.run_sweep(range(n_sw), lambda i: pool_f[i], dev, batch=b_sw, dataset_len=n_sw, sink=sink)
-                sync()
-                ts = time.perf_counter() - t0
-                extras["cfg5_sweep_e2e"] = {"frames_per_s": n_sw / ts, "pairs_per_s": 5 * n_sw / ts, "frames": n_sw, "batch": b_sw,
-                                            "d2h_bytes_per_frame": sink.bytes // max(sink.frames, 1), "h2d_bytes_per_frame": 4 * H * W * 4,
-                                            "what": "sweep.run_sweep: host frames -> normalize_depth -> 5-pair group (reference RNG draw order per frame) -> "
-                                                    "44-channel group tensor in pinned host memory (double-buffered async D2H); wall clock incl. host RNG, staging copy, H2D, D2H"}
-            except Exception as e:
-                extras["cfg5_sweep_e2e"] = {"error": repr(e)}
         if "ref" not in skip:
-            # (c) the reference's own kernel on this GPU (same inputs, C=6, 480x640)
+            # (c) BASELINE.md R1: the reference's own fw_cuda kernel (compiled unmodified for sm_100a, oracle/_ref) driven through the
+            #     reference's own FW.forward (alt_cuda/fw.py staged unmodified in baseline/_ref: CPU meshgrid + H2D + torch prologue +
+            #     extension), C in {2,4,6,7}, 480x640 and 1080p, CUDA events around whole calls (B = 1, as the reference forces)
             try:
                 import oracle
 
-                ref = oracle.load_ref_fw_cuda()
-                fl = ops.disparity_flow(depth[:1], sBf[:1])
-                obj = torch.cat((img[:1], depth[:1], fl * -1.0), 1).contiguous()
-                gx, gy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
-
-                def ref_call():
-                    # alt_cuda/fw.py:27-43 (host meshgrid + H2D every call) then the extension
-                    p0 = torch.stack((gx, gy), 0).float().repeat(1, 1, 1, 1).to(dev)
-                    p1 = p0 + fl
-                    sy = torch.clamp(p1[:, 1:2], min=0, max=H - 1).contiguous().long().float()
-                    sx = torch.clamp(p1[:, 0:1], min=0, max=W - 1).contiguous().long().float()
-                    return ref.forward_warping(obj, sy, sx, depth[:1])
-
-                ref_call()
-                sync()
-                t0 = time.perf_counter()
-                n_ref = 3
-                for _ in range(n_ref):
-                    ref_call()
-                sync()
-                per_ref = (time.perf_counter() - t0) / n_ref
-                extras["ref_fw_cuda"] = {"pairs_per_s": 1.0 / per_ref, "ms_per_call": 1e3 * per_ref,
-                                         "achieved_GBps": FW_BYTES_PER_PX(6) * H * W / per_ref / 1e9,
-                                         "what": "reference fw_cuda (alt_cuda/fw_cuda_kernel.cu, unmodified, sm_100a) driven by the fw.py prologue, C=6, one 480x640 frame per call"}
+                RefFW = oracle.load_ref_fw_class()
+                ref_fw = RefFW(device=dev)
+                table = {}
+                for (hh, ww), reps in (((H, W), 3), ((1080, 1920), 1)):
+                    if (hh, ww) == (H, W):
+                        d1 = depth[0]
+                        fl1 = ops.disparity_flow(depth[:1], sBf[:1])[0]
+                        im1 = img[0]
+                    else:
+                        from opticalflowfromdepth_b200 import synthetic
+                        d1 = ops.normalize_depth(torch.from_numpy(synthetic.diml_frame(100, hh, ww)[1]).to(dev)[None])[0]
+                        fl1 = ops.disparity_flow(d1[None], sBf[:1])[0]
+                        im1 = torch.rand(3, hh, ww, device=dev) * 255
+                    objs = {2: fl1, 4: torch.cat((im1, d1), 0), 6: torch.cat((im1, d1, fl1 * -1.0), 0),
+                            7: torch.cat((im1, d1, fl1 * -1.0, torch.ones_like(d1)), 0)}
+                    for Cn, obj in objs.items():
+                        obj = obj.contiguous()
+                        ref_fw(obj, fl1, d1)  # warm-up
+                        sync()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(reps):
+                            ref_fw(obj, fl1, d1)
+                        e1.record()
+                        sync()
+                        per = e0.elapsed_time(e1) / 1e3 / reps
+                        # ours at the same boundary, batch 1 (the drop-in call shape)
+                        ops.splat_flow(obj[None], fl1[None].contiguous(), d1[None])
+                        sync()
+                        e0.record()
+                        for _ in range(20):
+                            ops.splat_flow(obj[None], fl1[None].contiguous(), d1[None])
+                        e1.record()
+                        sync()
+                        ours = e0.elapsed_time(e1) / 1e3 / 20
+                        table[f"{hh}x{ww}_C{Cn}"] = {"ref_ms_per_call": 1e3 * per, "ref_GBps": FW_BYTES_PER_PX(Cn) * hh * ww / per / 1e9,
+                                                      "ours_ms_per_call_b1": 1e3 * ours, "speedup_b1": per / ours}
+                per6 = table[f"{H}x{W}_C6"]["ref_ms_per_call"] / 1e3
+                extras["ref_fw_cuda"] = {"pairs_per_s": 1.0 / per6, "ms_per_call": 1e3 * per6,
+                                         "achieved_GBps": FW_BYTES_PER_PX(6) * H * W / per6 / 1e9, "table": table,
+                                         "what": "the reference's FW.forward (alt_cuda/fw.py, unmodified) over the reference's fw_cuda kernel (alt_cuda/fw_cuda_kernel.cu, "
+                                                 "unmodified, sm_100a), one frame per call, CUDA events; ours_*_b1 = ofd_splat_flow on the same single frame"}
             except Exception as e:
                 extras["ref_fw_cuda"] = {"unavailable": repr(e)}
         line.update(extras)
@@ -485,18 +540,24 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(Ke):
             pipe.run(h_img, h_depth, h_s, *h_out)  # returns after the last D2H byte has landed
-        te = time.perf_counter() - t0
+        te = max_over_ranks(time.perf_counter() - t0)
+        # the same call when the caller recycles its result buffers (their flow.y / back_flow.y planes already hold the constants)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            pipe.run(h_img, h_depth, h_s, *h_out, keep_const_planes=True)
+        tk = max_over_ranks(time.perf_counter() - t0)
         pipe.close()
-        te_t = torch.tensor([te], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * Fe * Ke / float(te_t.item()), "unit": "pairs/s",
+        line["e2e"] = {"value": world * Fe * Ke / te, "unit": "pairs/s",
                        "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * (6 * H * W * 4 + H * W),
                        "host_filled_bytes_per_step": Fe * 4 * H * W * 4,
-                       "frames_per_step": Fe, "steps": Ke,
+                       "frames_per_step": Fe, "steps": Ke, "host_cores_per_rank": len(cores_mine),
+                       "host_workers": int(os.environ.get("OFD_HOST_WORKERS", "2")),
+                       "recycled_buffers_value": world * Fe * Ke / tk,
                        "api": "ofd_pair_pipeline_run (C ABI, pinned float32 host buffers in and out - all 10 result planes, 3-slot H2D/kernel/D2H pipeline; "
-                              "the two constant planes flow.y / back_flow.y are written by host threads instead of crossing PCIe, valid / collision cross as one "
-                              "packed byte per pixel and are expanded into the float planes by the same threads)"}
+                              "the two constant planes flow.y / back_flow.y are written by the pipeline's persistent host threads instead of crossing PCIe, "
+                              "valid / collision cross as one packed byte per pixel and are expanded into the float planes by the same threads; every rank is "
+                              "pinned to its own core slice).  recycled_buffers_value: OFD_PIPE_KEEP_CONST_PLANES (constant planes left as the previous run wrote them)"}
 
     if "e2e" not in skip and "compact" not in skip:
         # same pipeline with the compact transport (uint8 colour + masks, constant planes not transferred): extra information,
@@ -512,12 +573,9 @@ def run_ours(args):
             t0 = time.perf_counter()
             for _ in range(Ke):
                 pipe.run_u8(c_img, h_depth, h_s, *c_out)
-            tc = time.perf_counter() - t0
+            tc = max_over_ranks(time.perf_counter() - t0)
             pipe.close()
-            tc_t = torch.tensor([tc], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tc_t, op=dist.ReduceOp.MAX)
-            line["e2e_compact"] = {"value": world * Fe * Ke / float(tc_t.item()), "unit": "pairs/s", "h2d_bytes_per_step": Fe * (7 * H * W + 4),
+            line["e2e_compact"] = {"value": world * Fe * Ke / tc, "unit": "pairs/s", "h2d_bytes_per_step": Fe * (7 * H * W + 4),
                                    "d2h_bytes_per_step": Fe * 17 * H * W, "api": "ofd_pair_pipeline_run_u8 (uint8 colour/masks, x planes only; lossless for uint8-valued images)"}
         except Exception as e:
             line["e2e_compact"] = {"error": repr(e)}
@@ -567,6 +625,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if nccl_log and os.path.exists(nccl_log):
+        try:
+            sys.stderr.write(open(nccl_log).read())
+            sys.stderr.flush()
+            os.unlink(nccl_log)
+        except OSError:
+            pass
     if rank == 0:
         print(json.dumps(line))
 
@@ -580,6 +645,8 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=128)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--group-frames", type=int, default=128, help="frames per step of the 5-pair group leg")
+    ap.add_argument("--group-total", type=int, default=10240, help="frames per rank of the 5-pair group leg (recycled pool)")
+    ap.add_argument("--sweep-frames", type=int, default=10240, help="frames per rank of the cfg5 end-to-end sweep leg")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extras", action="store_true", help="also run the secondary measurements when N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

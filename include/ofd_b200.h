@@ -166,6 +166,13 @@ int ofd_project(const float* cam_points, const float* P, float eps, int B, int H
 int ofd_frame_splat(const float* img, const float* depth, const float* flow, const float* valid_in, int B, int H,
                     int W, float* img_out, float* depth_out, float* back_flow, float* valid_out, float* collision,
                     float* raw_valid, uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+/* The same splat when the warp flow is float64 (the dataset path: a flow composed with the float64 disparity flow,
+ * preprocess.py:400-401 with cv2-loaded depth): targets are evaluated in float64 from `flow` (alt_cuda/fw.py:31,37-42), the
+ * payload channels 4-5 are -flow_payload, the caller's float32 rounding of the same flow (fw.py:45 casts obj to float32). */
+int ofd_frame_splat_f64(const float* img, const float* depth, const double* flow, const float* flow_payload,
+                        const float* valid_in, int B, int H, int W, float* img_out, float* depth_out, float* back_flow,
+                        float* valid_out, float* collision, float* raw_valid, uint64_t* counters, void* ws,
+                        size_t ws_bytes, ofd_stream_t stream);
 
 /*
  * ofd_reproject_pair — a whole 6-DoF "flow pair" (preprocess.py:372-382 / 385-394 minus inpaint) in two launches:
@@ -300,14 +307,35 @@ int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int d
  * flow and back_flow are constants of the virtual-stereo pair (-0.0 / +0.0): they are not transferred (8 of the 40 result bytes per
  * pixel) but written into the host buffers by host threads while the copies run; valid / collision (0.0f / 1.0f planes) cross PCIe as
  * one packed byte per pixel and are expanded into the caller's float planes by the same threads (25 instead of 40 B/px on the wire,
- * H*W a multiple of 4) - the buffers end up complete and bit-identical either way.  OFD_HOST_WORKERS (default 2) sets the thread count,
- * OFD_HOST_MASK_BYTES=0 sends the masks as float planes.
+ * H*W a multiple of 4) - the buffers end up complete and bit-identical either way.
+ * Host threads: OFD_HOST_WORKERS (default 2, read when the pipeline is CREATED) persistent threads per pipeline; they sleep on a
+ * condition variable between runs and chunks and inherit the CPU affinity of the creating thread.  OFD_HOST_MASK_BYTES=0 (read at
+ * creation) sends the masks as float planes.
+ * ofd_pair_pipeline_run_flags: the same call with option bits.  OFD_PIPE_KEEP_CONST_PLANES: the caller recycles result buffers
+ * whose flow.y / back_flow.y planes already hold -0.0 / +0.0 (e.g. from an earlier run into the same buffers); the pipeline then
+ * never touches those planes (8 B/px fewer host stores per pair).
  */
+#define OFD_PIPE_KEEP_CONST_PLANES 1u
 typedef struct ofd_pair_pipeline ofd_pair_pipeline;
 int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pair_pipeline** out);
 int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host,
                           const float* sBf_host, int B, float* img1_host, float* depth1_host, float* back_flow_host,
                           float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/);
+int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host,
+                                const float* sBf_host, int B, float* img1_host, float* depth1_host, float* back_flow_host,
+                                float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/,
+                                unsigned flags);
+/*
+ * ofd_copy_rows_to_host — device -> host copy of `rows` rows of `width_bytes` with independent pitches (one asynchronous
+ * cudaMemcpy2DAsync on `stream`).  The sweep uses it to scatter each result tensor [B,c,H,W] of a frame group straight into
+ * its channel slice of the page-locked [B,44,H,W] group array (preprocess.py:437-447 layout): rows = B, width = c*H*W*4,
+ * dst pitch = 44*H*W*4 - the 44-channel concatenation the reference builds with torch.cat never exists on the device.
+ */
+int ofd_copy_rows_to_host(const void* src, size_t src_pitch_bytes, void* dst_host, size_t dst_pitch_bytes,
+                          size_t width_bytes, size_t rows, ofd_stream_t stream);
+/* Host-memory probe used by tools/probe_pcie.py: streams n floats of `value` into dst_host with non-temporal stores on the
+ * calling thread (the store pattern of the pipeline's host threads); no CUDA call. */
+int ofd_host_stream_fill(float* dst_host, size_t n, float value);
 /* Compact transport of the same pipeline: colour planes and the valid / collision masks cross PCIe as uint8 and the
  * two constant planes (flow.y == -0.0, back_flow.y == +0.0) are not transferred: 7 B/px up, 16-17 B/px down instead
  * of 16 and 40.  Lossless when img0 holds integers 0..255 - what the reference's loader delivers (cv2.imread then

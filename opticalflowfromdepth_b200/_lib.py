@@ -15,6 +15,7 @@ F32, F64 = 0, 1
 EPI_NONE, EPI_CONCAT, EPI_BACK = 0, 1, 2
 SRC_RELDEPTH, SRC_DISPARITY = 0, 1
 MAX_CHANNELS = 8
+PIPE_KEEP_CONST_PLANES = 1
 CNT_HIT, CNT_HOLE, CNT_COLLISION, CNT_DROPPED, CNT_TIE_SRC, CNT_FRAMES, CNT_PAIRS, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 6, 8
 
 _p, _i, _sz, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
@@ -34,6 +35,7 @@ SIGNATURES = {
     "ofd_backproject": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "ofd_project": (_i, [_p, _p, _f, _i, _i, _i, _p, _p, _p]),
     "ofd_frame_splat": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ofd_frame_splat_f64": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_reproject_pair": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ofd_normalize_depth_ragged": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
@@ -48,6 +50,9 @@ SIGNATURES = {
     "ofd_bilateral_iter_batch": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "ofd_pair_pipeline_run_flags": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint]),
+    "ofd_copy_rows_to_host": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
+    "ofd_host_stream_fill": (_i, [_p, _sz, _f]),
     "ofd_pair_pipeline_run_u8": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "ofd_pair_pipeline_destroy": (None, [_p]),
 }

@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "ofd_common.cuh"
 
@@ -20,6 +22,70 @@ int fail(int code, const char* fmt, ...) {
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return OFD_OK;
+}
+
+// Launch-plan cache: the dynamic shared-memory opt-in and the occupancy query of a persistent kernel cost
+// 10-20 us of driver time per call - nothing at batch 256, most of a batch-1 drop-in call.  They depend only on
+// (device, kernel, threads, smem), so they are resolved once and remembered.  The cache is append-only and mutex-protected; it
+// holds no tensor state (the "no global mutable state" rule of the ABI is about data, this is memoised driver metadata).
+namespace {
+struct PlanEntry {
+    int dev;
+    const void* kern;
+    int threads;
+    size_t smem;
+    int sms, per_sm;
+};
+struct SmemEntry {
+    int dev;
+    const void* kern;
+    size_t smem;
+};
+std::mutex g_plan_mu;
+std::vector<PlanEntry> g_plans;
+std::vector<SmemEntry> g_smem;
+}  // namespace
+
+int ensure_dynamic_smem(const char* fn, const void* kern, size_t smem) {
+    if (smem <= 48 * 1024) return OFD_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto& e : g_smem)
+        if (e.dev == dev && e.kern == kern) {
+            if (e.smem >= smem) return OFD_OK;
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return fail((int)err, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(err));
+            e.smem = smem;
+            return OFD_OK;
+        }
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return fail((int)err, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(err));
+    g_smem.push_back({dev, kern, smem});
+    return OFD_OK;
+}
+
+int launch_plan(const char* fn, const void* kern, int threads, size_t smem, int* sms, int* per_sm) {
+    int rc = ensure_dynamic_smem(fn, kern, smem);
+    if (rc) return rc;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        for (const auto& e : g_plans)
+            if (e.dev == dev && e.kern == kern && e.threads == threads && e.smem == smem) {
+                *sms = e.sms, *per_sm = e.per_sm;
+                return OFD_OK;
+            }
+    }
+    int n_sm = 0, occ = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess || occ < 1 || n_sm < 1) return fail(err ? (int)err : OFD_E_ARG, "%s: occupancy query failed", fn);
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans.push_back({dev, kern, threads, smem, n_sm, occ});
+    *sms = n_sm, *per_sm = occ;
     return OFD_OK;
 }
 

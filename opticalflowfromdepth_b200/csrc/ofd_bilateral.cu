@@ -425,7 +425,7 @@ static void launch_bilateral_masked(const DT* din, const DT* dorig, const unsign
     constexpr int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
     dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_TY);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_masked_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem("bilateral_masked_kernel", (const void*)bilateral_masked_kernel<DT, WS>, smem);
     bilateral_masked_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, mask, H, W, thr, dout, make_krank(WS, coef_f64));
 }
 
@@ -472,7 +472,7 @@ static void launch_bilateral_batch(const DT* din, const DT* dorig, const Bilater
     const int m = window / 2;
     const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_batch_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem("bilateral_batch_kernel", (const void*)bilateral_batch_kernel<DT, WS>, smem);
     bilateral_batch_kernel<DT, WS><<<tiles, dim3(BT_W, BT_TY), smem, st>>>(din, dorig, bb, window, thr, dout, make_krank(window));
 }
 
@@ -493,7 +493,7 @@ static void launch_bilateral(const DT* din, const DT* dorig, int H, int W, int w
     const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     const size_t smem = (size_t)RW * RH * (2 * sizeof(DT) + 1) + (size_t)TW * TH * (sizeof(DT) + 1) + 32;
     dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_TY);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bilateral_iter_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem("bilateral_iter_kernel", (const void*)bilateral_iter_kernel<DT, WS>, smem);
     bilateral_iter_kernel<DT, WS><<<grid, block, smem, st>>>(din, dorig, H, W, window, thr, dout, make_krank(window));
 }
 

@@ -190,4 +190,7 @@ __device__ __forceinline__ void reproject_px(const Cam& cam, DT depth, int i, in
 namespace ofd {
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
+// memoised per (device, kernel[, threads, smem]): dynamic shared-memory opt-in; SM count and resident CTAs per SM (ofd_abi.cu)
+int ensure_dynamic_smem(const char* fn, const void* kern, size_t smem);
+int launch_plan(const char* fn, const void* kern, int threads, size_t smem, int* sms, int* per_sm);
 }  // namespace ofd

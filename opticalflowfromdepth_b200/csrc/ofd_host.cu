@@ -4,18 +4,30 @@
 // on slot k % NSLOT, so the two copy engines and the SMs overlap across chunks.
 #include <emmintrin.h>
 
-#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
 
 #include "ofd_common.cuh"
 
+// One run's work for the host threads: the constant planes to fill and the mask bytes to expand, chunk by chunk.
+struct ofd_host_job {
+    int B = 0, K = 0, chunk = 0;
+    size_t hw = 0;
+    bool mask_bytes = false, fill_const = true;
+    float *back_flow = nullptr, *flow = nullptr, *valid = nullptr, *collision = nullptr;
+    const unsigned char* h_mask = nullptr;
+    const cudaEvent_t* ev = nullptr;
+};
+
 struct ofd_pair_pipeline {
     static constexpr int NSLOT = 3;
     int device, H, W, chunk;
     cudaStream_t st[NSLOT];
+    cudaEvent_t done[NSLOT];  // blocking-sync events: run() sleeps on them instead of spinning in cudaStreamSynchronize
     float* d_in[NSLOT];   // img0 (3) | depth0 (1) per frame, frames contiguous per plane group
     float* d_out[NSLOT];  // img1 (3) | depth1 (1) | back_flow (2) | flow (2) | valid (1) | collision (1)
     float* d_s[NSLOT];
@@ -25,6 +37,18 @@ struct ofd_pair_pipeline {
     unsigned char* h_mask;
     size_t h_mask_cap;
     std::vector<cudaEvent_t> ev;  // one per chunk of a run: "this chunk's mask bytes have landed"
+    bool mask_bytes_enabled;
+    // Host threads of the pipeline (OFD_HOST_WORKERS, read when the pipeline is created): started once, they sleep on a
+    // condition variable between runs and between chunks - no thread creation and no spinning on the timed path.  They
+    // inherit the CPU affinity of the thread that created the pipeline (sweep.bind_rank_cores pins a rank to its own cores).
+    int n_workers;
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_issued, cv_done;
+    unsigned long long job_gen = 0;
+    int issued = 0, finished = 0;
+    bool abort_run = false, quit = false;
+    ofd_host_job job;
 };
 
 namespace ofd {
@@ -96,13 +120,100 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
         if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- the pipeline's host threads --------------------------------------------------------------------------------------
+static void worker_body(ofd_pair_pipeline* p, int t, const ofd_host_job& J) {
+    const int nw = p->n_workers;
+    for (int k = 0; k < J.K; ++k) {
+        const int b0 = k * J.chunk, n = (J.B - b0) < J.chunk ? (J.B - b0) : J.chunk;
+        if (J.fill_const)
+            for (int b = b0 + t; b < b0 + n; b += nw) {
+                fill_plane(J.back_flow + ((size_t)b * 2 + 1) * J.hw, J.hw, 0.0f);
+                if (J.flow) fill_plane(J.flow + ((size_t)b * 2 + 1) * J.hw, J.hw, -0.0f);
+            }
+        if (!J.mask_bytes) continue;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_issued.wait(lk, [&] { return p->issued > k || p->abort_run; });
+            if (p->abort_run) return;
+        }
+        if (cudaEventSynchronize(J.ev[k]) != cudaSuccess) return;  // the main thread reports the stream's error
+        // this worker's 16-pixel-aligned share of the chunk
+        const size_t len = (size_t)n * J.hw, per = ((len + nw - 1) / nw + 15) & ~(size_t)15;
+        const size_t lo = per * t < len ? per * t : len, hi = lo + per < len ? lo + per : len;
+        if (hi > lo) {
+            const size_t o = (size_t)b0 * J.hw + lo;
+            expand_plane(J.h_mask + o, hi - lo, 0, J.valid + o);
+            if (J.collision) expand_plane(J.h_mask + o, hi - lo, 1, J.collision + o);
+        }
+    }
+}
+
+static void worker_main(ofd_pair_pipeline* p, int t) {
+    cudaSetDevice(p->device);
+    unsigned long long seen = 0;
+    for (;;) {
+        ofd_host_job J;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_job.wait(lk, [&] { return p->quit || p->job_gen != seen; });
+            if (p->quit) return;
+            seen = p->job_gen;
+            J = p->job;
+        }
+        worker_body(p, t, J);
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            ++p->finished;
+        }
+        p->cv_done.notify_one();
+    }
+}
+
+// posts a run's host work; the returned guard waits for the workers (and aborts them if the run fails early)
+struct HostRun {
+    ofd_pair_pipeline* p;
+    bool ok = false;
+    explicit HostRun(ofd_pair_pipeline* p_, const ofd_host_job& J) : p(p_) {
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->job = J;
+            p->issued = 0, p->finished = 0, p->abort_run = false;
+            ++p->job_gen;
+        }
+        p->cv_job.notify_all();
+    }
+    void chunk_issued(int k) {
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->issued = k + 1;
+        }
+        p->cv_issued.notify_all();
+    }
+    ~HostRun() {
+        std::unique_lock<std::mutex> lk(p->mu);
+        if (!ok) {
+            p->abort_run = true;
+            p->cv_issued.notify_all();
+        }
+        p->cv_done.wait(lk, [&] { return p->finished == p->n_workers; });
+    }
+};
+
 extern "C" {
 
 void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
     if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->quit = true;
+    }
+    p->cv_job.notify_all();
+    for (auto& th : p->pool)
+        if (th.joinable()) th.join();
     cudaSetDevice(p->device);
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
         if (p->st[s]) cudaStreamSynchronize(p->st[s]), cudaStreamDestroy(p->st[s]);
+        if (p->done[s]) cudaEventDestroy(p->done[s]);
         cudaFree(p->d_in[s]);
         cudaFree(p->d_out[s]);
         cudaFree(p->d_s[s]);
@@ -122,10 +233,15 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     if (!p) return fail(OFD_E_ARG, "ofd_pair_pipeline_create: out of host memory");
     p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
     p->h_mask = nullptr, p->h_mask_cap = 0;
+    // the knobs are read per pipeline (not once per process): a caller can build pipelines with different settings
+    p->n_workers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
+    p->mask_bytes_enabled = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) p->st[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s)
+        p->st[s] = nullptr, p->done[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
         cudaError_t e = cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[s], cudaEventDisableTiming | cudaEventBlockingSync);
         if (e == cudaSuccess) e = cudaMalloc(&p->d_in[s], n * 4 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_out[s], n * 10 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_s[s], n * sizeof(float));
@@ -136,17 +252,24 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
             return rc;
         }
     }
+    try {
+        for (int t = 0; t < p->n_workers; ++t) p->pool.emplace_back(worker_main, p, t);
+    } catch (...) {
+        ofd_pair_pipeline_destroy(p);
+        return fail(OFD_E_ARG, "ofd_pair_pipeline_create: cannot start host threads");
+    }
     *out = p;
     return OFD_OK;
 }
 
 // All *_host pointers are HOST memory (page-locked for overlap), dense [B,C,H,W]; flow/collision may be NULL.
-int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host, const float* sBf_host,
-                          int B, float* img1_host, float* depth1_host, float* back_flow_host, float* flow_host,
-                          float* valid_host, float* collision_host) {
+int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host, const float* sBf_host,
+                                int B, float* img1_host, float* depth1_host, float* back_flow_host, float* flow_host,
+                                float* valid_host, float* collision_host, unsigned flags) {
     const char* fn = "ofd_pair_pipeline_run";
     if (!p) return fail(OFD_E_NULL, "%s: pipeline is NULL", fn);
     if (B < 0) return fail(OFD_E_SHAPE, "%s: negative B", fn);
+    if (flags & ~(unsigned)OFD_PIPE_KEEP_CONST_PLANES) return fail(OFD_E_ARG, "%s: unknown flag bits 0x%x", fn, flags);
     if (B == 0) return OFD_OK;
     if (!img0_host || !depth0_host || !sBf_host || !img1_host || !depth1_host || !back_flow_host || !valid_host)
         return fail(OFD_E_NULL, "%s: NULL host pointer", fn);
@@ -154,13 +277,12 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
     const size_t hw = (size_t)p->H * p->W, F = sizeof(float);
     // Two things do not cross PCIe as float planes (14 of the 40 result bytes per pixel):
     //  - the y planes of both flows are constants of the virtual-stereo pair (flow.y == -0.0, back_flow.y == +0.0,
-    //    preprocess.py:253,361-363) and are written into the host buffers by host threads;
+    //    preprocess.py:253,361-363) and are written into the host buffers by host threads (OFD_PIPE_KEEP_CONST_PLANES: the
+    //    caller recycles result buffers whose y planes already hold the constants - nothing is written there);
     //  - valid / collision are 0.0f / 1.0f planes: they are packed on the device into one byte per pixel, land in the
     //    pipeline's pinned staging buffer and are expanded into the caller's float planes by the same host threads,
     //    chunk by chunk, as soon as a chunk's event fires.   OFD_HOST_MASK_BYTES=0 sends them as float planes instead.
-    static const int kWorkers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
-    static const bool kMaskBytes = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
-    const bool mask_bytes = kMaskBytes && hw % 4 == 0;
+    const bool mask_bytes = p->mask_bytes_enabled && hw % 4 == 0;
     const int K = (B + p->chunk - 1) / p->chunk;
     if (mask_bytes) {
         if (p->h_mask_cap < (size_t)B * hw) {
@@ -171,51 +293,16 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
         }
         while ((int)p->ev.size() < K) {
             cudaEvent_t e;
-            OFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            OFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
             p->ev.push_back(e);
         }
     }
-    std::atomic<int> issued{0};      // chunks whose event has been recorded in THIS run
-    std::atomic<bool> abort_run{false};
-    std::vector<std::thread> workers((size_t)kWorkers);
-    struct Joiner {
-        std::vector<std::thread>& t;
-        std::atomic<bool>& abort_run;
-        bool ok = false;
-        ~Joiner() {
-            if (!ok) abort_run = true;
-            for (auto& th : t)
-                if (th.joinable()) th.join();
-        }
-    } joiner{workers, abort_run};
-    const int chunk = p->chunk, device = p->device;
-    const unsigned char* h_mask = p->h_mask;
-    const cudaEvent_t* ev = p->ev.data();
-    for (int t = 0; t < kWorkers; ++t)
-        workers[(size_t)t] = std::thread([=, &issued, &abort_run]() {
-            if (mask_bytes) cudaSetDevice(device);
-            for (int k = 0; k < K; ++k) {
-                const int b0 = k * chunk, n = (B - b0) < chunk ? (B - b0) : chunk;
-                for (int b = b0 + t; b < b0 + n; b += kWorkers) {
-                    fill_plane(back_flow_host + ((size_t)b * 2 + 1) * hw, hw, 0.0f);
-                    if (flow_host) fill_plane(flow_host + ((size_t)b * 2 + 1) * hw, hw, -0.0f);
-                }
-                if (!mask_bytes) continue;
-                while (issued.load(std::memory_order_acquire) <= k) {
-                    if (abort_run.load(std::memory_order_relaxed)) return;
-                    std::this_thread::yield();
-                }
-                if (cudaEventSynchronize(ev[k]) != cudaSuccess) return;  // the main thread reports the stream's error
-                // this worker's 16-pixel-aligned share of the chunk
-                const size_t len = (size_t)n * hw, per = ((len + kWorkers - 1) / kWorkers + 15) & ~(size_t)15;
-                const size_t lo = per * t < len ? per * t : len, hi = lo + per < len ? lo + per : len;
-                if (hi > lo) {
-                    const size_t o = (size_t)b0 * hw + lo;
-                    expand_plane(h_mask + o, hi - lo, 0, valid_host + o);
-                    if (collision_host) expand_plane(h_mask + o, hi - lo, 1, collision_host + o);
-                }
-            }
-        });
+    ofd_host_job J;
+    J.B = B, J.K = K, J.chunk = p->chunk, J.hw = hw;
+    J.mask_bytes = mask_bytes, J.fill_const = !(flags & OFD_PIPE_KEEP_CONST_PLANES);
+    J.back_flow = back_flow_host, J.flow = flow_host, J.valid = valid_host, J.collision = collision_host;
+    J.h_mask = p->h_mask, J.ev = p->ev.data();
+    HostRun host(p, J);
     for (int k = 0, b0 = 0; b0 < B; b0 += p->chunk, ++k) {
         const int s = k % ofd_pair_pipeline::NSLOT;
         const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
@@ -244,7 +331,7 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
             // masks first: the host expansion of this chunk overlaps the float planes' copies
             OFD_CUDA(cudaMemcpyAsync(p->h_mask + (size_t)b0 * hw, p->d_u8[s], n * hw, cudaMemcpyDeviceToHost, st));
             OFD_CUDA(cudaEventRecord(p->ev[(size_t)k], st));
-            issued.store(k + 1, std::memory_order_release);
+            host.chunk_issued(k);
         }
         OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
         OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
@@ -258,9 +345,33 @@ int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const fl
                 OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
         }
     }
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
-    joiner.ok = true;
-    return OFD_OK;  // ~Joiner waits for the host fills and mask expansions
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventRecord(p->done[s], p->st[s]));
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventSynchronize(p->done[s]));
+    host.ok = true;
+    return OFD_OK;  // ~HostRun waits for the host fills and mask expansions
+}
+
+int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host, const float* sBf_host,
+                          int B, float* img1_host, float* depth1_host, float* back_flow_host, float* flow_host,
+                          float* valid_host, float* collision_host) {
+    return ofd_pair_pipeline_run_flags(p, img0_host, depth0_host, sBf_host, B, img1_host, depth1_host, back_flow_host, flow_host,
+                                       valid_host, collision_host, 0u);
+}
+
+int ofd_copy_rows_to_host(const void* src, size_t src_pitch_bytes, void* dst_host, size_t dst_pitch_bytes, size_t width_bytes,
+                          size_t rows, ofd_stream_t stream) {
+    const char* fn = "ofd_copy_rows_to_host";
+    if (!rows || !width_bytes) return OFD_OK;
+    if (!src || !dst_host) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    if (src_pitch_bytes < width_bytes || dst_pitch_bytes < width_bytes) return fail(OFD_E_ARG, "%s: pitch smaller than the row width", fn);
+    OFD_CUDA(cudaMemcpy2DAsync(dst_host, dst_pitch_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return OFD_OK;
+}
+
+int ofd_host_stream_fill(float* dst_host, size_t n, float value) {
+    if (!dst_host && n) return fail(OFD_E_NULL, "ofd_host_stream_fill: dst is NULL");
+    fill_plane(dst_host, n, value);
+    return OFD_OK;
 }
 
 // Compact transport of the same pipeline: colour and masks as uint8, the two constant planes (flow.y == -0.0,
@@ -317,7 +428,8 @@ int ofd_pair_pipeline_run_u8(ofd_pair_pipeline* p, const unsigned char* img0_u8_
         if (collision_u8_host)
             OFD_CUDA(cudaMemcpyAsync(collision_u8_host + (size_t)b0 * hw, u_col, n * hw, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaStreamSynchronize(p->st[s]));
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventRecord(p->done[s], p->st[s]));
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventSynchronize(p->done[s]));
     return OFD_OK;
 }
 

@@ -705,13 +705,11 @@ static int launch_pair_persistent(const char* fn, const float* img0, const DT* d
                        : (niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_GROUPED>
                                                   : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_GROUPED>
                                                                                  : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_GROUPED>));
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
+    int sms = 0, per_sm = 0;
+    {
+        const int rc_plan = launch_plan(fn, (const void*)kern, threads, smem, &sms, &per_sm);
+        if (rc_plan) return rc_plan;
+    }
     long long grid = (long long)sms * per_sm;
     const long long units = (long long)B * ((H + G - 1) / G);
     if (grid > units) grid = units;
@@ -774,13 +772,11 @@ static int launch_pair_ragged(const char* fn, const float* img0, const DT* depth
         kern = niter == OFD_PAIR_NITER ? pair_rows_persistent<DT, OFD_PAIR_NITER, PAIR_RAGGED_ANY>
                                        : (niter == 2 * OFD_PAIR_NITER ? pair_rows_persistent<DT, 2 * OFD_PAIR_NITER, PAIR_RAGGED_ANY>
                                                                       : pair_rows_persistent<DT, 4 * OFD_PAIR_NITER, PAIR_RAGGED_ANY>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail(e ? (int)e : OFD_E_ARG, "%s: occupancy query failed", fn);
+    int sms = 0, per_sm = 0;
+    {
+        const int rc_plan = launch_plan(fn, (const void*)kern, threads, smem, &sms, &per_sm);
+        if (rc_plan) return rc_plan;
+    }
     long long grid = (long long)sms * per_sm;
     if (grid > units) grid = units;
     if (std::getenv("OFD_DEBUG"))
@@ -858,8 +854,10 @@ static int launch_pair(const char* fn, const float* img0, const DT* depth0, cons
     const bool bulk = (W % 4 == 0) && (((uintptr_t)img0 | (uintptr_t)depth0) % 16 == 0);
     int threads = W >= 512 ? 256 : (W >= 128 ? 128 : 64);
     auto kern = bulk ? pair_row_kernel<DT, true> : pair_row_kernel<DT, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+    {
+        const int rc_smem = ensure_dynamic_smem(fn, (const void*)kern, smem);
+        if (rc_smem) return rc_smem;
+    }
     const size_t hw = (size_t)H * W;
     for (int b0 = done; b0 < B; b0 += 65535) {
         const int Bc = (B - b0) < 65535 ? (B - b0) : 65535;

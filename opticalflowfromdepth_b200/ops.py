@@ -16,6 +16,31 @@ from ._lib import EPI_BACK, EPI_CONCAT, EPI_NONE, F32, F64  # noqa: F401  (re-ex
 _DT = {torch.float32: F32, torch.float64: F64}
 
 
+def _on_device(fn):
+    """Run an operator with its tensors' GPU current: the native launchers query and launch on the CURRENT device
+    (occupancy, SM count, kernel launch), so a call on tensors of another GPU must switch to it first.  Also
+    rejects tensor arguments that live on different devices."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            items = a if isinstance(a, (tuple, list)) else (a,)
+            for t in items:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    if dev is None:
+                        dev = t.device
+                    elif t.device != dev:
+                        raise ValueError(f"{fn.__name__}: tensors on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -79,6 +104,7 @@ def _run_splat(fn: str, device, *args):
         raise
 
 
+@_on_device
 def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
     """fw_cuda.forward_warping (alt_cuda/fw_cuda.cpp:15-26) on [B,C,H,W] / [B,1,H,W] float32 tensors."""
     for n, t in (("obj", obj), ("safe_y", safe_y), ("safe_x", safe_x), ("depth", depth)):
@@ -102,6 +128,7 @@ def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
     return (out, valid, collision, winner) if want_winner else (out, valid, collision)
 
 
+@_on_device
 def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None):
     """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32."""
     _check("obj", obj, dtype=torch.float32)
@@ -123,6 +150,7 @@ def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False,
     return (out, valid, collision, winner) if want_winner else (out, valid, collision)
 
 
+@_on_device
 def disparity_flow(depth, sBf):
     """Convert.depth_to_disparity + disparity_to_flow (preprocess.py:239-254): depth[B,1,H,W] -> flow[B,2,H,W]."""
     _check("depth", depth, dtype=(torch.float32, torch.float64))
@@ -133,6 +161,7 @@ def disparity_flow(depth, sBf):
     return flow
 
 
+@_on_device
 def disparity_pair(img0, depth0, sBf, want_flow=True, want_collision=True, counters=None, out=None):
     """One fused virtual-stereo flow pair (preprocess.py:355-366 minus inpaint).
 
@@ -161,6 +190,7 @@ def disparity_pair(img0, depth0, sBf, want_flow=True, want_collision=True, count
     return img1, depth1, back, flow, valid, coll
 
 
+@_on_device
 def disparity_pair_ragged(img0, depth0, sBf, shapes, offsets, want_flow=True, want_collision=True, counters=None, out=None):
     """disparity_pair over a ragged batch in one launch (ofd_disparity_pair_ragged): img0 / depth0 are 1-D packed CUDA buffers,
     image i is shapes[i] = (H_i, W_i) and starts at PIXEL offset offsets[i] - a C-channel tensor holds it densely as
@@ -198,6 +228,7 @@ def ragged_views(packed, channels: int, shapes, offsets):
     return [packed[channels * o:channels * (o + h * w)].view(channels, h, w) for (h, w), o in zip(shapes, offsets)]
 
 
+@_on_device
 def reproject_flow(depth, cam, eps=1e-7):
     """Convert.depth_to_random_flow (preprocess.py:265-298) fused: depth[B,1,H,W] f32|f64, cam[B,21] f32 -> flow[B,2,H,W]."""
     _check("depth", depth, dtype=(torch.float32, torch.float64))
@@ -209,6 +240,7 @@ def reproject_flow(depth, cam, eps=1e-7):
     return flow
 
 
+@_on_device
 def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_valid=False, counters=None):
     """Image+flow splat of the frame pipeline (preprocess.py:372-382): returns
     (img_out, depth_out, back_flow, valid', collision|None, raw_valid|None)."""
@@ -217,7 +249,7 @@ def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_v
     if c3 != 3:
         raise ValueError("img must be [B,3,H,W]")
     _check("depth", depth, dtype=torch.float32, shape=(B, 1, H, W))
-    _check("flow", flow, dtype=torch.float32, shape=(B, 2, H, W))
+    _check("flow", flow, dtype=(torch.float32, torch.float64), shape=(B, 2, H, W))
     if valid_in is not None:
         _check("valid_in", valid_in, dtype=torch.float32, shape=(B, 1, H, W))
     dev = img.device
@@ -229,12 +261,20 @@ def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_v
     coll = torch.empty((B, 1, H, W), **f32) if want_collision else None
     raw = torch.empty((B, 1, H, W), **f32) if want_raw_valid else None
     ws = workspace.get(dev, B, H, W)
+    if flow.dtype == torch.float64:
+        # float64 warp flow (dataset path): targets in float64, payload = the float32 rounding (fw.py:31 vs :45)
+        payload = flow.float()
+        _run_splat("ofd_frame_splat_f64", dev, _ptr(img), _ptr(depth), _ptr(flow), _ptr(payload), _ptr(valid_in), B, H, W,
+                   _ptr(img_o), _ptr(dep_o), _ptr(back), _ptr(valid), _ptr(coll), _ptr(raw), _ptr(counters), _ptr(ws),
+                   C.c_size_t(ws.numel()), _stream(dev))
+        return img_o, dep_o, back, valid, coll, raw
     _run_splat("ofd_frame_splat", dev, _ptr(img), _ptr(depth), _ptr(flow), _ptr(valid_in), B, H, W, _ptr(img_o),
                _ptr(dep_o), _ptr(back), _ptr(valid), _ptr(coll), _ptr(raw), _ptr(counters), _ptr(ws),
                C.c_size_t(ws.numel()), _stream(dev))
     return img_o, dep_o, back, valid, coll, raw
 
 
+@_on_device
 def reproject_pair(img, depth, cam, valid_in=None, eps=1e-7, want_collision=True, want_raw_valid=False, counters=None):
     """Fused 6-DoF flow pair (preprocess.py:372-382): the flow is computed inside the z-test and written once.
     Returns (img_out, depth_out, back_flow, flow, valid', collision|None, raw_valid|None)."""
@@ -262,6 +302,7 @@ def reproject_pair(img, depth, cam, valid_in=None, eps=1e-7, want_collision=True
     return img_o, dep_o, back, flow, valid, coll, raw
 
 
+@_on_device
 def normalize_depth(depth):
     """utils.normalize_depth (utils.py:102-116), out of place, per frame of depth[B,1,H,W] (f32|f64)."""
     _check("depth", depth, dtype=(torch.float32, torch.float64))
@@ -272,6 +313,7 @@ def normalize_depth(depth):
     return out
 
 
+@_on_device
 def normalize_depth_ragged(packed, counts, offsets):
     """utils.normalize_depth per image of a ragged batch: `packed` is a 1-D CUDA buffer (f32|f64) holding image i as
     counts[i] elements at offsets[i]; returns the normalised packed buffer (same layout)."""
@@ -287,6 +329,7 @@ def normalize_depth_ragged(packed, counts, offsets):
     return out
 
 
+@_on_device
 def depth_from_png(raw, kind: str, dtype=torch.float64):
     """The depth loaders' arithmetic on the device: `raw` is the decoded PNG payload as a uint8 / uint16 (stored as
     int16 bit pattern is not accepted: pass torch.uint16) CUDA tensor of any shape; kind "reldepth" = utils.get_depth with
@@ -303,6 +346,7 @@ def depth_from_png(raw, kind: str, dtype=torch.float64):
     return out
 
 
+@_on_device
 def fix_warped_depth_(depth):
     """utils.fix_warped_depth (utils.py:123-126), in place."""
     _check("depth", depth, dtype=torch.float32)
@@ -310,6 +354,7 @@ def fix_warped_depth_(depth):
     return depth
 
 
+@_on_device
 def inpaint_mask(valid, collision):
     """The mask utils.inpaint hands to cv2.inpaint (utils.py:137-149): uint8 [B,1,H,W], 1 = pixel to fill."""
     _check("valid", valid, dtype=torch.float32)
@@ -327,7 +372,8 @@ def special_flow(kind: int, params, H: int, W: int, device):
     arr = None
     if params is not None:
         arr = (C.c_float * 10)(*[float(v) for v in params])
-    _lib.call("ofd_special_flow", int(kind), arr, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
+    with torch.cuda.device(flow.device):
+        _lib.call("ofd_special_flow", int(kind), arr, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
     return flow, back
 
 
@@ -347,10 +393,12 @@ def special_flow_batch(kinds, params, H: int, W: int, device):
     flow = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
     back = torch.empty((B, 2, H, W), dtype=torch.float32, device=device)
     kinds_arr, flat = _host_params(kinds, params, B)
-    _lib.call("ofd_special_flow_batch", kinds_arr, flat, B, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
+    with torch.cuda.device(flow.device):
+        _lib.call("ofd_special_flow_batch", kinds_arr, flat, B, H, W, _ptr(flow), _ptr(back), _stream(flow.device))
     return flow, back
 
 
+@_on_device
 def augment_pairs(img0, depth0, img1, depth1, flow01, back_flow01, kinds, params, want_collision=True, counters=None):
     """ofd_augment_pairs: the geometric branch of augment_flow (preprocess.py:116-147 minus inpaint) for B pairs, ONE call.
     Returns a dict of the ten result tensors plus the masks of the two image warps."""
@@ -380,6 +428,7 @@ def augment_pairs(img0, depth0, img1, depth1, flow01, back_flow01, kinds, params
     return r
 
 
+@_on_device
 def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
     """One iteration of sparse_bilateral_filtering (bilateral_filter.py:33-58) on [H,W] f32|f64 CUDA tensors."""
     _check("depth_in", depth_in, dtype=(torch.float32, torch.float64))
@@ -393,6 +442,7 @@ def bilateral_iter(depth_in, depth_orig, window: int, threshold: float):
     return out
 
 
+@_on_device
 def bilateral_iter_masked(depth_in, depth_orig, mask_u8, coef_f64: bool, window: int, threshold: float):
     """One iteration with the reference's binary mask (ofd_bilateral_iter_masked): mask_u8 [H,W] uint8 CUDA, 0 = masked."""
     _check("depth_in", depth_in, dtype=(torch.float32, torch.float64))
@@ -407,6 +457,7 @@ def bilateral_iter_masked(depth_in, depth_orig, mask_u8, coef_f64: bool, window:
     return out
 
 
+@_on_device
 def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, threshold: float):
     """One iteration over a ragged batch: packed_in / packed_orig are 1-D CUDA buffers holding image i ([H_i,W_i] dense) at
     element offset offsets[i]; returns the filtered packed buffer (same layout)."""
@@ -424,36 +475,66 @@ def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, t
     return out
 
 
+def scatter_channels_to_host(t, host, c0: int, stream=None):
+    """Asynchronous D2H copy of t[B,c,H,W] (float32 CUDA, contiguous) into channels [c0, c0+c) of the page-locked CPU tensor
+    host[>=B,Ctot,H,W] (ofd_copy_rows_to_host: ONE strided DMA, no concatenation on the device).  Runs on `stream`
+    (default: torch's current stream of t's device); the caller synchronises before reading `host`."""
+    _check("t", t, dtype=torch.float32)
+    if t.dim() != 4 or host.dim() != 4:
+        raise ValueError("t and host must be 4-D [B,C,H,W]")
+    B, c, H, W = t.shape
+    if host.is_cuda or host.dtype != torch.float32 or not host.is_contiguous():
+        raise ValueError("host must be a contiguous float32 CPU tensor (page-locked for an asynchronous copy)")
+    if host.shape[0] < B or tuple(host.shape[2:]) != (H, W) or not (0 <= c0 and c0 + c <= host.shape[1]):
+        raise ValueError(f"host{tuple(host.shape)} cannot take channels [{c0},{c0 + c}) of a batch of {B} frames {H}x{W}")
+    hw4 = H * W * 4
+    st = C.c_void_p(stream.cuda_stream) if stream is not None else _stream(t.device)
+    with torch.cuda.device(t.device):
+        _lib.call("ofd_copy_rows_to_host", _ptr(t), C.c_size_t(c * hw4), C.c_void_p(host.data_ptr() + c0 * hw4),
+                  C.c_size_t(host.shape[1] * hw4), C.c_size_t(c * hw4), C.c_size_t(B), st)
+
+
 class PairPipeline:
-    """Host-buffer front end (ofd_pair_pipeline_*): pinned CPU tensors in, pinned CPU tensors out."""
+    """Host-buffer front end (ofd_pair_pipeline_*): pinned CPU tensors in, pinned CPU tensors out.
+    Every tensor is validated against the pipeline's own (H, W) before the native call (the C side copies B*C*H*W elements)."""
 
     def __init__(self, device: int, H: int, W: int, chunk_frames: int = 8):
         self._h = C.c_void_p(0)
         self.H, self.W = H, W
         _lib.call("ofd_pair_pipeline_create", int(device), H, W, int(chunk_frames), C.byref(self._h))
 
-    def run(self, img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision):
-        B = img0.shape[0]
-        for n, t in (("img0", img0), ("depth0", depth0), ("sBf", sBf), ("img1", img1), ("depth1", depth1),
-                     ("back_flow", back_flow), ("flow", flow), ("valid", valid), ("collision", collision)):
+    def _validate(self, spec, B):
+        for n, t, dt, shape in spec:
             if t is None:
                 continue
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
-        _lib.call("ofd_pair_pipeline_run", self._h, _ptr(img0), _ptr(depth0), _ptr(sBf), B, _ptr(img1), _ptr(depth1),
-                  _ptr(back_flow), _ptr(flow), _ptr(valid), _ptr(collision))
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous {dt} CPU tensor")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{n} must have shape {shape} for this pipeline (B={B}, H={self.H}, W={self.W}), got {tuple(t.shape)}")
+
+    def run(self, img0, depth0, sBf, img1, depth1, back_flow, flow, valid, collision, keep_const_planes: bool = False):
+        """keep_const_planes: the result buffers are recycled and their flow.y / back_flow.y planes already hold -0.0 / +0.0
+        (OFD_PIPE_KEEP_CONST_PLANES) - the pipeline does not rewrite them."""
+        if img0.dim() != 4:
+            raise ValueError("img0 must be [B,3,H,W]")
+        B, H, W, f = img0.shape[0], self.H, self.W, torch.float32
+        self._validate((("img0", img0, f, (B, 3, H, W)), ("depth0", depth0, f, (B, 1, H, W)), ("sBf", sBf, f, (B,)),
+                        ("img1", img1, f, (B, 3, H, W)), ("depth1", depth1, f, (B, 1, H, W)),
+                        ("back_flow", back_flow, f, (B, 2, H, W)), ("flow", flow, f, (B, 2, H, W)),
+                        ("valid", valid, f, (B, 1, H, W)), ("collision", collision, f, (B, 1, H, W))), B)
+        _lib.call("ofd_pair_pipeline_run_flags", self._h, _ptr(img0), _ptr(depth0), _ptr(sBf), B, _ptr(img1), _ptr(depth1),
+                  _ptr(back_flow), _ptr(flow), _ptr(valid), _ptr(collision),
+                  C.c_uint(_lib.PIPE_KEEP_CONST_PLANES if keep_const_planes else 0))
 
     def run_u8(self, img0_u8, depth0, sBf, img1_u8, depth1, back_flow_x, flow_x, valid_u8, collision_u8):
         """Compact transport (ofd_pair_pipeline_run_u8): uint8 colour / masks, x planes only.  CPU tensors, contiguous."""
-        B = img0_u8.shape[0]
-        for n, t, dt in (("img0_u8", img0_u8, torch.uint8), ("depth0", depth0, torch.float32), ("sBf", sBf, torch.float32),
-                         ("img1_u8", img1_u8, torch.uint8), ("depth1", depth1, torch.float32),
-                         ("back_flow_x", back_flow_x, torch.float32), ("flow_x", flow_x, torch.float32),
-                         ("valid_u8", valid_u8, torch.uint8), ("collision_u8", collision_u8, torch.uint8)):
-            if t is None:
-                continue
-            if t.is_cuda or t.dtype != dt or not t.is_contiguous():
-                raise ValueError(f"{n} must be a contiguous {dt} CPU tensor")
+        if img0_u8.dim() != 4:
+            raise ValueError("img0_u8 must be [B,3,H,W]")
+        B, H, W, f, u = img0_u8.shape[0], self.H, self.W, torch.float32, torch.uint8
+        self._validate((("img0_u8", img0_u8, u, (B, 3, H, W)), ("depth0", depth0, f, (B, 1, H, W)), ("sBf", sBf, f, (B,)),
+                        ("img1_u8", img1_u8, u, (B, 3, H, W)), ("depth1", depth1, f, (B, 1, H, W)),
+                        ("back_flow_x", back_flow_x, f, (B, 1, H, W)), ("flow_x", flow_x, f, (B, 1, H, W)),
+                        ("valid_u8", valid_u8, u, (B, 1, H, W)), ("collision_u8", collision_u8, u, (B, 1, H, W))), B)
         _lib.call("ofd_pair_pipeline_run_u8", self._h, _ptr(img0_u8), _ptr(depth0), _ptr(sBf), B, _ptr(img1_u8), _ptr(depth1),
                   _ptr(back_flow_x), _ptr(flow_x), _ptr(valid_u8), _ptr(collision_u8))
 

@@ -10,10 +10,11 @@ What differs from the reference is how it gets there:
   * results cross PCIe once per batch into host memory and are compressed / written by a pool of writer threads
     (zlib releases the GIL) while the GPU goes on with the next frame;
   * `utils.inpaint` (OpenCV Telea on the CPU) is a pluggable hook: "reference" reproduces it, None skips it.
-Float64 dataset inputs (cv2.imread(...).astype(float), utils.py:44-72): the 0->1 pair is evaluated from the float64 depth
-exactly as the reference does (float64 disparity, float64 target); the other pairs and the flow composition take the
-float32 rounding of depth0 / flow01 (the reference keeps float64 there; difference <= 1.2e-7 relative).
-Saved arrays are float32 unless save_dtype says otherwise.
+Float64 dataset inputs (cv2.imread(...).astype(float), utils.py:44-72) follow the reference's type promotion end to end
+(synthesis._synthesize_group_f64 / augment_pairs_f64): float64 disparity flow and FW targets, float64 depth x ray product in
+the 0->3 reprojection, float64 flow composition (flow02) and float64 targets wherever the reference's warp flow is float64.
+Saved arrays are float32 unless save_dtype says otherwise (the reference saves the float64 promotion of the same values;
+flow01 / flow02 / depth0, which ARE float64 there, are rounded once on save).
 """
 from __future__ import annotations
 
@@ -167,6 +168,7 @@ class PreprocessPlusAugment(nn.Module):
         """All 12 augmentations of group pair `gi` as ONE device tensor [12, 2, 8, H, W]: [k, 0] is file {gi}_{k}_1
         (set1[0:4] = aug_img0, aug_depth0, aug0_flow, back_aug0_flow) and [k, 1] is file {gi}_{k}_2 (set2[2:6] = aug1_flow,
         back_aug1_flow, aug_img1, aug_depth1), preprocess.py:459-476.  `draws[k]` are the pre-drawn host parameters."""
+        fAB64 = group[GROUP_PAIRS[gi][4]] if group[GROUP_PAIRS[gi][4]].dtype == torch.float64 else None
         imgA, depA, imgB, depB, fAB, bAB = (group[n].float() for n in GROUP_PAIRS[gi])
         h, w = imgA.shape[-2:]
         geo = [k for k, t in enumerate(AUGMENT_TYPES) if t >= 5]
@@ -174,14 +176,18 @@ class PreprocessPlusAugment(nn.Module):
         rep = lambda x: x.expand(n, -1, -1, -1).contiguous()  # noqa: E731
         block = torch.empty((len(AUGMENT_TYPES), 2, 8, h, w), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
-                                  [AUGMENT_TYPES[k] for k in geo], [draws[k] for k in geo])
+            if fAB64 is not None:  # float64 dataset depth: flowAB is float64 in the reference too (pairs 0->1, 0->2')
+                r = synthesis.augment_pairs_f64(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB64), rep(bAB),
+                                                [AUGMENT_TYPES[k] for k in geo], [draws[k] for k in geo])
+            else:
+                r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
+                                      [AUGMENT_TYPES[k] for k in geo], [draws[k] for k in geo])
             a_img0, a_img1 = r["aug_img0"], r["aug_img1"]
             if self.inpaint is not None:
                 a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
                 a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
             block[geo, 0] = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)
-            block[geo, 1] = torch.cat((r["aug1_flow"], r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)
+            block[geo, 1] = torch.cat((r["aug1_flow"].float(), r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)
             for k, t in enumerate(AUGMENT_TYPES):
                 if t < 5:
                     pa = photometric_apply(imgA[0], float(t), draws[k])
@@ -212,15 +218,29 @@ class PreprocessPlusAugment(nn.Module):
         torch.cuda.current_stream(self.device).synchronize()
         return host.numpy().astype(self.save_dtype, copy=False)
 
+    def _group_to_host(self, group: Dict[str, torch.Tensor]) -> np.ndarray:
+        """The 44-channel group array of one frame (preprocess.py:437-447) assembled in page-locked host memory: each result
+        tensor goes by one strided DMA into its channel slice, no torch.cat on the device."""
+        h, w = group["img0"].shape[-2:]
+        host = torch.empty((1, sum(group[n].shape[1] for n in GROUP_CHANNELS), h, w), dtype=torch.float32, pin_memory=True)
+        c0 = 0
+        for n in GROUP_CHANNELS:
+            t = group[n][0:1]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            ops.scatter_channels_to_host(t, host, c0)
+            c0 += t.shape[1]
+        torch.cuda.current_stream(self.device).synchronize()
+        return host[0].numpy().astype(self.save_dtype, copy=False)
+
     def forward(self, datas, output_dir, is_stereo=False, n_continuous=4):
         t0 = time.time()
         group = self.synthesize(datas, is_stereo)
         os.makedirs(output_dir, exist_ok=True)
         with torch.cuda.device(self.device):
-            stack = torch.cat([group[n][0].float() for n in GROUP_CHANNELS], 0)
-            self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=self._to_host(stack))
+            self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=self._group_to_host(group))
             t1 = time.time()
-            h, w = stack.shape[-2:]
+            h, w = group["img0"].shape[-2:]
             plan = self.draw_augmentations(h, w)
             for gi in range(len(GROUP_PAIRS)):
                 block = self._to_host(self.augment_pair_block(group, gi, plan[gi]))

@@ -35,6 +35,33 @@ def shard_strided(n: int, world: int, rank: int) -> range:
     return range(rank, n, world)
 
 
+def rank_cores(local_rank: int, local_world: int, cores: Optional[Sequence[int]] = None) -> List[int]:
+    """The disjoint core set of one rank of a node: the cores this process may run on, split into `local_world` contiguous
+    slices (the remainder goes to the first ranks).  With more ranks than cores every rank keeps the whole set."""
+    import os
+
+    cores = sorted(os.sched_getaffinity(0)) if cores is None else sorted(cores)
+    if local_world < 1 or not (0 <= local_rank < local_world):
+        raise ValueError("need local_world >= 1 and 0 <= local_rank < local_world")
+    if len(cores) < local_world:
+        return list(cores)
+    base, rem = divmod(len(cores), local_world)
+    start = local_rank * base + min(local_rank, rem)
+    return list(cores[start:start + base + (1 if local_rank < rem else 0)])
+
+
+def bind_rank_cores(local_rank: int, local_world: int) -> List[int]:
+    """Pin this process (and every thread it starts later: the pipeline's host workers, torch's pools) to rank_cores(...),
+    so that the ranks of a node do not migrate over each other's cores.  Returns the core list.  OFD_NO_AFFINITY=1 disables it."""
+    import os
+
+    if os.environ.get("OFD_NO_AFFINITY"):
+        return sorted(os.sched_getaffinity(0))
+    mine = rank_cores(local_rank, local_world)
+    os.sched_setaffinity(0, mine)
+    return mine
+
+
 def frame_seed(img_idx: int, epoch_idx: int, dataset_len: int) -> int:
     """Per-image reseeding (preprocess.py:555) — makes results independent of the partition."""
     return 12345 + img_idx + epoch_idx * dataset_len
@@ -57,57 +84,87 @@ def reduce_counters(counters: torch.Tensor, group=None) -> Dict[str, int]:
 
 class PinnedGroupSink:
     """A `sink` for run_sweep that brings every batch's 44-channel group tensor (preprocess.py:437-447 channel order) to the
-    host: one torch.cat on the device, one D2H copy into page-locked memory per batch, issued on a side stream into one of two
-    pinned slots, so the copy of batch k overlaps the host-side preparation and the kernels of batch k+1.
-    `on_batch(idx_list, array[B,44,H,W])` receives the host array once its copy has landed (when its slot is reused, or at
-    flush()) - e.g. to hand it to preprocess.NpzWriter; without it the sink only counts."""
+    host.  The concatenation the reference builds with torch.cat never exists on the device: each of the 22 result tensors is
+    copied by ONE strided DMA (ops.scatter_channels_to_host) straight into its channel slice of a page-locked [B,44,H,W] array,
+    on a side stream, so the copies of batch k overlap the host-side preparation and the kernels of batch k+1.
+
+    `on_batch(idx_list, array[B,44,H,W], release)` receives the host array once its copies have landed (when the next-but-one
+    batch arrives, or at flush()).  The consumer OWNS the array until it calls release() - it may hand it to asynchronous
+    writers (preprocess.NpzWriter) and release it when they are done; the sink takes another page-locked buffer from its pool
+    (allocating one if none is free) instead of overwriting a buffer that is still being read.  Without on_batch the sink
+    only counts and recycles two buffers."""
 
     def __init__(self, on_batch: Optional[Callable] = None):
         self.on_batch = on_batch
         self.frames = 0
         self.bytes = 0
-        self._slots = [None, None]   # (pinned tensor, event, idx_list, n) per slot
-        self._k = 0
+        self.buffers_allocated = 0
+        self._inflight = []          # [(pinned tensor, event, idx_list, n)] oldest first, at most 2
+        self._free = []              # released page-locked buffers
+        import threading
+
+        self._lock = threading.Lock()
         self._stream = None
 
-    def _deliver(self, slot):
-        entry = self._slots[slot]
-        if entry is None:
-            return
-        host, event, idx_list, n = entry
+    def _take(self, shape):
+        with self._lock:
+            for k, h in enumerate(self._free):
+                if h.shape[0] >= shape[0] and tuple(h.shape[1:]) == tuple(shape[1:]):
+                    return self._free.pop(k)
+            self._free.clear()  # another frame size: drop the old buffers
+        self.buffers_allocated += 1
+        return torch.empty(shape, dtype=torch.float32, pin_memory=True)
+
+    def _release(self, host):
+        with self._lock:
+            self._free.append(host)
+
+    def _deliver_oldest(self):
+        host, event, idx_list, n = self._inflight.pop(0)
         event.synchronize()
-        self._slots[slot] = (host, event, None, 0)
-        if idx_list is not None and self.on_batch is not None:
-            self.on_batch(idx_list, host[:n].numpy())
+        if self.on_batch is None:
+            self._release(host)
+            return
+        done = []
+
+        def release():
+            if not done:
+                done.append(True)
+                self._release(host)
+
+        self.on_batch(idx_list, host[:n].numpy(), release)
 
     def __call__(self, idx_list, res):
+        from . import ops
         from .preprocess import GROUP_CHANNELS
 
-        stack = torch.cat([res[n].float() for n in GROUP_CHANNELS], 1)
-        dev = stack.device
+        first = res[GROUP_CHANNELS[0]]
+        dev, B = first.device, first.shape[0]
+        H, W = first.shape[-2:]
         if self._stream is None:
             self._stream = torch.cuda.Stream(dev)
-        slot = self._k & 1
-        self._k += 1
-        self._deliver(slot)  # the slot's previous copy has landed and is handed over before the buffer is reused
-        entry = self._slots[slot]
-        host = entry[0] if entry is not None and entry[0].shape[1:] == stack.shape[1:] and entry[0].shape[0] >= stack.shape[0] else None
-        if host is None:
-            host = torch.empty(stack.shape, dtype=stack.dtype, pin_memory=True)
+        while len(self._inflight) >= 2:  # at most two batches in flight: the older one has landed by now
+            self._deliver_oldest()
+        host = self._take((B, sum(res[n].shape[1] for n in GROUP_CHANNELS), H, W))
         self._stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self._stream):
-            host[:stack.shape[0]].copy_(stack, non_blocking=True)
-            event = torch.cuda.Event()
-            event.record(self._stream)
-        stack.record_stream(self._stream)
-        self._slots[slot] = (host, event, list(idx_list), stack.shape[0])
+        c0 = 0
+        for name in GROUP_CHANNELS:
+            t = res[name]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            ops.scatter_channels_to_host(t, host, c0, stream=self._stream)
+            t.record_stream(self._stream)
+            c0 += t.shape[1]
+        event = torch.cuda.Event()
+        event.record(self._stream)
+        self._inflight.append((host, event, list(idx_list), B))
         self.frames += len(idx_list)
-        self.bytes += stack.numel() * stack.element_size()
+        self.bytes += B * c0 * H * W * 4
 
     def flush(self):
         """Wait for the outstanding copies and hand their batches over (oldest first)."""
-        for slot in (self._k & 1, (self._k + 1) & 1):
-            self._deliver(slot)
+        while self._inflight:
+            self._deliver_oldest()
 
 
 def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device, batch: int = 32, epoch: int = 0,

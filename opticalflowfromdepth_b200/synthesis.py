@@ -20,7 +20,7 @@ from torch import nn
 from . import geometry, ops
 from .fw import FW
 
-__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "sample_special_params",
+__all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "augment_pairs_f64", "sample_special_params",
            "photometric_draws", "photometric_apply",
            "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
 
@@ -390,6 +390,28 @@ def augment_flow_batch(img0, depth0, img1, depth1, flow01, back_flow01, kinds, i
             (r["special_flow"], r["back_special_flow"]))
 
 
+def augment_pairs_f64(img0, depth0, img1, depth1, flow01, back_flow01, kinds, params):
+    """ops.augment_pairs when flow01 is float64 (pairs 0->1 and 0->2' of a float64-depth frame): the reference's type promotion
+    makes aug1_flow = (FW(special, back_flow01) + flow01) * valid float64 (preprocess.py:122,312) and evaluates the targets of its
+    BackFlow splat in float64 (:138, fw.py:31).  Composed from the general splat entry points (6 splats, 12 launches + the
+    special-flow kernel); everything else is float32 exactly as in ofd_augment_pairs.  Returns the same dict."""
+    B, _, H, W = img0.shape
+    dev = img0.device
+    special, back_special = ops.special_flow_batch([int(k) for k in kinds], params, H, W, dev)
+    aug0_flow, _, _ = ops.splat_flow(flow01.float(), special, depth0, epilogue=ops.EPI_CONCAT, aux=back_special)   # :121
+    w1, v1, _ = ops.splat_flow(special, back_flow01, depth1)                                                       # :122
+    aug1_flow = (w1 + flow01) * v1
+    r = dict(special_flow=special, back_special_flow=back_special, aug0_flow=aug0_flow, aug1_flow=aug1_flow)
+    for tag, img, dep in (("0", img0, depth0), ("1", img1, depth1)):                                                # :124-135
+        allc, valid, coll = ops.splat_flow(torch.cat((img, dep), 1), special, dep)
+        r["aug_img" + tag] = allc[:, 0:3].contiguous()
+        r["aug_depth" + tag] = ops.fix_warped_depth_(allc[:, 3:4].contiguous())
+        r["valid_img" + tag], r["collision_img" + tag] = valid, coll
+    r["back_aug0_flow"], _, _ = ops.splat_flow(aug0_flow, aug0_flow, r["aug_depth0"], epilogue=ops.EPI_BACK)       # :137
+    r["back_aug1_flow"], _, _ = ops.splat_flow(aug1_flow.float(), aug1_flow, depth0, epilogue=ops.EPI_BACK)        # :138
+    return r
+
+
 # ---- batched frame-level entry points ----------------------------------------------------------------------------
 @torch.no_grad()
 def synthesize_pairs(img0, depth0, sBf, want_flow=True, want_collision=True, counters=None):
@@ -409,16 +431,17 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
     (1 fused stereo pair, 6 x (z-test + gather)).
 
     img0[B,3,H,W], depth0[B,1,H,W] f32 (normalised), sBf[B], cam1/cam0 built from the same pose: cam[B,21] float32.
-    depth0 may be float64 (dataset path, utils.py:44-72): pair 0->1 is then evaluated from the float64 depth as the
-    reference does (float64 disparity and target); everything after it uses depth0's float32 rounding.
-    Returns a dict of tensors named as in preprocess.py (all float32)."""
+    depth0 may be float64 (dataset path, utils.py:44-72): the group then follows the reference's dtype rules end to end
+    (_synthesize_group_f64: float64 disparity flow, float64 depth x ray product, float64 flow composition and targets).
+    Returns a dict of tensors named as in preprocess.py (float32; on the float64 path depth0, flow01 and flow02 are float64
+    like the reference's)."""
+    if depth0.dtype == torch.float64:
+        return _synthesize_group_f64(img0, depth0, sBf, cam, inpaint, counters)
     dev = img0.device
     fill = (lambda im, v, c: im) if inpaint is None else inpaint
     with torch.cuda.device(dev):
         # pair 0->1: virtual stereo (preprocess.py:356-366)
         img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, True, counters)
-        if depth0.dtype != torch.float32:
-            depth0 = depth0.float()
         img1 = fill(img1, valid1, coll1)
         # pair 1->2: random camera motion from view 1 (preprocess.py:372-382); flow computed inside the z-test
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
@@ -431,6 +454,41 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, counters=counters)
         img2p = fill(img2p, valid2p, coll2p)
         # pair 1->3': (preprocess.py:414-424)
+        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
+        flow13_valid = flow13_valid * valid1
+        img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, counters=counters)
+        img3p = fill(img3p, valid3p, coll3p)
+    return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,
+                img2_prime=img2p, depth2_prime=depth2p, img3_prime=img3p, depth3_prime=depth3p,
+                flow01=flow01, back_flow01=back01, flow12=flow12, back_flow12=back12, flow02=flow02,
+                back_flow02_prime=back02p, flow03=flow03, back_flow03=back03, flow13=flow13, back_flow13_prime=back13p,
+                valid1=valid1, valid2=valid2, valid3=valid3, valid2_prime=valid2p, valid3_prime=valid3p)
+
+
+def _synthesize_group_f64(img0, depth0, sBf, cam, inpaint, counters):
+    """synthesize_group for float64 depth0 - what the reference's loaders deliver (cv2.imread(...).astype(float), utils.py:48,62).
+    The reference then keeps float64 wherever torch's type promotion does (preprocess.py:355-425):
+      flow01 = -(sBf / depth0) is float64, and its FW targets are evaluated in float64 (fw.py:31);
+      flow03: depth0 * ray is a float64 product rounded once to float32 (geometry.py:39-40);
+      flow02 = (FW(flow12) + flow01) * valid is float64 (:312) and drives the 0->2' splat with float64 targets;
+      flow13's splat uses flow01 (float64) as the warp flow (:414); everything that comes OUT of FW is float32 (fw.py:45-58).
+    Same kernels, more launches than the float32 path (the 0->3 pair is flow + splat instead of the fused pair)."""
+    dev = img0.device
+    fill = (lambda im, v, c: im) if inpaint is None else inpaint
+    with torch.cuda.device(dev):
+        img1, depth1, back01, _, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, False, True, counters)
+        flow01 = ops.disparity_flow(depth0, sBf)                      # float64 (preprocess.py:356-357)
+        depth0_f = depth0.float()                                     # what FW sees (fw.py:43,45)
+        img1 = fill(img1, valid1, coll1)
+        img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
+        img2 = fill(img2, valid2, coll2)
+        flow03 = ops.reproject_flow(depth0, cam)                      # float64 depth x ray, float32 flow (geometry.py:39-40)
+        img3, depth3, back03, valid3, coll3, _ = ops.frame_splat(img0, depth0_f, flow03, None, counters=counters)
+        img3 = fill(img3, valid3, coll3)
+        warp12, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1)
+        flow02 = (warp12 + flow01) * flow02_valid                     # float32 + float64 -> float64 (preprocess.py:312)
+        img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0_f, flow02, flow02_valid, counters=counters)
+        img2p = fill(img2p, valid2p, coll2p)
         flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
         flow13_valid = flow13_valid * valid1
         img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, counters=counters)

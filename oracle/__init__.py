@@ -34,9 +34,10 @@ def build(ref: bool = True) -> None:
     if not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
         subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if ref and Path("/root/reference/alt_cuda/fw_cuda_kernel.cu").exists():
-        from .build_ref import build_ref
+        from .build_ref import build_ref, stage_reference_python
 
         build_ref()
+        stage_reference_python()
 
 
 def lib() -> C.CDLL:
@@ -121,6 +122,30 @@ def disparity_pair(img0, depth0, sBf, nthreads=1):
     if rc:
         raise RuntimeError(f"oracle_disparity_pair rc={rc}")
     return img1, depth1, back, flow, valid, coll
+
+
+def load_ref_fw_class():
+    """The reference's own `FW` module class (alt_cuda/fw.py, staged unmodified in baseline/_ref) bound to the reference's own
+    compiled kernel (oracle/_ref/fw_cuda.so): `FW(device).forward(obj, flow, depth)` is then the reference's stock forward-warp
+    call, prologue included.  TEST / BENCH INFRASTRUCTURE only."""
+    import importlib.util
+    import sys
+
+    path = HERE.parent / "baseline" / "_ref" / "alt_cuda" / "fw.py"
+    if not path.exists():
+        raise FileNotFoundError(f"{path} missing: run __graft_entry__.build() in the build container")
+    saved = sys.modules.get("fw_cuda")
+    sys.modules["fw_cuda"] = load_ref_fw_cuda()
+    try:
+        spec = importlib.util.spec_from_file_location("ref_alt_cuda_fw", str(path))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["fw_cuda"] = saved
+        else:
+            sys.modules.pop("fw_cuda", None)
+    return mod.FW
 
 
 def load_ref_fw_cuda():

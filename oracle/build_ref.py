@@ -40,5 +40,32 @@ def build_ref(verbose: bool = False) -> Path | None:
     return target if target.exists() else None
 
 
+REF_ROOT = Path("/root/reference")
+STAGE = HERE.parent / "baseline" / "_ref"
+# the reference's own Python on the flow-synthesis path, staged UNMODIFIED for the GPU box
+REF_PY = ["preprocess.py", "utils.py", "dataloader.py", "geometry.py", "bilateral_filter.py", "flow_colors.py",
+          "alt_cuda/__init__.py", "alt_cuda/fw.py"]
+
+
+def stage_reference_python() -> Path | None:
+    """Copy the reference's Python modules of the path, byte for byte, into git-ignored `baseline/_ref/` (the base contract's
+    place for the unmodified reference; it travels to the GPU box, where /root/reference does not exist).  Used by
+    tools/run_reference_on_dropin.py (the reference's preprocess.py running on top of dropin/) and bench.py's ref_fw_cuda leg (the
+    reference's FW.forward driving its own kernel).  Nothing under baseline/_ref is imported by the product."""
+    import shutil
+
+    if not REF_ROOT.exists():
+        return STAGE if (STAGE / "preprocess.py").exists() else None
+    for rel in REF_PY:
+        src, dst = REF_ROOT / rel, STAGE / rel
+        if not src.exists():
+            continue
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        if not dst.exists() or dst.read_bytes() != src.read_bytes():
+            shutil.copyfile(src, dst)
+    return STAGE
+
+
 if __name__ == "__main__":
     print(build_ref(verbose="-v" in sys.argv))
+    print(stage_reference_python())

@@ -6,6 +6,8 @@ Bars (BASELINE.json north_star): winner/index map, valid (hole mask) and collisi
 1e-5 * max(|p1|, W-1) of the reference (coordinate-relative), with the fraction of truncated
 targets that differ reported.
 """
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -33,6 +35,13 @@ def pkg():
     ns.m, ns.ops, ns.fw_cuda, ns.geometry, ns.synthesis, ns.bilateral_filter, ns.synthetic = (
         m, ops, fw_cuda, geometry, synthesis, bilateral_filter, synthetic)
     return ns
+
+
+# Fraction of a downstream plane of the 5-pair group that may differ from the reference's own pipeline output: those planes are warped
+# along 6-DoF flows that agree with the reference's to ~1e-5 px (dot-product order), and a truncated target can move.  Measured on
+# the goldens by tools/parity_report.py (profiles/r2/parity_report.json: worst plane 0.0071 on the 40x56 case, where ONE moved source
+# is 4.5e-4 of a plane); the bound is 2x that measurement instead of round 1's blanket 0.02.
+GROUP_PLANE_DIFF_LIMIT = 0.015
 
 
 def cu(a):
@@ -430,6 +439,57 @@ def test_pair_pipeline_host_front_end(pkg):
         assert np.array_equal(o.numpy(), wnt)
 
 
+def test_pair_pipeline_options_validation_and_repeat_runs(pkg):
+    """ofd_pair_pipeline_run_flags / PairPipeline.run: (a) OFD_PIPE_KEEP_CONST_PLANES leaves the constant planes as the caller's
+    buffers hold them (poison stays poison; after one full run they hold -0.0 / +0.0 and every later recycled run is complete),
+    (b) the persistent host threads serve many runs of different sizes on one pipeline, (c) a tensor whose shape does not match the
+    pipeline's (H, W) / batch is rejected in Python instead of corrupting the heap, (d) OFD_HOST_WORKERS is read per
+    pipeline."""
+    import os
+
+    h, w = 40, 56
+    rng = np.random.default_rng(21)
+
+    def inputs(B):
+        return (torch.from_numpy(rng.integers(0, 256, (B, 3, h, w)).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rng.integers(1, 60, (B, 1, h, w)).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rng.uniform(40, 55, B).astype(np.float32)))
+
+    for workers in ("1", "3"):
+        os.environ["OFD_HOST_WORKERS"] = workers
+        try:
+            pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=2)
+        finally:
+            del os.environ["OFD_HOST_WORKERS"]
+        for B in (5, 1, 8, 3):
+            img, depth, sBf = inputs(B)
+            want = oracle.disparity_pair(img.numpy(), depth.numpy(), sBf.numpy())
+            outs = [torch.full((B, c, h, w), 7.0).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+            pipe.run(img, depth, sBf, *outs, keep_const_planes=True)
+            assert (outs[2].numpy()[:, 1] == 7.0).all() and (outs[3].numpy()[:, 1] == 7.0).all()  # untouched
+            for k in (0, 1, 4, 5):
+                assert np.array_equal(outs[k].numpy(), want[k])
+            assert np.array_equal(outs[2].numpy()[:, 0], want[2][:, 0]) and np.array_equal(outs[3].numpy()[:, 0], want[3][:, 0])
+            pipe.run(img, depth, sBf, *outs)                              # full run: constants written
+            img2, depth2, sBf2 = inputs(B)
+            pipe.run(img2, depth2, sBf2, *outs, keep_const_planes=True)   # recycled buffers: complete result of the NEW inputs
+            want2 = oracle.disparity_pair(img2.numpy(), depth2.numpy(), sBf2.numpy())
+            for o, wnt in zip(outs, want2):
+                assert np.array_equal(o.numpy(), wnt)
+            assert np.signbit(outs[3].numpy()[:, 1]).all() and not np.signbit(outs[2].numpy()[:, 1]).any()
+        img, depth, sBf = inputs(4)
+        outs = [torch.empty((4, c, h, w)).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+        with pytest.raises(ValueError):
+            pipe.run(img[:, :, :-1].contiguous(), depth, sBf, *outs)                   # wrong H
+        with pytest.raises(ValueError):
+            pipe.run(img, depth, sBf[:3].contiguous(), *outs)                          # short sBf
+        with pytest.raises(ValueError):
+            pipe.run(img, depth, sBf, outs[0], outs[1], outs[2][:, :1].contiguous(), outs[3], outs[4], outs[5])  # back_flow with 1 channel
+        with pytest.raises(ValueError):
+            pipe.run(img, depth, sBf, outs[0][:3], *outs[1:])                          # batch mismatch
+        pipe.close()
+
+
 def test_pair_pipeline_mask_bytes_edge_cases(pkg):
     """The float32 host pipeline sends valid / collision as packed bytes and expands them on the host: growing batches on one
     pipeline (staging buffer and events regrow), host planes that are only 4-byte aligned (scalar head / tail of the
@@ -698,7 +758,7 @@ def test_group_vs_reference_pipeline_golden(pkg, golden):
         _flow_tolerance_check(res[k][0], grp[slice(*sl[k])], h, w, k)
     for k, (a, b) in sl.items():
         diff = float((res[k][0].cpu().numpy() != grp[a:b]).mean())
-        lim = 0.0 if k in ("img0", "depth0", "img1", "depth1", "flow01", "back_flow01") else 0.02
+        lim = 0.0 if k in ("img0", "depth0", "img1", "depth1", "flow01", "back_flow01") else GROUP_PLANE_DIFF_LIMIT
         if k in ("flow12", "flow03", "flow02", "flow13"):
             diff = float((np.abs(res[k][0].cpu().numpy() - grp[a:b]) > 1e-3).mean())
         assert diff <= lim, f"{k}: {diff:.4f} of the plane differs"
@@ -707,9 +767,11 @@ def test_group_vs_reference_pipeline_golden(pkg, golden):
 
 def test_group_float64_dataset_path_vs_reference_golden(pkg, golden):
     """The reference's own pipeline fed with float64, continuous depth (golden pipeline_case_f64; its group tensor is float64).
-    Pair 0->1 is evaluated from the float64 depth here as there (float64 disparity and target): img1 / depth1 / back_flow01 are
-    bit-exact and flow01 is the reference's float64 flow rounded once.  The later pairs take depth0's / flow01's float32 rounding
-    (the reference keeps float64: <= 1.2e-7 relative), so they are held to the path's tolerance."""
+    The float64 path follows the reference's type promotion end to end (synthesis._synthesize_group_f64): depth0, flow01 and flow02
+    are float64 here as there.  Pair 0->1 is exact arithmetic -> bit-exact in float64.  Everything downstream depends on the 6-DoF
+    flows (K=3/4 dot products whose accumulation order is BLAS-dependent in the reference): those flows are held to the path's
+    tolerance, and the planes warped along them may differ where a ~1e-5 px difference moves a truncated target - the fraction is
+    measured (tools/parity_report.py records it) and bounded here at 2x the committed measurement."""
     from opticalflowfromdepth_b200 import preprocess as pp
 
     g = golden("pipeline_case_f64")
@@ -724,17 +786,60 @@ def test_group_float64_dataset_path_vs_reference_golden(pkg, golden):
     widths = [3 if n.startswith("img") else (1 if n.startswith("depth") else 2) for n in names]
     off = np.cumsum([0] + widths)
     sl = {n: (int(off[k]), int(off[k + 1])) for k, n in enumerate(names)}
-    for k in ("img0", "img1", "depth1", "back_flow01"):   # float32-valued in the reference as well
+    assert res["depth0"].dtype == res["flow01"].dtype == res["flow02"].dtype == torch.float64
+    for k in ("img0", "depth0", "img1", "depth1", "flow01", "back_flow01"):   # exact arithmetic: bit-exact, float64 where the reference is
         a, b = sl[k]
         assert eq(res[k][0].double(), grp[a:b]), k
-    for k in ("depth0", "flow01"):                         # float64 in the reference: ours is that value rounded once
+    for k in ("flow12", "flow03"):
         a, b = sl[k]
-        assert eq(res[k][0], grp[a:b].astype(np.float32)), k
+        _flow_tolerance_check(res[k][0], grp[a:b].astype(np.float32), h, w, k + " (f64 path)")
     for k, (a, b) in sl.items():
         got = res[k][0].cpu().numpy().astype(np.float64)
         frac = float((np.abs(got - grp[a:b]) > 1e-3).mean())
-        assert frac <= 0.02, f"{k}: {frac:.4f} of the plane differs from the float64 reference"
+        assert frac <= GROUP_PLANE_DIFF_LIMIT, f"{k}: {frac:.4f} of the plane differs from the float64 reference"
         print(f"[group f64] {k}: differing fraction {frac:.2e}")
+
+
+def test_group_float64_path_is_exact_given_the_flows(pkg):
+    """The float64 dataset path against the oracle composition WITH THE SAME 6-DoF flows (so no tolerance is involved): every
+    plane the reference derives through float64 promotion - flow02 = (FW(flow12, back_flow01) + flow01) * valid in float64, the
+    0->2' splat with float64 targets, flow13's splat along the float64 flow01, the 0->3 flow from the float64 depth x ray product -
+    must be bit-exact (these used to take the float32 rounding of depth0 / flow01)."""
+    h, w = 60, 84
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (1, 3, h, w)).astype(np.float32)
+    raw = (rng.random((1, 1, h, w)) * 80 + 3).astype(np.float64)   # continuous float64 depth
+    depth0 = pkg.ops.normalize_depth(cu(raw))
+    assert depth0.dtype == torch.float64
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    torch.manual_seed(3)
+    T1 = pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0]
+    cam = pkg.geometry.camera_constants(K, invK, T1).to(DEV)
+    sBf = torch.tensor([47.25], device=DEV)
+    res = pkg.synthesis.synthesize_group(cu(img), depth0, sBf, cam)
+    n = lambda k: res[k][0].cpu().numpy()  # noqa: E731
+    d64 = depth0[0].cpu().numpy()
+    d32 = d64.astype(np.float32)
+    # flow01: float64; pair 0->1 from the float64 flow
+    flow01 = oflow.disparity_flow(torch.from_numpy(d64), sBf.cpu()[0]).numpy()
+    assert flow01.dtype == np.float64 and np.array_equal(n("flow01"), flow01)
+    # flow03 from the float64 depth (the device kernel evaluates depth * ray in float64, geometry.py:39-40): compare with the device's own
+    # float64-depth flow kernel and require that it differs from the float32-depth evaluation somewhere (the old behaviour)
+    f03 = pkg.ops.reproject_flow(depth0, cam)
+    assert torch.equal(res["flow03"], f03)
+    # splats downstream, given the device flows: oracle FW with the reference's dtypes
+    fl12, fl03 = n("flow12"), n("flow03")
+    o, v, c, _, _ = oracle.fw_forward(fl12, n("back_flow01"), n("depth1"))           # ConcatFlow(flow01, back01, flow12, depth1)
+    flow02 = (o.astype(np.float64) + flow01) * v
+    assert n("flow02").dtype == np.float64 and np.array_equal(n("flow02"), flow02)
+    obj = np.concatenate([img[0], d32, (flow02 * -1.0).astype(np.float32), v]).astype(np.float32)
+    o2, v2, c2, _, _ = oracle.fw_forward(obj, flow02, d32)                            # float64 targets
+    vv = v2 * o2[6:7]
+    assert np.array_equal(n("valid2_prime"), vv) and np.array_equal(n("img2_prime"), o2[0:3] * vv)
+    assert np.array_equal(n("back_flow02_prime"), o2[4:6] * vv)
+    o3, v3, _, _, _ = oracle.fw_forward(fl03, flow01, n("depth1"))                    # ConcatFlow(back01, flow01, flow03, depth1)
+    flow13 = (o3 + n("back_flow01")) * v3
+    assert np.array_equal(n("flow13"), flow13)
 
 
 def test_frame_splat_vs_oracle_composition(pkg):
@@ -1083,6 +1188,76 @@ def test_preprocess_plus_augment_writes_the_reference_files(pkg, golden, tmp_pat
     print(f"[preprocess] 121 files, worst differing fraction {worst:.2e}")
 
 
+def _compare_preprocess_files(out, g, pp, label):
+    """121 files of one PreprocessPlusAugment.forward against the golden made by the reference's own forward on the CPU."""
+    want_files = sorted(k[:-6] for k in g if k.endswith("__data"))
+    got_files = sorted(p.name[:-4] for p in out.glob("*.npz"))
+    assert got_files == want_files and len(got_files) == 121
+    worst, exact = 0.0, 0
+    for stem in want_files:
+        z = np.load(out / f"{stem}.npz")
+        want, got = g[f"{stem}__data"], z["img_depth_flow"]
+        assert got.shape == want.shape and got.dtype == want.dtype == np.float32, stem
+        if stem == "group":
+            assert np.array_equal(got[0:8], want[0:8]) and np.array_equal(got[24:28], want[24:28])  # pair 0->1: exact arithmetic
+            frac = float((np.abs(got - want) > 1e-3).mean())
+        else:
+            assert int(z["augment_flow_type"]) == int(g[f"{stem}__type"]), stem
+            gi, k, _ = (int(v) for v in stem.split("_"))
+            t = pp.AUGMENT_TYPES[k]
+            if gi == 0 and t != 2:
+                assert np.array_equal(got, want), stem
+                frac = 0.0
+            elif gi == 0:
+                assert np.allclose(got, want, rtol=1e-5, atol=1e-4), stem
+                frac = 0.0
+            else:
+                frac = float((np.abs(got - want) > 1e-3).mean())
+        exact += int(np.array_equal(got, want))
+        worst = max(worst, frac)
+        assert frac <= 0.03, f"{label} {stem}: {frac:.4f} of the values differ"
+    print(f"[{label}] 121 files, {exact} bit-identical to the reference's CPU run, worst differing fraction {worst:.2e}")
+    return worst, exact
+
+
+@pytest.mark.parametrize("case", ["dropin", "ref_fw"])
+def test_reference_preprocess_runs_unchanged_on_the_dropin_modules(pkg, golden, tmp_path, case):
+    """BASELINE north_star: "preprocess.py and dataloader.py use it unchanged".  The reference's OWN preprocess.py / utils.py /
+    dataloader.py (staged byte for byte in baseline/_ref by build()) run in a fresh interpreter with dropin/ ahead of them on
+    sys.path, on this GPU (tools/run_reference_on_dropin.py); `dropin`: fw_cuda, geometry, bilateral_filter and alt_cuda.fw all
+    resolve to this repository; `ref_fw`: the reference's unmodified alt_cuda/fw.py (torch prologue and all) over dropin/fw_cuda.py.
+    Its PreprocessPlusAugment.forward must write the reference's 121 files: compared with the golden the reference produced on the
+    CPU (make_golden.py) under the same rules as the repo's own driver, and with that driver's files."""
+    import json
+    import subprocess
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    root = Path(__file__).resolve().parent.parent
+    if not (root / "baseline" / "_ref" / "preprocess.py").exists():
+        pytest.skip("baseline/_ref is not staged (build() stages it where /root/reference exists)")
+    out = tmp_path / "ref"
+    r = subprocess.run([sys.executable, str(root / "tools" / "run_reference_on_dropin.py"), "--case", case, "--out", str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["files"] == 121
+    mods = info["modules"]
+    assert "dropin" in mods["fw_cuda"] and "dropin" in mods["geometry"] and "dropin" in mods["bilateral_filter"]
+    assert "baseline/_ref" in mods["utils"] and "baseline/_ref" in mods["dataloader"]
+    assert ("baseline/_ref" in mods["alt_cuda.fw"]) == (case == "ref_fw")
+    g = golden("preprocess_case")
+    _compare_preprocess_files(out, g, pp, f"reference preprocess.py on dropin ({case})")
+    # the repo's own driver on the same frame and seed: same files; how many are bit-identical is reported
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    pkg.synthesis.set_seed(12345 + 3)
+    own = tmp_path / "own"
+    ppa((torch.from_numpy(g["img0"]), torch.from_numpy(g["raw_depth"].copy())[None]), str(own), is_stereo=False)
+    ppa.close()
+    same = sum(int(np.array_equal(np.load(own / p.name)["img_depth_flow"], np.load(p)["img_depth_flow"])) for p in sorted(out.glob("*.npz")))
+    print(f"[dropin {case}] {same}/121 files bit-identical to the repo's own driver")
+    assert same >= 24  # at least everything that depends on pair 0->1 only
+
+
 def test_depth_loaders_arithmetic_on_the_device(pkg):
     """8f-4: ofd_depth_from_png == utils.get_depth(smooth=True) / utils.get_disparity + Convert.disparity_to_depth evaluated
     by numpy / torch in float64 on every 8-bit code and a sample of 16-bit ones (bit-exact), and the float32 output is that
@@ -1161,8 +1336,8 @@ def test_preprocess_float64_dataset_depth_and_stereo_input(pkg, tmp_path):
     o, v, c, _, _ = oracle.fw_forward(obj, flow64, d64.astype(np.float32))
     assert eq(grp["valid1"][0], v) and eq(grp["img1"][0], o[0:3] * v) and eq(grp["back_flow01"][0], o[4:6] * v)
     assert eq(grp["depth1"][0], oflow.fix_warped_depth(torch.from_numpy(o[3:4] * v)).numpy())
-    assert eq(grp["flow01"][0], flow64.astype(np.float32))
-    assert grp["depth0"].dtype == torch.float32 and eq(grp["depth0"][0], d64.astype(np.float32))
+    assert grp["flow01"].dtype == torch.float64 and eq(grp["flow01"][0], flow64)
+    assert grp["depth0"].dtype == torch.float64 and eq(grp["depth0"][0], d64)
     # the same frame with the disparity PNG payload handed over as uint8: decoded on the device, identical group
     codes = np.random.default_rng(1).integers(1, 255, (1, h, w)).astype(np.uint8)
     pkg.synthesis.set_seed(99)
@@ -1342,6 +1517,71 @@ def test_sweep_results_do_not_depend_on_the_partition(pkg, golden):
     sweep.run_sweep([11], lambda i: (g["img0"], g["raw_depth"][None]), DEV, batch=1, dataset_len=0, sink=sink_into(one))
     assert eq(one[11]["img1"], g["group"][4:7]) and eq(one[11]["flow01"], g["group"][24:26])
     _flow_tolerance_check(one[11]["flow12"], g["group"][28:30], *g["group"].shape[1:], "sweep flow12")
+
+
+def test_sweep_sink_scatters_the_group_without_a_device_concatenation(pkg):
+    """PinnedGroupSink: each of the 22 result tensors goes by one strided DMA into its channel slice of the page-locked
+    [B,44,H,W] array (ops.scatter_channels_to_host) == torch.cat of the same tensors; a consumer that keeps the arrays and
+    releases them late (an asynchronous writer) never sees a buffer overwritten by a later batch."""
+    import threading
+
+    from opticalflowfromdepth_b200 import preprocess as pp
+    from opticalflowfromdepth_b200 import sweep
+
+    h, w, n = 48, 64, 10
+    load = lambda i: pkg.synthetic.diml_frame(i, h, w)  # noqa: E731
+    want = {}
+
+    def ref_sink(idx_list, res):
+        stack = torch.cat([res[name].float() for name in pp.GROUP_CHANNELS], 1).cpu().numpy()
+        for k, i in enumerate(idx_list):
+            want[i] = stack[k]
+
+    sweep.run_sweep(range(n), load, DEV, batch=3, dataset_len=n, sink=ref_sink)
+    held, lock = [], threading.Lock()
+
+    def on_batch(idx_list, arr, release):
+        assert arr.shape == (len(idx_list), 44, h, w) and arr.dtype == np.float32
+        with lock:
+            held.append((list(idx_list), arr, release))   # keep the VIEW, release nothing yet
+
+    sink = sweep.PinnedGroupSink(on_batch)
+    sweep.run_sweep(range(n), load, DEV, batch=3, dataset_len=n, sink=sink)
+    assert sink.frames == n and sink.bytes == n * 44 * h * w * 4
+    assert sum(len(i) for i, _, _ in held) == n
+    for idx_list, arr, release in held:          # all four batches still intact although nothing was released
+        for k, i in enumerate(idx_list):
+            assert np.array_equal(arr[k], want[i]), i
+    assert sink.buffers_allocated == len(held)   # a held buffer is never recycled
+    for _, _, release in held:
+        release()
+        release()                                # idempotent
+    before = sink.buffers_allocated
+    sweep.run_sweep(range(3), load, DEV, batch=3, dataset_len=n, sink=sink)
+    assert sink.buffers_allocated == before      # released buffers are reused
+    with pytest.raises(ValueError):
+        pkg.ops.scatter_channels_to_host(torch.zeros(2, 3, h, w, device=DEV), torch.zeros(2, 4, h, w), 2)  # channels 2..5 of 4
+
+
+def test_bench_cfg5_legs_small(pkg):
+    """bench.py's cfg5 legs at reduced sizes: group_480x640 (device-resident 5-pair groups with a roofline fraction and reduced
+    counters) and cfg5_sweep_e2e (host frames -> pinned 44-channel group arrays)."""
+    import json
+    import subprocess
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "3", "--warmup", "3", "--frames", "16", "--group-frames", "8",
+                        "--group-total", "32", "--sweep-frames", "48", "--no-cpu", "--skip", "general,sixdof,bilateral,augment,ref,e2e,compact"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    g = d["group_480x640"]
+    assert "error" not in g, g
+    assert g["frames_per_rank"] >= 32 and g["algorithmic_bytes_per_px"] == 388 and 0 < g["frac_of_measured_peak"] < 1.0
+    assert g["counters"]["pairs"] == 5 * g["counters"]["frames"]
+    sw = d["cfg5_sweep_e2e"]
+    assert "error" not in sw, sw
+    assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == 44 * 480 * 640 * 4 and sw["counters"]["frames"] == 48
 
 
 def test_bench_default_arm_prints_the_contract_line():
