@@ -38,6 +38,7 @@ struct ofd_pair_pipeline {
     size_t h_mask_cap;
     std::vector<cudaEvent_t> ev;  // one per chunk of a run: "this chunk's mask bytes have landed"
     bool mask_bytes_enabled;
+    bool spin_sync;  // OFD_HOST_SYNC=spin: wait with cudaStreamSynchronize / spinning events instead of blocking-sync events
     // Host threads of the pipeline (OFD_HOST_WORKERS, read when the pipeline is created): started once, they sleep on a
     // condition variable between runs and between chunks - no thread creation and no spinning on the timed path.  They
     // inherit the CPU affinity of the thread that created the pipeline (sweep.bind_rank_cores pins a rank to its own cores).
@@ -236,12 +237,17 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     // the knobs are read per pipeline (not once per process): a caller can build pipelines with different settings
     p->n_workers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
     p->mask_bytes_enabled = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
+    {
+        const char* e = getenv("OFD_HOST_SYNC");
+        p->spin_sync = e && (e[0] == 's' || e[0] == 'S');
+    }
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s)
         p->st[s] = nullptr, p->done[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
         cudaError_t e = cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[s], cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&p->done[s], cudaEventDisableTiming | (p->spin_sync ? 0u : (unsigned)cudaEventBlockingSync));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_in[s], n * 4 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_out[s], n * 10 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_s[s], n * sizeof(float));
@@ -293,7 +299,7 @@ int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, co
         }
         while ((int)p->ev.size() < K) {
             cudaEvent_t e;
-            OFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+            OFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (p->spin_sync ? 0u : (unsigned)cudaEventBlockingSync)));
             p->ev.push_back(e);
         }
     }

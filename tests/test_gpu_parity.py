@@ -7,6 +7,7 @@ Bars (BASELINE.json north_star): winner/index map, valid (hole mask) and collisi
 targets that differ reported.
 """
 import sys
+from pathlib import Path
 
 import numpy as np
 import pytest
