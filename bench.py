@@ -204,7 +204,8 @@ def run_ours(args):
     if world > 1:
         # stdout carries the one JSON line, so NCCL's log (version banner, "comm ... nranks N" init lines) goes to a per-rank file
         # and is replayed to stderr at the end - not silenced
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+        # (unconditionally: the level may come from /etc/nccl.conf rather than the environment)
+        if not os.environ.get("NCCL_DEBUG_FILE"):
             nccl_log = f"/tmp/ofd_nccl_{os.getpid()}_r{rank}.log"
             os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)

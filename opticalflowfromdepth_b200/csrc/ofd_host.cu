@@ -38,7 +38,7 @@ struct ofd_pair_pipeline {
     size_t h_mask_cap;
     std::vector<cudaEvent_t> ev;  // one per chunk of a run: "this chunk's mask bytes have landed"
     bool mask_bytes_enabled;
-    bool spin_sync;  // OFD_HOST_SYNC=spin: wait with cudaStreamSynchronize / spinning events instead of blocking-sync events
+    bool spin_sync;  // default: spinning event waits; OFD_HOST_SYNC=block uses blocking-sync events (sleeping waits, ~4 % slower)
     // Host threads of the pipeline (OFD_HOST_WORKERS, read when the pipeline is created): started once, they sleep on a
     // condition variable between runs and between chunks - no thread creation and no spinning on the timed path.  They
     // inherit the CPU affinity of the thread that created the pipeline (sweep.bind_rank_cores pins a rank to its own cores).
@@ -238,8 +238,9 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     p->n_workers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
     p->mask_bytes_enabled = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
     {
+        // measured on B200 boxes (profiles/r2/tune_e2e.txt): spinning waits 6.35 k pairs/s, blocking-sync events 6.12 k
         const char* e = getenv("OFD_HOST_SYNC");
-        p->spin_sync = e && (e[0] == 's' || e[0] == 'S');
+        p->spin_sync = !(e && (e[0] == 'b' || e[0] == 'B'));
     }
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s)

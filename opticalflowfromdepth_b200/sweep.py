@@ -178,51 +178,60 @@ def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device
     camera pose are drawn in the reference's order, so a frame's result does not depend on batch size, shard or rank.
     sink(idx_list, results_dict) receives each batch's device tensors (e.g. to stage them to pinned host memory).
     Returns the counter block (frames, pairs, hit/hole/collision/dropped/tie pixel counts) of this rank."""
-    from . import geometry, ops, synthesis
+    from . import ops, synthesis
 
     dev = torch.device(device)
     if counters is None:
         counters = ops.new_counters(dev)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
     stage = {}  # page-locked staging of the input batch: frames are copied in once, the H2D copy is asynchronous
-    for idx_list in batches(indices, batch):
-        frames = [load_frame(i) for i in idx_list]
-        n = len(frames)
-        key = (frames[0][0].shape, frames[0][0].dtype, frames[0][1].shape, frames[0][1].dtype)
-        if stage.get("key") != key or stage["img"][0].shape[0] < n:
-            stage = {"key": key, "flip": 0,
-                     "img": [torch.empty((max(batch, n),) + frames[0][0].shape, dtype=torch.from_numpy(frames[0][0]).dtype, pin_memory=True) for _ in range(2)],
-                     "raw": [torch.empty((max(batch, n),) + frames[0][1].shape, dtype=torch.from_numpy(frames[0][1]).dtype, pin_memory=True) for _ in range(2)],
-                     "ev": [None, None]}
-        slot = stage["flip"]
-        stage["flip"] ^= 1
-        if stage["ev"][slot] is not None:
-            stage["ev"][slot].synchronize()  # the previous H2D copy out of this staging slot has finished
-        h_img, h_raw = stage["img"][slot], stage["raw"][slot]
-        for k, f in enumerate(frames):
-            h_img[k].copy_(torch.from_numpy(f[0]))
-            h_raw[k].copy_(torch.from_numpy(f[1]))
-        img = h_img[:n].to(dev, non_blocking=True)
-        raw = h_raw[:n].to(dev, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        stage["ev"][slot] = ev
-        h, w = img.shape[-2:]
-        K, inv_K = synthesis.Plausible.K((h, w))
-        s_vals, cams = [], []
-        for i in idx_list:
-            synthesis.set_seed(frame_seed(i, epoch, dataset_len))
-            s_vals.append(float(synthesis.Convert.disparity_scale()))          # preprocess.py:356 (first draw)
-            T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)  # :372 -> :277
-            cams.append(geometry.camera_constants(K, inv_K, T1))
-        sBf = torch.tensor(s_vals, dtype=torch.float32, device=dev)
-        cam = torch.cat(cams).to(dev)
-        with torch.cuda.device(dev):
-            depth = ops.normalize_depth(raw)                                    # :355
-        res = synthesis.synthesize_group(img, depth, sBf, cam, inpaint=inpaint, counters=counters)
-        counters[_lib.CNT_FRAMES] += len(idx_list)
-        counters[_lib.CNT_PAIRS] += 5 * len(idx_list)
-        if sink is not None:
-            sink(idx_list, res)
+    # the staging copies (5 MB per frame) run on a few threads (torch's copy_ releases the GIL); under torchrun every rank is
+    # confined to its own core slice (bind_rank_cores), so the pool never exceeds it
+    copiers = ThreadPoolExecutor(max_workers=max(1, min(4, len(os.sched_getaffinity(0)))))
+    try:
+        for idx_list in batches(indices, batch):
+            frames = [load_frame(i) for i in idx_list]
+            n = len(frames)
+            key = (frames[0][0].shape, frames[0][0].dtype, frames[0][1].shape, frames[0][1].dtype)
+            if stage.get("key") != key or stage["img"][0].shape[0] < n:
+                stage = {"key": key, "flip": 0,
+                         "img": [torch.empty((max(batch, n),) + frames[0][0].shape, dtype=torch.from_numpy(frames[0][0]).dtype, pin_memory=True) for _ in range(2)],
+                         "raw": [torch.empty((max(batch, n),) + frames[0][1].shape, dtype=torch.from_numpy(frames[0][1]).dtype, pin_memory=True) for _ in range(2)],
+                         "ev": [None, None]}
+            slot = stage["flip"]
+            stage["flip"] ^= 1
+            if stage["ev"][slot] is not None:
+                stage["ev"][slot].synchronize()  # the previous H2D copy out of this staging slot has finished
+            h_img, h_raw = stage["img"][slot], stage["raw"][slot]
+
+            def put(k, h_img=h_img, h_raw=h_raw, frames=frames):
+                h_img[k].copy_(torch.from_numpy(frames[k][0]))
+                h_raw[k].copy_(torch.from_numpy(frames[k][1]))
+
+            pending = [copiers.submit(put, k) for k in range(n)]
+            # while the copies run: this batch's random draws, in the reference's per-frame order (preprocess.py:555,356,372)
+            h, w = frames[0][0].shape[-2:]
+            s_host, cam_host, _ = synthesis.frame_draws_batch([frame_seed(i, epoch, dataset_len) for i in idx_list], (h, w))
+            for f in pending:
+                f.result()
+            img = h_img[:n].to(dev, non_blocking=True)
+            raw = h_raw[:n].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            stage["ev"][slot] = ev
+            sBf = s_host.to(dev)
+            cam = cam_host.to(dev)
+            with torch.cuda.device(dev):
+                depth = ops.normalize_depth(raw)                                    # :355
+            res = synthesis.synthesize_group(img, depth, sBf, cam, inpaint=inpaint, counters=counters)
+            counters[_lib.CNT_FRAMES] += len(idx_list)
+            counters[_lib.CNT_PAIRS] += 5 * len(idx_list)
+            if sink is not None:
+                sink(idx_list, res)
+    finally:
+        copiers.shutdown(wait=True)
     if sink is not None and hasattr(sink, "flush"):
         sink.flush()
     return counters

@@ -21,7 +21,7 @@ from . import geometry, ops
 from .fw import FW
 
 __all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "augment_pairs_f64", "sample_special_params",
-           "photometric_draws", "photometric_apply",
+           "photometric_draws", "photometric_apply", "frame_draws_batch",
            "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
 
 
@@ -128,6 +128,40 @@ class Plausible:
         else:
             T = geometry.transformation_from_parameters(axisangle, translation)
         return T, axisangle, translation
+
+
+def frame_draws_batch(seeds, size):
+    """The first random draws of PreprocessPlusAugment.forward for a batch of independently seeded frames (preprocess.py:555,
+    356, 372 -> 277): per frame, after set_seed(seed), one disparity scale (Convert.disparity_scale) and one camera pose
+    (Plausible.random_motion(1/36, 1/36, 0.1, 0.1)), packed for the kernels as (sBf[n] float32, cam[n,21] float32, T1[n,4,4]).
+
+    Bit-identical to the per-frame calls (tests/test_host_logic_cpu.py::test_frame_draws_batch_equals_per_frame_draws) at a
+    tenth of their host time: the 13 draws of a frame come from a private torch.Generator seeded like the global one (same
+    mt19937 stream: rand, then 6 x (randint, rand) as utils.get_random orders them, utils.py:96-100), and the float32 arithmetic
+    that turns them into scale, axis-angle, translation, Rodrigues rotation and (K T)[:3] runs ONCE per batch on [n,...] tensors
+    (the same elementwise torch ops, so the same roundings)."""
+    h, w = size
+    n = len(seeds)
+    gen = torch.Generator()
+    rows_u, rows_s = [], []
+    for seed in seeds:
+        gen.manual_seed(int(seed))
+        u = [torch.rand(1, generator=gen).item()]
+        sg = []
+        for _ in range(6):
+            sg.append(torch.randint(0, 2, (1,), generator=gen).item() * 2 - 1)
+            u.append(torch.rand(1, generator=gen).item())
+        rows_u.append(u)
+        rows_s.append(sg)
+    u = torch.tensor(rows_u, dtype=torch.float32).reshape(n, 7)
+    sg = torch.tensor(rows_s, dtype=torch.int64).reshape(n, 6)
+    sBf = (u[:, 0] * 0.3 + torch.tensor(0.8)) * Plausible.B() * Plausible.f()
+    ang = sg[:, 0:3] * (u[:, 1:4] * (math.pi * (1. / 36.)) + torch.tensor(math.pi * (1. / 36.)))
+    tr = sg[:, 3:6] * (u[:, 4:7] * 0.1 + torch.tensor(0.1))
+    T1 = geometry.transformation_from_parameters(ang[:, None, :].contiguous(), tr[:, None, :].contiguous())
+    K, inv_K = Plausible.K((h, w))
+    cam = geometry.camera_constants(K.expand(n, 4, 4), inv_K.expand(n, 4, 4), T1)
+    return sBf.to(torch.float32).contiguous(), cam, T1
 
 
 # ---- preprocess.py:237-298 -------------------------------------------------------------------------------------

@@ -6,9 +6,10 @@
  *
  * Parity status: the reference has no tests, golden vectors or fixtures for this path, so
  * this oracle is pinned against (a) the reference's own Python (alt_cuda/fw.py prologue, preprocess.py Convert,
- * geometry.py, bilateral_filter.py) imported in the build container by tests/golden/make_golden.py, and (b) the
- * reference's own CUDA kernel compiled unmodified from /root/reference/alt_cuda into oracle/_ref/ and run on the
- * B200 by tests/test_gpu_reference_kernel.py.
+ * geometry.py, bilateral_filter.py) imported in the build container by tests/golden/make_golden.py (small cases, arrays
+ * committed) and tests/golden/make_golden_fullsize.py (480x640 / 368x496 / ReDWeb / 1080p, SHA-256 digests committed), and
+ * (b) the reference's own CUDA kernel compiled unmodified from /root/reference/alt_cuda into oracle/_ref/ and run on the
+ * B200 by tests/test_gpu_parity.py::test_against_the_reference_kernel_itself.
  *
  * Each function cites the reference lines it restates.
  */

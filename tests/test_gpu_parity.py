@@ -244,6 +244,30 @@ def test_against_the_reference_kernel_itself(pkg):
     assert torch.equal(o2, r_out) and torch.equal(v2, r_valid) and torch.equal(c2, r_coll)
 
 
+@pytest.mark.parametrize("h,w,C", [(480, 640, 6), (368, 496, 4), (632, 558, 2), (1080, 1920, 7)])
+def test_against_the_reference_fw_forward_at_baseline_sizes(pkg, h, w, C):
+    """The reference's OWN forward-warp call at the BASELINE sizes: its FW.forward (alt_cuda/fw.py, staged unmodified in
+    baseline/_ref - CPU meshgrid, H2D, torch prologue) over its own kernel (fw_cuda_kernel.cu compiled unmodified, oracle/_ref),
+    against this repo's FW.forward on the same 6-DoF flow: output, valid (hole mask) and collision bit-exact.  The reference
+    kernel is serial (one block of C threads): 0.1 s at 480x640, 0.8 s at 1080p."""
+    try:
+        RefFW = oracle.load_ref_fw_class()
+    except (FileNotFoundError, ImportError, OSError) as e:
+        pytest.skip(f"reference FW unavailable: {e}")
+    from opticalflowfromdepth_b200.fw import FW
+
+    img, depth = _cfg1_inputs(pkg, 1, h, w)
+    flow, _ = _six_dof_flow(pkg, depth, 11 + C)
+    vin = (torch.rand(1, 1, h, w, device=DEV) > 0.1).float()
+    obj = {2: flow, 4: torch.cat((img, depth), 1), 6: torch.cat((img, depth, flow * -1.0), 1),
+           7: torch.cat((img, depth, flow * -1.0, vin), 1)}[C][0].contiguous()
+    r_out, r_valid, r_coll = RefFW(device=DEV)(obj, flow[0], depth[0])
+    torch.cuda.synchronize()
+    out, valid, coll = FW(DEV)(obj, flow[0], depth[0])
+    assert torch.equal(out, r_out) and torch.equal(valid, r_valid) and torch.equal(coll, r_coll)
+    assert 0.3 < float(r_valid.mean()) < 1.0 and out.shape == (C, h, w)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # fused virtual-stereo pair
 # ---------------------------------------------------------------------------------------------------------------
@@ -1583,6 +1607,25 @@ def test_bench_cfg5_legs_small(pkg):
     sw = d["cfg5_sweep_e2e"]
     assert "error" not in sw, sw
     assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == 44 * 480 * 640 * 4 and sw["counters"]["frames"] == 48
+
+
+@pytest.mark.parametrize("tag", ["cfg1_480x640", "cfg4_368x496", "cfg2_redweb", "cfg3_1080p"])
+def test_full_size_planes_match_the_reference_digests(pkg, tag):
+    """Parity pinned at the BASELINE sizes by the REFERENCE: tests/golden/make_golden_fullsize.py ran the
+    reference's own Python at 480x640 / 368x496 / a ReDWeb size / 1080p and committed the SHA-256 of every plane that must be
+    bit-exact plus its sampled 6-DoF flow; here the CUDA path regenerates the seeded inputs and must hash to the same digests
+    (normalize_depth, disparity flow, FW.forward out / valid / collision / winner map, fused pair, C=7 splat + hole mask, ConcatFlow,
+    BackFlow, 5-iteration bilateral), with the 6-DoF flow inside 1e-5 * max(|p1|, W-1)."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import parity_fullsize as pf
+
+    want, flows = pf.load_fixtures()
+    r = pf.run_case(tag, want[tag], flows, DEV)
+    bad = [k for k, v in r["checks"].items() if not v]
+    print(f"[fullsize {tag}] {len(r['checks'])} checks; " + ", ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in r["numbers"].items()))
+    assert not bad, f"{tag}: planes that differ from the reference's digests: {bad}"
+    assert len(r["checks"]) >= 15 or not r["numbers"]["reference_flow12_reproduced_on_this_cpu"]
+    assert r["numbers"]["flow12_truncated_target_mismatch_fraction"] <= 1e-3
 
 
 def test_bench_default_arm_prints_the_contract_line():

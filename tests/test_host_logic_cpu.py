@@ -329,3 +329,27 @@ def test_bind_rank_cores_sets_and_restores_affinity():
         assert set(sweep.bind_rank_cores(0, 2)) == before
     finally:
         del os.environ["OFD_NO_AFFINITY"]
+
+
+def test_frame_draws_batch_equals_per_frame_draws():
+    """synthesis.frame_draws_batch (the sweep's host path: 13 generator draws per frame from a private generator + one batched
+    evaluation of scale / Rodrigues pose / (K T)[:3]) is bit-identical to set_seed + Convert.disparity_scale + Plausible.random_motion
+    + camera_constants per frame, for every batch size (so sweep results do not depend on the batching)."""
+    from opticalflowfromdepth_b200 import geometry, synthesis
+
+    size = (480, 640)
+    K, inv_K = synthesis.Plausible.K(size)
+    seeds = list(range(12345, 12345 + 40)) + [0, 1, 2**31 - 1, 99991]
+    want = []
+    for s in seeds:
+        synthesis.set_seed(s)
+        sc = torch.as_tensor(synthesis.Convert.disparity_scale(), dtype=torch.float32)
+        T1, _, _ = synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)
+        want.append((sc, geometry.camera_constants(K, inv_K, T1)[0], T1[0]))
+    for bs in (1, 3, 16, len(seeds)):
+        for k in range(0, len(seeds), bs):
+            sBf, cam, T = synthesis.frame_draws_batch(seeds[k:k + bs], size)
+            assert sBf.dtype == cam.dtype == torch.float32 and cam.shape == (len(seeds[k:k + bs]), 21)
+            for j in range(sBf.shape[0]):
+                w = want[k + j]
+                assert torch.equal(sBf[j], w[0]) and torch.equal(cam[j], w[1]) and torch.equal(T[j], w[2]), (bs, k + j)

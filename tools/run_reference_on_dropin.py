@@ -75,7 +75,13 @@ def main():
     exec(compile("\n".join(src), pp.__file__, "exec"), pp.__dict__)
     pp.device = args.device
 
-    where = {name: getattr(sys.modules[name], "__file__", "?") for name in ("fw_cuda", "geometry", "bilateral_filter", "alt_cuda.fw", "utils", "dataloader")}
+    def origin(name):  # where the reference's `import <name>` resolves in this interpreter
+        if name in sys.modules:
+            return getattr(sys.modules[name], "__file__", "?")
+        spec = importlib.util.find_spec(name)
+        return spec.origin if spec else None
+
+    where = {name: origin(name) for name in ("fw_cuda", "geometry", "bilateral_filter", "alt_cuda.fw", "utils", "dataloader")}
     g = np.load(ROOT / "tests" / "golden" / f"{args.golden}.npz")
     img0, raw = torch.from_numpy(g["img0"]), torch.from_numpy(g["raw_depth"].copy())[None]
     out = Path(args.out)
