@@ -326,6 +326,20 @@ int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, co
                                 float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/,
                                 unsigned flags);
 /*
+ * ofd_inpaint_telea — the fill of utils.inpaint (utils.py:136-151: cv2.inpaint(img_u8, mask, 3, cv2.INPAINT_TELEA) on the host, 95
+ * calls per frame in preprocess.py) on the device, for a batch: img[B,3,H,W] float32 (truncated to uint8 like .astype(np.uint8),
+ * utils.py:147), mask[B,1,H,W] uint8 (!= 0 = fill; ofd_inpaint_mask produces it), range = inpaint radius (the reference uses 3)
+ * -> out[B,3,H,W] float32 (uint8-valued).  Telea's fast-marching method with OpenCV's per-pixel arithmetic, marched in LAYERS
+ * (all hole pixels with a 4-neighbour in earlier layers at once) instead of OpenCV's serial heap order: not bit-identical to
+ * cv2.inpaint by construction - tests state and measure the difference (fraction of bytes off by more than one grey level).
+ * One cooperative kernel; `ws` holds ofd_inpaint_workspace_bytes(B,H,W) bytes (256-byte aligned, no initialisation needed).
+ * stats_host (optional, HOST pointer to 2 x uint32): layers marched and pixels filled; passing it synchronises the stream.
+ */
+size_t ofd_inpaint_workspace_bytes(int B, int H, int W);
+int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W, int range, float* out, void* ws,
+                      size_t ws_bytes, uint32_t* stats_host, ofd_stream_t stream);
+
+/*
  * ofd_copy_rows_to_host — device -> host copy of `rows` rows of `width_bytes` with independent pitches (one asynchronous
  * cudaMemcpy2DAsync on `stream`).  The sweep uses it to scatter each result tensor [B,c,H,W] of a frame group straight into
  * its channel slice of the page-locked [B,44,H,W] group array (preprocess.py:437-447 layout): rows = B, width = c*H*W*4,

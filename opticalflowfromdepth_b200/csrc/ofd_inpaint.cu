@@ -1,0 +1,351 @@
+// ofd_inpaint.cu — Telea fast-marching inpainting on the GPU: the fill of utils.inpaint (utils.py:136-151), which the reference
+// hands to OpenCV on the host (cv2.inpaint(img_u8, mask, 3, cv2.INPAINT_TELEA)) 95 times per frame.
+//
+// OpenCV's algorithm (the published one: A. Telea, "An image inpainting technique based on the fast marching method", 2004, as
+// implemented in opencv/modules/photo/src/inpaint.cpp, which is NOT part of /root/reference - third-party, unpinned, restated from
+// its published form):
+//   1. the hole's 4-neighbour ring ("band") gets T = 0; a fast-marching pass over the known pixels within `range` of the hole gives
+//      them T = -distance; hole pixels get T = +distance when they are reached;
+//   2. hole pixels are filled in order of increasing T (a heap): a pixel is computed when the first of its 4-neighbours is popped -
+//      its T from the upwind quadrant solve, its colour as the weighted mean of the already known pixels within `range`
+//      (weights: direction x distance x level-set factors) plus a gradient term - and is then known to every later pixel.
+// The heap makes this inherently serial.  Here the march advances in LAYERS: layer k holds the hole pixels that have a 4-neighbour in
+// layers < k (layer 0 = known).  All pixels of a layer are computed in parallel from pixels of earlier layers only, with the same
+// per-pixel arithmetic, in the same operand order, as OpenCV's.  For thin disocclusion bands the layer order and the heap order give
+// nearly the same result; deep holes differ more (the fill order inside a ring of equal depth differs).  Bit equality with the
+// heap order is therefore NOT claimed: tests/test_gpu_parity.py measures the fraction of bytes that differ from cv2.inpaint by more
+// than one grey level and states the bound; synthesis.inpaint keeps backend="cv2" selectable.
+//
+// One cooperative kernel per batch: init -> outward ring march (2 * range layers) -> inward layers until no hole pixel is left,
+// each layer in two phases (compute into a staging list; commit + enqueue the next frontier) separated by grid-wide barriers, so
+// that every read of a layer sees the state at the layer's start (deterministic results).
+#include <cooperative_groups.h>
+
+#include "ofd_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ofd {
+
+constexpr float T_FAR = 1.0e6f;         // inpaint.cpp: cvSet(t, 1.0e6f)
+constexpr unsigned short L_INSIDE = 0xFFFFu;
+
+struct TeleaParams {
+    const float* img;          // [B,3,H,W] float32, uint8-valued
+    const unsigned char* mask; // [B,1,H,W], != 0 = fill
+    float* out;                // [B,3,H,W]
+    int B, H, W, range;
+    // workspace (per batch)
+    unsigned char* u8;         // [B,3,H,W] working image
+    unsigned short* L;         // [B,(H+2),(W+2)] layer: 0 known, 0xFFFF unfilled hole, k filled in layer k
+    float* T;                  // [B,(H+2),(W+2)]
+    unsigned char* G;          // [B,(H+2),(W+2)] outward march: 0 other, 1 band, 255 ring (uncomputed), k+1 computed in out-layer k
+    unsigned int* Q;           // [B,(H+2),(W+2)] 1 = already enqueued
+    unsigned int* list[2];     // frontier lists: (b << 24) | extended pixel index ... stored as two words when large
+    unsigned int* listb[2];    // frame index of each entry
+    float* stageT;             // per entry: T
+    uchar4* stageC;            // per entry: colour
+    unsigned int* count;       // [2] list sizes, [2] = layers done, [3] = filled pixels
+};
+
+// inpaint.cpp FastMarching_solve: upwind quadrant solve from the two neighbours (i1,j1), (i2,j2); `known(q)` = f != INSIDE
+__device__ __forceinline__ float fmm_solve(float a11, bool k1, float a22, bool k2) {
+    double sol;
+    const double m12 = a11 < a22 ? (double)a11 : (double)a22;
+    if (k1) {
+        if (k2) {
+            const double d = (double)a11 - (double)a22;
+            if (fabs(d) >= 1.0)
+                sol = 1 + m12;
+            else
+                sol = ((double)a11 + (double)a22 + sqrt(2 - d * d)) * 0.5;
+        } else {
+            sol = 1 + (double)a11;
+        }
+    } else if (k2) {
+        sol = 1 + (double)a22;
+    } else {
+        sol = 1 + m12;
+    }
+    return (float)sol;
+}
+
+__device__ __forceinline__ float min4(float a, float b, float c, float d) { return fminf(fminf(a, b), fminf(c, d)); }
+
+__global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ TeleaParams P) {
+    cg::grid_group grid = cg::this_grid();
+    const int H = P.H, W = P.W, EW = W + 2, EH = H + 2, range = P.range;
+    const size_t hw = (size_t)H * W, ehw = (size_t)EH * EW;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+
+    // ---- phase 0: working image, flags, T, band, ring ------------------------------------------------------------------------------
+    for (size_t e = tid; e < (size_t)P.B * 3 * hw; e += nth) {
+        float v = P.img[e];
+        v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+        P.u8[e] = (unsigned char)(int)v;  // .astype(np.uint8): truncation (utils.py:147)
+    }
+    if (tid < 4) P.count[tid] = 0;
+    for (size_t e = tid; e < (size_t)P.B * ehw; e += nth) {
+        const int b = (int)(e / ehw);
+        const int p = (int)(e - (size_t)b * ehw);
+        const int i = p / EW, j = p - i * EW;  // extended coordinates: interior is 1..H x 1..W
+        const unsigned char* m = P.mask + (size_t)b * hw;
+        auto hole = [&](int ii, int jj) -> bool { return ii >= 1 && ii <= H && jj >= 1 && jj <= W && m[(size_t)(ii - 1) * W + (jj - 1)] != 0; };
+        const bool interior = i >= 1 && i <= H && j >= 1 && j <= W;
+        const bool me = interior && hole(i, j);
+        bool band = false, ring = false;
+        if (interior && !me) {
+            band = hole(i - 1, j) || hole(i + 1, j) || hole(i, j - 1) || hole(i, j + 1);  // 3x3 cross dilation minus the mask
+            if (!band) {
+                for (int di = -range; di <= range && !ring; ++di)
+                    for (int dj = -range; dj <= range; ++dj)
+                        if (hole(i + di, j + dj)) {
+                            ring = true;  // (2 range + 1)^2 rectangle dilation minus mask minus band
+                            break;
+                        }
+            }
+        }
+        P.L[e] = me ? L_INSIDE : 0;
+        P.T[e] = band ? 0.0f : T_FAR;
+        P.G[e] = band ? 1 : (ring ? 255 : 0);
+        P.Q[e] = 0;
+    }
+    grid.sync();
+
+    // ---- phase 1: outward march over the ring (icvCalcFMM(out, t, Out, negate = true)) -------------------------------------------------
+    // out-layer k: ring pixels with a 4-neighbour popped earlier (band = layer 0).  In that pass every non-ring pixel counts as known
+    // with its current T (band 0, everything else 1e6), exactly as the flags of OpenCV's `out` matrix say.
+    for (int k = 1; k <= 2 * range; ++k) {
+        for (size_t e = tid; e < (size_t)P.B * ehw; e += nth) {
+            if (P.G[e] != 255) continue;
+            const int b = (int)(e / ehw);
+            const int p = (int)(e - (size_t)b * ehw);
+            const unsigned char* G = P.G + (size_t)b * ehw;
+            const float* T = P.T + (size_t)b * ehw;
+            auto popped = [&](int q) -> bool { const unsigned char g = G[q]; return g >= 1 && g <= k; };
+            if (!(popped(p - EW) || popped(p + EW) || popped(p - 1) || popped(p + 1))) continue;
+            auto known = [&](int q) -> bool { return G[q] <= k; };  // 0 (not ring), band, or computed in an earlier out-layer
+            const int up = p - EW, dn = p + EW, lf = p - 1, rt = p + 1;
+            const float d = min4(fmm_solve(T[up], known(up), T[lf], known(lf)), fmm_solve(T[dn], known(dn), T[lf], known(lf)),
+                                 fmm_solve(T[up], known(up), T[rt], known(rt)), fmm_solve(T[dn], known(dn), T[rt], known(rt)));
+            P.stageT[e] = d;  // staged: committed after the barrier (reads of this layer see the layer's start state)
+            P.Q[e] = 2;
+        }
+        grid.sync();
+        for (size_t e = tid; e < (size_t)P.B * ehw; e += nth)
+            if (P.Q[e] == 2) {
+                P.T[e] = P.stageT[e];
+                P.G[e] = (unsigned char)(k + 1);
+                P.Q[e] = 0;
+            }
+        grid.sync();
+    }
+    // negate the ring distances; build the first frontier: hole pixels with an interior known 4-neighbour
+    for (size_t e = tid; e < (size_t)P.B * ehw; e += nth) {
+        const unsigned char g = P.G[e];
+        if (g >= 2 && g != 255) P.T[e] = -P.T[e];
+        if (P.L[e] == L_INSIDE) {
+            const int b = (int)(e / ehw);
+            const int p = (int)(e - (size_t)b * ehw);
+            const unsigned short* L = P.L + (size_t)b * ehw;
+            auto trig = [&](int q) -> bool {
+                const int qi = q / EW, qj = q - qi * EW;
+                return L[q] == 0 && qi >= 1 && qi <= H && qj >= 1 && qj <= W;
+            };
+            if (trig(p - EW) || trig(p + EW) || trig(p - 1) || trig(p + 1)) {
+                const unsigned int slot = atomicAdd(&P.count[0], 1u);
+                P.list[0][slot] = (unsigned int)p;
+                P.listb[0][slot] = (unsigned int)b;
+                P.Q[e] = 1;
+            }
+        }
+    }
+    grid.sync();
+
+    // ---- phase 2: inward layers (icvTeleaInpaintFMM) -------------------------------------------------------------------------------------
+    int cur = 0;
+    for (unsigned int layer = 1; layer < L_INSIDE; ++layer) {
+        const unsigned int n = P.count[cur];
+        if (n == 0) break;
+        // (a) compute T and colour of every frontier pixel from pixels of earlier layers
+        if (tid == 0) P.count[cur ^ 1] = 0;  // nobody reads the other list's counter during this layer; ordered by the barrier below
+        for (size_t e = tid; e < n; e += nth) {
+            const int b = (int)P.listb[cur][e];
+            const int p = (int)P.list[cur][e];
+            const int i = p / EW, j = p - i * EW;
+            const unsigned short* L = P.L + (size_t)b * ehw;
+            const float* T = P.T + (size_t)b * ehw;
+            const unsigned char* I = P.u8 + (size_t)b * 3 * hw;
+            auto known = [&](int q) -> bool { return L[q] < layer; };  // f != INSIDE
+            const int up = p - EW, dn = p + EW, lf = p - 1, rt = p + 1;
+            const float dist = min4(fmm_solve(T[up], known(up), T[lf], known(lf)), fmm_solve(T[dn], known(dn), T[lf], known(lf)),
+                                    fmm_solve(T[up], known(up), T[rt], known(rt)), fmm_solve(T[dn], known(dn), T[rt], known(rt)));
+            // gradT (t(i,j) is the value just computed)
+            float gx, gy;
+            if (known(rt))
+                gx = known(lf) ? (T[rt] - T[lf]) * 0.5f : (T[rt] - dist);
+            else
+                gx = known(lf) ? (dist - T[lf]) : 0.0f;
+            if (known(dn))
+                gy = known(up) ? (T[dn] - T[up]) * 0.5f : (T[dn] - dist);
+            else
+                gy = known(up) ? (dist - T[up]) : 0.0f;
+            float Ia[3] = {0.f, 0.f, 0.f}, Jx[3] = {0.f, 0.f, 0.f}, Jy[3] = {0.f, 0.f, 0.f}, s[3] = {1.0e-20f, 1.0e-20f, 1.0e-20f};
+            for (int k = i - range; k <= i + range; ++k) {
+                if (k <= 0 || k >= EH - 1) continue;
+                const int km = k - 1 + (k == 1), kp = k - 1 - (k == EH - 2);
+                for (int l = j - range; l <= j + range; ++l) {
+                    if (l <= 0 || l >= EW - 1) continue;
+                    const int q = k * EW + l;
+                    if (!known(q) || (l - j) * (l - j) + (k - i) * (k - i) > range * range) continue;
+                    const int lm = l - 1 + (l == 1), lp = l - 1 - (l == EW - 2);
+                    const float ry = (float)(i - k), rx = (float)(j - l);
+                    const float len2 = rx * rx + ry * ry;
+                    const float dst = (float)(1. / ((double)len2 * sqrt((double)len2)));
+                    const float lev = (float)(1. / (1 + fabs((double)(T[q] - dist))));
+                    float dir = rx * gx + ry * gy;
+                    if (fabsf(dir) <= 0.01f) dir = 0.000001f;
+                    const float w = fabsf(dst * lev * dir);
+                    const bool kr = known(q + 1), kl = known(q - 1), kd = known(q + EW), ku = known(q - EW);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned char* Ic = I + (size_t)c * hw;
+                        // (row / column clamps only matter for frames with H < 2 or W < 2, where inpaint.cpp's km / lm shifts leave the image)
+                        auto px = [&](int r, int col) -> float {
+                            r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
+                            col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+                            return (float)Ic[(size_t)r * W + col];
+                        };
+                        float gix, giy;
+                        if (kr)
+                            gix = kl ? (px(km, lp + 1) - px(km, lm - 1)) * 2.0f : (px(km, lp + 1) - px(km, lm));
+                        else
+                            gix = kl ? (px(km, lp) - px(km, lm - 1)) : 0.0f;
+                        if (kd)
+                            giy = ku ? (px(kp + 1, lm) - px(km - 1, lm)) * 2.0f : (px(kp + 1, lm) - px(km, lm));
+                        else
+                            giy = ku ? (px(kp, lm) - px(km - 1, lm)) : 0.0f;
+                        Ia[c] += w * px(k - 1, l - 1);  // the tap's own pixel; the km / lm shifts apply to the gradients only
+                        Jx[c] -= w * (gix * rx);
+                        Jy[c] -= w * (giy * ry);
+                        s[c] += w;
+                    }
+                }
+            }
+            uchar4 col;
+            unsigned char* cp = reinterpret_cast<unsigned char*>(&col);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sat = (float)(Ia[c] / s[c] + (Jx[c] + Jy[c]) / (sqrtf(Jx[c] * Jx[c] + Jy[c] * Jy[c]) + 1.0e-20f) + 0.5f);
+                int v = __float2int_rn(sat);  // saturate_cast<uchar>(float): round to nearest even, saturate
+                if (!(sat == sat)) v = 0;
+                cp[c] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+            cp[3] = 0;
+            P.stageT[e] = dist;
+            P.stageC[e] = col;
+        }
+        grid.sync();
+        // (b) commit the layer and enqueue its unfilled 4-neighbours for the next one
+        for (size_t e = tid; e < n; e += nth) {
+            const int b = (int)P.listb[cur][e];
+            const int p = (int)P.list[cur][e];
+            const int i = p / EW, j = p - i * EW;
+            const size_t eb = (size_t)b * ehw;
+            P.T[eb + p] = P.stageT[e];
+            P.L[eb + p] = (unsigned short)layer;
+            const uchar4 col = P.stageC[e];
+            unsigned char* I = P.u8 + (size_t)b * 3 * hw + (size_t)(i - 1) * W + (j - 1);
+            I[0] = col.x, I[hw] = col.y, I[2 * hw] = col.z;
+            const int nb[4] = {p - EW, p - 1, p + EW, p + 1};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int q = nb[t];
+                const int qi = q / EW, qj = q - qi * EW;
+                if (qi <= 0 || qj <= 0 || qi > EH - 1 || qj > EW - 1) continue;  // inpaint.cpp: (i<=0)||(j<=0)||(i>rows-1)||(j>cols-1)
+                if (P.L[eb + q] == L_INSIDE && atomicExch(&P.Q[eb + q], 1u) == 0u) {
+                    const unsigned int slot = atomicAdd(&P.count[cur ^ 1], 1u);
+                    P.list[cur ^ 1][slot] = (unsigned int)q;
+                    P.listb[cur ^ 1][slot] = (unsigned int)b;
+                }
+            }
+        }
+        if (tid == 0) P.count[2] = layer, atomicAdd(&P.count[3], n);
+        grid.sync();
+        cur ^= 1;
+    }
+    // ---- result ------------------------------------------------------------------------------------------------------------------------------
+    for (size_t e = tid; e < (size_t)P.B * 3 * hw; e += nth) P.out[e] = (float)P.u8[e];
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+}  // namespace ofd
+
+using namespace ofd;
+
+extern "C" {
+
+size_t ofd_inpaint_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t hw = (size_t)H * W, ehw = (size_t)(H + 2) * (W + 2), nb = (size_t)B;
+    size_t n = 256;
+    n += align256(nb * 3 * hw);                 // u8
+    n += align256(nb * ehw * 2);                // L
+    n += align256(nb * ehw * 4);                // T
+    n += align256(nb * ehw);                    // G
+    n += align256(nb * ehw * 4);                // Q
+    n += 4 * align256(nb * hw * 4);             // list[2], listb[2]
+    n += align256(nb * ehw * 4);                // stageT (also indexed by extended pixel in the ring march)
+    n += align256(nb * hw * 4);                 // stageC
+    return n;
+}
+
+int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W, int range, float* out, void* ws, size_t ws_bytes,
+                      uint32_t* stats_host_or_null, ofd_stream_t stream) {
+    const char* fn = "ofd_inpaint_telea";
+    if (B < 0 || H < 0 || W < 0) return fail(OFD_E_SHAPE, "%s: negative dimension", fn);
+    if (range < 1 || range > 8) return fail(OFD_E_ARG, "%s: range %d outside [1,8]", fn, range);
+    if ((size_t)(H + 2) * (size_t)(W + 2) >= ((size_t)1 << 31)) return fail(OFD_E_SHAPE, "%s: frame too large", fn);
+    if (B == 0 || H == 0 || W == 0) return OFD_OK;
+    if (!img || !mask || !out) return fail(OFD_E_NULL, "%s: NULL tensor pointer", fn);
+    const size_t need = ofd_inpaint_workspace_bytes(B, H, W);
+    if (!ws || ((uintptr_t)ws & 255) || ws_bytes < need)
+        return fail(OFD_E_WORKSPACE, "%s: workspace needs %zu bytes, 256-byte aligned (got %zu)", fn, need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hw = (size_t)H * W, ehw = (size_t)(H + 2) * (W + 2), nb = (size_t)B;
+    unsigned char* w = (unsigned char*)ws;
+    TeleaParams P = {};
+    P.img = img, P.mask = mask, P.out = out, P.B = B, P.H = H, P.W = W, P.range = range;
+    P.count = (unsigned int*)w, w += 256;
+    P.u8 = w, w += align256(nb * 3 * hw);
+    P.L = (unsigned short*)w, w += align256(nb * ehw * 2);
+    P.T = (float*)w, w += align256(nb * ehw * 4);
+    P.G = w, w += align256(nb * ehw);
+    P.Q = (unsigned int*)w, w += align256(nb * ehw * 4);
+    for (int k = 0; k < 2; ++k) P.list[k] = (unsigned int*)w, w += align256(nb * hw * 4);
+    for (int k = 0; k < 2; ++k) P.listb[k] = (unsigned int*)w, w += align256(nb * hw * 4);
+    P.stageT = (float*)w, w += align256(nb * ehw * 4);
+    P.stageC = (uchar4*)w, w += align256(nb * hw * 4);
+    int sms = 0, per_sm = 0;
+    int rc = launch_plan(fn, (const void*)telea_kernel, 256, 0, &sms, &per_sm);
+    if (rc) return rc;
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return fail(OFD_E_ARG, "%s: device does not support cooperative launches", fn);
+    long long blocks = (long long)sms * per_sm;
+    const long long useful = (long long)((nb * ehw + 255) / 256);
+    if (blocks > useful) blocks = useful < 1 ? 1 : useful;
+    void* args[] = {(void*)&P};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)telea_kernel, dim3((unsigned)blocks), dim3(256), args, 0, st);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchCooperativeKernel: %s", fn, cudaGetErrorString(e));
+    if (stats_host_or_null) {  // layers marched / pixels filled: a synchronising read, for tests and reports only
+        e = cudaMemcpyAsync(stats_host_or_null, P.count + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail((int)e, "%s: %s", fn, cudaGetErrorString(e));
+    }
+    return check_launch(fn);
+}
+
+}  // extern "C"

@@ -365,6 +365,32 @@ def inpaint_mask(valid, collision):
     return mask
 
 
+_inpaint_ws = {}
+
+
+@_on_device
+def inpaint_telea(img, mask, radius: int = 3, want_stats: bool = False):
+    """cv2.inpaint(img_u8, mask, radius, cv2.INPAINT_TELEA) of utils.inpaint (utils.py:149) on the device, batched:
+    img[B,3,H,W] float32 CUDA (uint8-valued), mask[B,1,H,W] uint8 (1 = fill) -> float32 [B,3,H,W] (uint8-valued).
+    Layer-ordered fast marching (ofd_inpaint_telea); want_stats also returns (layers, filled pixels) and synchronises."""
+    _check("img", img, dtype=torch.float32)
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError("img must be [B,3,H,W]")
+    B, _, H, W = img.shape
+    _check("mask", mask, dtype=torch.uint8, shape=(B, 1, H, W))
+    out = torch.empty_like(img)
+    need = _lib.load().ofd_inpaint_workspace_bytes(B, H, W)
+    key = (img.device.index, torch.cuda.current_stream(img.device).cuda_stream)
+    ws = _inpaint_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device=img.device)
+        _inpaint_ws[key] = ws
+    stats = (C.c_uint32 * 2)() if want_stats else None
+    _lib.call("ofd_inpaint_telea", _ptr(img), _ptr(mask), B, H, W, int(radius), _ptr(out), _ptr(ws), C.c_size_t(ws.numel()),
+              stats, _stream(img.device))
+    return (out, (int(stats[0]), int(stats[1]))) if want_stats else out
+
+
 def special_flow(kind: int, params, H: int, W: int, device):
     """SpecialFlow (preprocess.py:24-105): returns (flow[2,H,W], back_flow[2,H,W]); params = 10 host floats or None."""
     flow = torch.empty((2, H, W), dtype=torch.float32, device=device)

@@ -121,7 +121,10 @@ class PreprocessPlusAugment(nn.Module):
                  save_dtype=np.float32, quiet: bool = False, reader_compat: bool = False):
         super().__init__()
         self.device = torch.device(device)
-        self.inpaint: Optional[Callable] = synthesis.inpaint if inpaint == "reference" else inpaint
+        # "reference": OpenCV's Telea fill on the host (the reference's values); "cuda": the device fill (ofd_inpaint_telea);
+        # None: skipped; or any callable (img, valid, collision) -> img
+        self.inpaint: Optional[Callable] = {"reference": synthesis.inpaint, "cuda": synthesis.inpaint_cuda}.get(inpaint, inpaint) \
+            if isinstance(inpaint, str) else inpaint
         self._own_writer = writer is None
         self.writer = writer if writer is not None else NpzWriter(compress=compress)
         self.save_dtype = save_dtype
@@ -268,6 +271,8 @@ def read_args(argv=None):
     parser.add_argument('--split_id', default=0, type=int)
     parser.add_argument('--specific_epoch_idx', default=-1, type=int)
     parser.add_argument('--no_inpaint', action='store_true', help='skip utils.inpaint (OpenCV Telea on the CPU)')
+    parser.add_argument('--inpaint', default='reference', choices=['reference', 'cuda'],
+                        help="Telea fill: 'reference' = cv2.inpaint on host threads (the reference's values), 'cuda' = ofd_inpaint_telea on the device")
     parser.add_argument('--writer_threads', default=8, type=int)
     parser.add_argument('--compress_level', default=6, type=int,
                         help='deflate level of the .npz files: 6 = np.savez_compressed (the reference), 1 = ~3x faster, 0 = stored')
@@ -284,7 +289,7 @@ def run(dataset, output_dir: str, is_stereo: bool, args, epochs=2) -> Dict[str, 
     device = f"cuda:{args.gpu}"
     lvl = getattr(args, "compress_level", 6)
     writer = NpzWriter(threads=args.writer_threads, compress=False if lvl == 0 else lvl)
-    ppa = PreprocessPlusAugment(device=device, inpaint=None if args.no_inpaint else "reference", writer=writer,
+    ppa = PreprocessPlusAugment(device=device, inpaint=None if args.no_inpaint else getattr(args, "inpaint", "reference"), writer=writer,
                                 reader_compat=getattr(args, "reader_compat", False))
     rng = sweep.shard_range(len(dataset), args.split, args.split_id)
     epochs = getattr(args, "epochs", epochs)

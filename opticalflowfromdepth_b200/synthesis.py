@@ -22,7 +22,7 @@ from .fw import FW
 
 __all__ = ["Plausible", "Convert", "ConcatFlow", "BackFlow", "SpecialFlow", "augment_flow", "augment_flow_batch", "augment_pairs_f64", "sample_special_params",
            "photometric_draws", "photometric_apply", "frame_draws_batch",
-           "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "synthesize_pairs", "synthesize_group"]
+           "normalize_depth", "fix_warped_depth", "get_random", "set_seed", "inpaint", "inpaint_cuda", "synthesize_pairs", "synthesize_group"]
 
 
 # ---- utils.py helpers ------------------------------------------------------------------------------------------
@@ -63,18 +63,28 @@ def fix_warped_depth(depth):
     return depth
 
 
-def inpaint(img, valid, collision):
-    """utils.inpaint (utils.py:136-151) as a HOST-SIDE HOOK, outside the hot path: the hole mask is computed on the
-    GPU (ofd_inpaint_mask); the Telea fill is OpenCV on the CPU exactly as in the reference (cv2.inpaint radius 3), with
-    the image crossing as uint8.  Accepts [3,H,W] + [1,H,W] or batched [B,3,H,W] + [B,1,H,W]; returns float32 on img's device."""
-    import cv2  # only needed when this hook is used
-
+def inpaint(img, valid, collision, backend="cv2"):
+    """utils.inpaint (utils.py:136-151).  The hole mask is computed on the GPU (ofd_inpaint_mask); the Telea fill is
+      backend="cv2":  OpenCV on the host exactly as in the reference (cv2.inpaint radius 3, the image crossing as uint8, the frames
+                      of a batch spread over host threads) - the reference's values, ~12 ms per 480x640 frame of host time;
+      backend="cuda": ofd_inpaint_telea - Telea's fast-marching fill with OpenCV's per-pixel arithmetic, marched in layers on the
+                      device, one cooperative kernel per batch, nothing crosses PCIe.  Not bit-identical to cv2 (the serial heap
+                      order is replaced by layer order); see tests/test_gpu_parity.py for the measured difference.
+    Accepts [3,H,W] + [1,H,W] or batched [B,3,H,W] + [B,1,H,W]; returns float32 on img's device."""
     single = img.dim() == 3
     im = img.unsqueeze(0) if single else img
     v = (valid.unsqueeze(0) if single else valid).float().contiguous()
     c = (collision.unsqueeze(0) if single else collision).float().contiguous()
     with torch.cuda.device(im.device):
-        mask = ops.inpaint_mask(v, c).cpu().numpy()
+        mask_dev = ops.inpaint_mask(v, c)
+        if backend == "cuda":
+            res = ops.inpaint_telea(im.float().contiguous(), mask_dev, 3)
+            return res[0] if single else res
+    if backend != "cv2":
+        raise ValueError("backend must be 'cv2' or 'cuda'")
+    import cv2  # only needed when this hook is used
+
+    mask = mask_dev.cpu().numpy()
     im_u8 = im.permute(0, 2, 3, 1).to(torch.uint8).cpu().numpy()  # .astype(np.uint8): truncation, utils.py:147
     n = im_u8.shape[0]
 
@@ -88,6 +98,11 @@ def inpaint(img, valid, collision):
         out = np.stack([fill(0)])
     res = torch.from_numpy(out.astype(np.float32)).permute(0, 3, 1, 2).contiguous().to(im.device)
     return res[0] if single else res
+
+
+def inpaint_cuda(img, valid, collision):
+    """synthesis.inpaint with the device fill (a hook for synthesize_group / augment_flow / PreprocessPlusAugment(inpaint="cuda"))."""
+    return inpaint(img, valid, collision, backend="cuda")
 
 
 # ---- preprocess.py:184-235 -------------------------------------------------------------------------------------

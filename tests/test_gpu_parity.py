@@ -1283,6 +1283,85 @@ def test_reference_preprocess_runs_unchanged_on_the_dropin_modules(pkg, golden, 
     assert same >= 24  # at least everything that depends on pair 0->1 only
 
 
+def _telea_inputs(rng, h, w, smooth):
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_oracle_cpu import _telea_case
+
+    return _telea_case(rng, h, w, smooth)
+
+
+def test_inpaint_telea_equals_the_layer_order_restatement(pkg):
+    """ofd_inpaint_telea (8f-1: the fill of utils.inpaint, utils.py:136-151, on the device) against oracle/inpaint.py in layer order
+    - the restatement whose heap-order twin reproduces cv2.inpaint bit for bit (tests/test_oracle_cpu.py) - on a batch of frames with
+    different masks: bit-exact, holes on the image borders and corners included; empty and all-hole masks are the identity; the
+    stats (layers marched, pixels filled) agree."""
+    from oracle import inpaint as oinp
+
+    rng = np.random.default_rng(5)
+    for (h, w), radius in (((36, 48), 3), ((21, 30), 3), ((24, 33), 2)):
+        cases = [_telea_inputs(rng, h, w, smooth) for smooth in (False, True, True)]
+        cases[2] = (cases[2][0], np.zeros((h, w), np.uint8))                  # nothing to fill
+        cases.append((cases[0][0], np.ones((h, w), np.uint8)))                # nothing known
+        one = np.zeros((h, w), np.uint8)
+        one[h // 2, w // 2] = 1
+        cases.append((cases[1][0], one))
+        img = cu(np.stack([c[0].transpose(2, 0, 1) for c in cases]).astype(np.float32))
+        mask = cu(np.stack([c[1][None] for c in cases]))
+        got, (layers, filled) = pkg.ops.inpaint_telea(img, mask, radius, want_stats=True)
+        want_layers, want_filled = 0, 0
+        for b, (im, m) in enumerate(cases):
+            want, (ly, fl) = oinp.telea(im, m, radius, order="layer", return_stats=True)
+            want_layers, want_filled = max(want_layers, ly), want_filled + fl
+            assert np.array_equal(got[b].cpu().numpy(), want.transpose(2, 0, 1).astype(np.float32)), (h, w, b)
+        assert (layers, filled) == (want_layers, want_filled)
+    again = pkg.ops.inpaint_telea(img, mask, radius)                            # workspace reuse, deterministic
+    assert torch.equal(again, got)
+
+
+def test_inpaint_telea_vs_cv2_on_pipeline_masks(pkg, golden):
+    """The device fill against cv2.inpaint itself on the masks the reference pipeline really produces (golden inpaint_case: the 5
+    inpaint calls of one frame, holes up to 48 % of the frame) and on a 480x640 pair with its real disocclusion mask.  The fill ORDER
+    differs by design (layers instead of OpenCV's serial heap), so the values are not bit-identical: known pixels must be untouched
+    (exact), every hole pixel filled, and the difference inside the holes is measured - stated tolerance: mean |difference| <= 12 grey
+    levels on i.i.d.-noise images (where any fill is arbitrary) and <= 3 levels on a smooth image; the fraction of hole bytes that
+    differ by more than one level is printed (tools/inpaint_report.py commits it to profiles/r2/inpaint_report.json)."""
+    cv2 = pytest.importorskip("cv2")
+    g = golden("inpaint_case")
+    h, w = g["mask0"].shape
+    rng = np.random.default_rng(8)
+    noise = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    y, x = np.mgrid[0:h, 0:w]
+    smooth = np.stack([(x * 3 + y) % 256, (x + 2 * y) % 256, 128 + 40 * np.sin(x / 5.0) + 30 * np.cos(y / 7.0)], -1).astype(np.uint8)
+    for name, base, lim in (("noise", noise, 12.0), ("smooth", smooth, 3.0)):
+        masks = np.stack([g[f"mask{k}"] for k in range(5)])
+        img = cu(np.repeat(base.transpose(2, 0, 1)[None].astype(np.float32), 5, 0))
+        got = pkg.ops.inpaint_telea(img, cu(masks[:, None]), 3).cpu().numpy().transpose(0, 2, 3, 1)
+        for k in range(5):
+            ref = cv2.inpaint(base, masks[k], 3, cv2.INPAINT_TELEA).astype(np.float32)
+            hole = masks[k] != 0
+            assert np.array_equal(got[k][~hole], ref[~hole])
+            d = np.abs(got[k] - ref)[hole]
+            print(f"[telea vs cv2] {name} mask{k}: hole {hole.mean():.2f} of the frame, mean |d| {d.mean():.2f}, > 1 level {(d > 1).mean():.3f}, max {d.max():.0f}")
+            assert d.mean() <= lim, (name, k, float(d.mean()))
+    # 480x640: the real disocclusion mask of a virtual-stereo pair, smooth synthetic image
+    H, W = 480, 640
+    _, depth = _cfg1_inputs(pkg, 1, H, W)
+    yy, xx = np.mgrid[0:H, 0:W]
+    im = np.stack([(xx * 3 + yy) % 256, (xx + 2 * yy) % 256, 128 + 40 * np.sin(xx / 15.0) + 30 * np.cos(yy / 17.0)]).astype(np.uint8).astype(np.float32)
+    pair = pkg.synthesis.synthesize_pairs(cu(im)[None], depth, torch.tensor([47.0], device=DEV))
+    mask = pkg.ops.inpaint_mask(pair["valid"], pair["collision"])
+    got, (layers, filled) = pkg.ops.inpaint_telea(pair["img1"], mask, 3, want_stats=True)
+    via_hook = pkg.synthesis.inpaint(pair["img1"], pair["valid"], pair["collision"], backend="cuda")
+    assert torch.equal(via_hook, got)
+    ref = pkg.synthesis.inpaint(pair["img1"], pair["valid"], pair["collision"], backend="cv2")
+    hole = (mask[0, 0] != 0).cpu().numpy()
+    d = np.abs(got[0].cpu().numpy() - ref[0].cpu().numpy())
+    assert filled == int(hole.sum()) and (d[:, ~hole] == 0).all()
+    dh = d[:, hole]
+    print(f"[telea vs cv2] 480x640 pair: hole {hole.mean():.3f} of the frame, {layers} layers, mean |d| {dh.mean():.2f}, > 1 level {(dh > 1).mean():.3f}, max {dh.max():.0f}")
+    assert dh.mean() <= 3.0
+
+
 def test_depth_loaders_arithmetic_on_the_device(pkg):
     """8f-4: ofd_depth_from_png == utils.get_depth(smooth=True) / utils.get_disparity + Convert.disparity_to_depth evaluated
     by numpy / torch in float64 on every 8-bit code and a sample of 16-bit ones (bit-exact), and the float32 output is that

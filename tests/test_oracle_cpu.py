@@ -169,3 +169,56 @@ def test_bilateral_mask_path_oracle_matches_reference(golden):
         assert got.dtype == g[f"{tag}_out"].dtype and np.array_equal(got, g[f"{tag}_out"], equal_nan=True), tag
     assert np.array_equal(obil.rank_table(225, np.float64), g["rank_table_f64"])
     assert not np.array_equal(g["rank_table"], g["rank_table_f64"])
+
+
+def _telea_case(rng, h, w, smooth):
+    if smooth:
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([(x * 3 + y) % 256, (x + 2 * y) % 256, 128 + 40 * np.sin(x / 5.0) + 30 * np.cos(y / 7.0)], -1).astype(np.uint8)
+    else:
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[5:9, 4:20] = 1
+    mask[12:14, :] = 1                 # a band across the whole frame
+    mask[h // 2:h // 2 + 8, w - 14:w - 11] = 1
+    mask[0:3, 0:5] = 1                 # image corner / borders (OpenCV's km / lm index shifts)
+    mask[h - 4:, w - 10:] = 1
+    mask[1, w // 2:w // 2 + 4] = 1
+    mask[rng.random((h, w)) > 0.97] = 1
+    return img, mask
+
+
+def test_telea_heap_order_restatement_equals_cv2():
+    """oracle/inpaint.py pins OpenCV's Telea arithmetic: with OpenCV's own fill order (a stable priority queue on T) the restatement
+    reproduces cv2.inpaint(..., 3, cv2.INPAINT_TELEA) - what utils.inpaint calls (utils.py:149) - bit for bit, holes at the image
+    borders and corners included.  The CUDA kernel shares this arithmetic and differs only in the fill order (layers)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import inpaint as oinp
+
+    rng = np.random.default_rng(0)
+    for (h, w), smooth in (((36, 48), False), ((36, 48), True), ((20, 27), False)):
+        img, mask = _telea_case(rng, h, w, smooth)
+        ref = cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)
+        assert np.array_equal(oinp.telea(img, mask, 3, order="heap"), ref), (h, w, smooth)
+    for radius in (1, 2, 5):
+        img, mask = _telea_case(rng, 24, 30, True)
+        assert np.array_equal(oinp.telea(img, mask, radius, order="heap"), cv2.inpaint(img, mask, radius, cv2.INPAINT_TELEA)), radius
+
+
+def test_telea_layer_order_fills_every_hole_and_touches_nothing_else():
+    """The layer order (the CUDA kernel's): every hole pixel reachable from known pixels is filled exactly once, known pixels are
+    never modified, an empty mask is the identity and a hole-only frame is left alone (nothing known to march from)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import inpaint as oinp
+
+    rng = np.random.default_rng(3)
+    img, mask = _telea_case(rng, 30, 40, True)
+    out, (layers, filled) = oinp.telea(img, mask, 3, order="layer", return_stats=True)
+    hole = mask != 0
+    assert filled == int(hole.sum()) and layers >= 2 and np.array_equal(out[~hole], img[~hole])
+    ref = cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)
+    d = np.abs(out.astype(int) - ref.astype(int))[hole]
+    print(f"[telea] layer vs heap order on a smooth frame: mean |d| = {d.mean():.2f} levels, > 1 level: {(d > 1).mean():.3f}, max {d.max()}")
+    assert d.mean() < 4.0
+    assert np.array_equal(oinp.telea(img, np.zeros_like(mask), 3), img)
+    assert np.array_equal(oinp.telea(img, np.ones_like(mask), 3), img)
