@@ -221,17 +221,20 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     }
     __syncthreads();
     // 2. discontinuity of interior image pixels from their four shared-memory neighbours (:63-116)
+    int any_flag = 0;  // this thread saw a discontinuity (computed or forced) somewhere in the raw tile
     for (int e = tid; e < RW * RH; e += nthr) {
         const int tr = e / RW, tc = e - tr * RW;
         const int r = r0 + tr, c = c0 + tc;
         const bool tested = tr > 0 && tr < RH - 1 && tc > 0 && tc < RW - 1 && r >= 1 && r <= H - 2 && c >= 1 && c <= W - 2;
         if constexpr (!MASK) {
+            any_flag |= sflag[e];  // forced discontinuities (depth_orig == 0) count as well
             if (tested) {
                 // branch-free: the four comparisons are evaluated and OR-ed (| not ||), one predicated store
                 const DT inv = sinv[e];
                 const bool disc = (fabs(inv - sinv[e - RW]) > thr) | (fabs(inv - sinv[e + RW]) > thr) |
                                   (fabs(inv - sinv[e - 1]) > thr) | (fabs(inv - sinv[e + 1]) > thr);
                 if (disc) sflag[e] |= 1;
+                any_flag |= disc;
             }
         } else {
             // a difference counts only between two unmasked pixels (:72-80); then depth_orig == 0 forces (:46) and the mask clears
@@ -243,10 +246,26 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
                 disc = ((fabs(inv - sinv[e - RW]) > thr) & ((sflag[e - RW] & 4) != 0)) | ((fabs(inv - sinv[e + RW]) > thr) & ((sflag[e + RW] & 4) != 0)) |
                        ((fabs(inv - sinv[e - 1]) > thr) & ((sflag[e - 1] & 4) != 0)) | ((fabs(inv - sinv[e + 1]) > thr) & ((sflag[e + 1] & 4) != 0));
             }
-            sflag[e] = (fe & 4) | (((fe & 4) && (disc || (fe & 2))) ? 1 : 0);  // bit 0 = final discontinuity, bit 1 dropped
+            const unsigned char fin = (fe & 4) | (((fe & 4) && (disc || (fe & 2))) ? 1 : 0);  // bit 0 = final discontinuity, bit 1 dropped
+            sflag[e] = fin;
+            any_flag |= fin & 1;
         }
     }
-    __syncthreads();
+    // 2b. block-uniform early-out: a tile without a single discontinuity in its raw tile (a superset of every window of the tile,
+    //     ring replication included: clamped taps stay inside the raw tile) keeps its (ring-replicated) depth - steps 3-4 (replication
+    //     pass, row masks, window counts, compaction, selection) are skipped.  Smooth regions are most of a depth map.
+    if (!__syncthreads_or(any_flag)) {
+        const int c = tile_x * BT_W + threadIdx.x;
+#pragma unroll
+        for (int rr = 0; rr < BIL_RPT; ++rr) {
+            const int r = tile_y * BT_H + threadIdx.y * BIL_RPT + rr;
+            if (r < H && c < W) {
+                const int rc = r < 1 ? 1 : (r > H - 2 ? H - 2 : r), cc = c < 1 ? 1 : (c > W - 2 ? W - 2 : c);
+                dout[(size_t)r * W + c] = sraw[(rc - r0) * RW + (cc - c0)];
+            }
+        }
+        return;
+    }
     // 3. the reference's border rule (:141-147): every tap reads row clamp(r,1,H-2), column clamp(c,1,W-2).  A tile whose
     //    window tile lies inside [1,H-2] x [1,W-2] needs no clamping: its taps read the raw tile in place.  Only tiles
     //    on the image border run the replication pass.

@@ -77,6 +77,21 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
     const int H = P.H, W = P.W, EW = W + 2, EH = H + 2, range = P.range;
     const size_t hw = (size_t)H * W, ehw = (size_t)EH * EW;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    // per-warp tap table of phase 2: (2 range + 1)^2 taps x TAP_F floats {w, w*I[3], w*gix*rx[3], w*giy*ry[3], used}
+    constexpr int TAP_F = 11;
+    extern __shared__ float s_dyn[];
+    const int D = 2 * range + 1, NT = D * D;
+    const int lane = threadIdx.x & 31;
+    const size_t gwarp = tid >> 5, nwarps = nth >> 5;
+    float* s_dst = s_dyn;                                              // [NT]  distance factor of every tap offset
+    float* tw = s_dyn + ((NT + 3) & ~3) + (size_t)(threadIdx.x >> 5) * NT * TAP_F;
+    for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+        const int dk = t / D - range, dl = t - (t / D) * D - range;
+        const float ry = (float)(-dk), rx = (float)(-dl);
+        const float len2 = rx * rx + ry * ry;
+        s_dst[t] = len2 > 0.f ? (float)(1. / ((double)len2 * sqrt((double)len2))) : 0.f;  // inpaint.cpp: 1 / (|r|^2 * sqrt(|r|^2))
+    }
+    __syncthreads();
 
     // ---- phase 0: working image, flags, T, band, ring ------------------------------------------------------------------------------
     for (size_t e = tid; e < (size_t)P.B * 3 * hw; e += nth) {
@@ -167,9 +182,13 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
     for (unsigned int layer = 1; layer < L_INSIDE; ++layer) {
         const unsigned int n = P.count[cur];
         if (n == 0) break;
-        // (a) compute T and colour of every frontier pixel from pixels of earlier layers
+        // (a) compute T and colour of every frontier pixel from pixels of earlier layers.  ONE WARP PER PIXEL: the lanes evaluate the
+        //     (2 range + 1)^2 taps in parallel (flags, weights, gradients: the expensive part) into a per-warp shared-memory table; lanes
+        //     0-2 (one per colour) then add the tap contributions in OpenCV's tap order (k outer, l inner), so every float32 sum is
+        //     formed in the same order as the serial code - the result does not depend on the lane layout.  (A thread per pixel ran a
+        //     layer of a few thousand pixels at ~1 warp per SM: 130 us per layer; profiles/r2/inpaint_report_v1_thread_per_pixel.json.)
         if (tid == 0) P.count[cur ^ 1] = 0;  // nobody reads the other list's counter during this layer; ordered by the barrier below
-        for (size_t e = tid; e < n; e += nth) {
+        for (size_t e = gwarp; e < n; e += nwarps) {
             const int b = (int)P.listb[cur][e];
             const int p = (int)P.list[cur][e];
             const int i = p / EW, j = p - i * EW;
@@ -190,60 +209,72 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
                 gy = known(up) ? (T[dn] - T[up]) * 0.5f : (T[dn] - dist);
             else
                 gy = known(up) ? (dist - T[up]) : 0.0f;
-            float Ia[3] = {0.f, 0.f, 0.f}, Jx[3] = {0.f, 0.f, 0.f}, Jy[3] = {0.f, 0.f, 0.f}, s[3] = {1.0e-20f, 1.0e-20f, 1.0e-20f};
-            for (int k = i - range; k <= i + range; ++k) {
-                if (k <= 0 || k >= EH - 1) continue;
+            for (int t = lane; t < NT; t += 32) {
+                const int dk = t / D, dl = t - dk * D;
+                const int k = i - range + dk, l = j - range + dl;
+                float* slot = tw + t * TAP_F;
+                bool use = k > 0 && k < EH - 1 && l > 0 && l < EW - 1 && (l - j) * (l - j) + (k - i) * (k - i) <= range * range;
+                const int q = k * EW + l;
+                use = use && known(q);
+                slot[10] = use ? 1.0f : 0.0f;
+                if (!use) continue;
                 const int km = k - 1 + (k == 1), kp = k - 1 - (k == EH - 2);
-                for (int l = j - range; l <= j + range; ++l) {
-                    if (l <= 0 || l >= EW - 1) continue;
-                    const int q = k * EW + l;
-                    if (!known(q) || (l - j) * (l - j) + (k - i) * (k - i) > range * range) continue;
-                    const int lm = l - 1 + (l == 1), lp = l - 1 - (l == EW - 2);
-                    const float ry = (float)(i - k), rx = (float)(j - l);
-                    const float len2 = rx * rx + ry * ry;
-                    const float dst = (float)(1. / ((double)len2 * sqrt((double)len2)));
-                    const float lev = (float)(1. / (1 + fabs((double)(T[q] - dist))));
-                    float dir = rx * gx + ry * gy;
-                    if (fabsf(dir) <= 0.01f) dir = 0.000001f;
-                    const float w = fabsf(dst * lev * dir);
-                    const bool kr = known(q + 1), kl = known(q - 1), kd = known(q + EW), ku = known(q - EW);
+                const int lm = l - 1 + (l == 1), lp = l - 1 - (l == EW - 2);
+                const float ry = (float)(i - k), rx = (float)(j - l);
+                const float lev = (float)(1. / (1 + fabs((double)(T[q] - dist))));
+                float dir = rx * gx + ry * gy;
+                if (fabsf(dir) <= 0.01f) dir = 0.000001f;
+                const float w = fabsf(s_dst[t] * lev * dir);
+                const bool kr = known(q + 1), kl = known(q - 1), kd = known(q + EW), ku = known(q - EW);
+                slot[0] = w;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned char* Ic = I + (size_t)c * hw;
-                        // (row / column clamps only matter for frames with H < 2 or W < 2, where inpaint.cpp's km / lm shifts leave the image)
-                        auto px = [&](int r, int col) -> float {
-                            r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
-                            col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
-                            return (float)Ic[(size_t)r * W + col];
-                        };
-                        float gix, giy;
-                        if (kr)
-                            gix = kl ? (px(km, lp + 1) - px(km, lm - 1)) * 2.0f : (px(km, lp + 1) - px(km, lm));
-                        else
-                            gix = kl ? (px(km, lp) - px(km, lm - 1)) : 0.0f;
-                        if (kd)
-                            giy = ku ? (px(kp + 1, lm) - px(km - 1, lm)) * 2.0f : (px(kp + 1, lm) - px(km, lm));
-                        else
-                            giy = ku ? (px(kp, lm) - px(km - 1, lm)) : 0.0f;
-                        Ia[c] += w * px(k - 1, l - 1);  // the tap's own pixel; the km / lm shifts apply to the gradients only
-                        Jx[c] -= w * (gix * rx);
-                        Jy[c] -= w * (giy * ry);
-                        s[c] += w;
-                    }
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned char* Ic = I + (size_t)c * hw;
+                    // (row / column clamps only matter for frames with H < 2 or W < 2, where inpaint.cpp's km / lm shifts leave the image)
+                    auto px = [&](int r, int col) -> float {
+                        r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
+                        col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+                        return (float)Ic[(size_t)r * W + col];
+                    };
+                    float gix, giy;
+                    if (kr)
+                        gix = kl ? (px(km, lp + 1) - px(km, lm - 1)) * 2.0f : (px(km, lp + 1) - px(km, lm));
+                    else
+                        gix = kl ? (px(km, lp) - px(km, lm - 1)) : 0.0f;
+                    if (kd)
+                        giy = ku ? (px(kp + 1, lm) - px(km - 1, lm)) * 2.0f : (px(kp + 1, lm) - px(km, lm));
+                    else
+                        giy = ku ? (px(kp, lm) - px(km - 1, lm)) : 0.0f;
+                    slot[1 + c] = w * px(k - 1, l - 1);  // the tap's own pixel; the km / lm shifts apply to the gradients only
+                    slot[4 + c] = w * (gix * rx);
+                    slot[7 + c] = w * (giy * ry);
                 }
             }
-            uchar4 col;
-            unsigned char* cp = reinterpret_cast<unsigned char*>(&col);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float sat = (float)(Ia[c] / s[c] + (Jx[c] + Jy[c]) / (sqrtf(Jx[c] * Jx[c] + Jy[c] * Jy[c]) + 1.0e-20f) + 0.5f);
+            __syncwarp();
+            unsigned int byte = 0;
+            if (lane < 3) {
+                const int c = lane;
+                float Ia = 0.f, Jx = 0.f, Jy = 0.f, sw = 1.0e-20f;
+                for (int t = 0; t < NT; ++t) {
+                    const float* slot = tw + t * TAP_F;
+                    if (slot[10] != 0.0f) {
+                        Ia += slot[1 + c];
+                        Jx -= slot[4 + c];
+                        Jy -= slot[7 + c];
+                        sw += slot[0];
+                    }
+                }
+                const float sat = (float)(Ia / sw + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f) + 0.5f);
                 int v = __float2int_rn(sat);  // saturate_cast<uchar>(float): round to nearest even, saturate
                 if (!(sat == sat)) v = 0;
-                cp[c] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+                byte = (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v));
             }
-            cp[3] = 0;
-            P.stageT[e] = dist;
-            P.stageC[e] = col;
+            const unsigned int c0 = __shfl_sync(0xFFFFFFFFu, byte, 0), c1 = __shfl_sync(0xFFFFFFFFu, byte, 1), c2 = __shfl_sync(0xFFFFFFFFu, byte, 2);
+            if (lane == 0) {
+                P.stageT[e] = dist;
+                P.stageC[e] = make_uchar4((unsigned char)c0, (unsigned char)c1, (unsigned char)c2, 0);
+            }
+            __syncwarp();
         }
         grid.sync();
         // (b) commit the layer and enqueue its unfilled 4-neighbours for the next one
@@ -305,7 +336,7 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
                       uint32_t* stats_host_or_null, ofd_stream_t stream) {
     const char* fn = "ofd_inpaint_telea";
     if (B < 0 || H < 0 || W < 0) return fail(OFD_E_SHAPE, "%s: negative dimension", fn);
-    if (range < 1 || range > 8) return fail(OFD_E_ARG, "%s: range %d outside [1,8]", fn, range);
+    if (range < 1 || range > 5) return fail(OFD_E_ARG, "%s: range %d outside [1,5]", fn, range);
     if ((size_t)(H + 2) * (size_t)(W + 2) >= ((size_t)1 << 31)) return fail(OFD_E_SHAPE, "%s: frame too large", fn);
     if (B == 0 || H == 0 || W == 0) return OFD_OK;
     if (!img || !mask || !out) return fail(OFD_E_NULL, "%s: NULL tensor pointer", fn);
@@ -328,7 +359,9 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     P.stageT = (float*)w, w += align256(nb * ehw * 4);
     P.stageC = (uchar4*)w, w += align256(nb * hw * 4);
     int sms = 0, per_sm = 0;
-    int rc = launch_plan(fn, (const void*)telea_kernel, 256, 0, &sms, &per_sm);
+    const int NT = (2 * range + 1) * (2 * range + 1);
+    const size_t smem = ((size_t)((NT + 3) & ~3) + (size_t)8 * NT * 11) * sizeof(float);  // dst table + 8 warps x NT taps x 11 floats
+    int rc = launch_plan(fn, (const void*)telea_kernel, 256, smem, &sms, &per_sm);
     if (rc) return rc;
     int dev = 0, coop = 0;
     cudaGetDevice(&dev);
@@ -338,7 +371,7 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     const long long useful = (long long)((nb * ehw + 255) / 256);
     if (blocks > useful) blocks = useful < 1 ? 1 : useful;
     void* args[] = {(void*)&P};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)telea_kernel, dim3((unsigned)blocks), dim3(256), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)telea_kernel, dim3((unsigned)blocks), dim3(256), args, smem, st);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchCooperativeKernel: %s", fn, cudaGetErrorString(e));
     if (stats_host_or_null) {  // layers marched / pixels filled: a synchronising read, for tests and reports only
         e = cudaMemcpyAsync(stats_host_or_null, P.count + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);

@@ -39,10 +39,12 @@ def pkg():
 
 
 # Fraction of a downstream plane of the 5-pair group that may differ from the reference's own pipeline output: those planes are warped
-# along 6-DoF flows that agree with the reference's to ~1e-5 px (dot-product order), and a truncated target can move.  Measured on
-# the goldens by tools/parity_report.py (profiles/r2/parity_report.json: worst plane 0.0071 on the 40x56 case, where ONE moved source
-# is 4.5e-4 of a plane); the bound is 2x that measurement instead of round 1's blanket 0.02.
-GROUP_PLANE_DIFF_LIMIT = 0.015
+# along 6-DoF flows whose K=3/4 dot products are BLAS-order dependent in the reference, and a ~1e-5 px flow difference can move a
+# truncated target.  MEASURED on B200 against the reference's CPU run (tools/parity_report.py -> profiles/r2/parity_report.json):
+# 0.0 on every plane of both goldens (the kernel's ascending-k FMA chains reproduce this image's CPU matmul bit for bit; the same holds
+# for the sampled full-size flows).  The bound is one moved source pixel per 40x56 plane with its 3x3 neighbourhood (2e-3) instead of
+# round 1's blanket 0.02 - room for another host BLAS, nothing more.
+GROUP_PLANE_DIFF_LIMIT = 0.002
 
 
 def cu(a):
