@@ -21,6 +21,8 @@
 // that every read of a layer sees the state at the layer's start (deterministic results).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "ofd_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -367,6 +369,10 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop) return fail(OFD_E_ARG, "%s: device does not support cooperative launches", fn);
+    if (const char* env = getenv("OFD_TELEA_BLOCKS_PER_SM")) {  // tuning knob: fewer blocks make the grid-wide barriers cheaper
+        const int v = atoi(env);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     long long blocks = (long long)sms * per_sm;
     const long long useful = (long long)((nb * ehw + 255) / 256);
     if (blocks > useful) blocks = useful < 1 ? 1 : useful;
