@@ -326,6 +326,27 @@ int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, co
                                 float* flow_host /*nullable*/, float* valid_host, float* collision_host /*nullable*/,
                                 unsigned flags);
 /*
+ * Input side on the device.
+ * ofd_jpeg_*: utils.get_img (utils.py:17-25) decodes on the host with cv2.imread(path, -1) and converts BGR uint8 HWC to float32 CHW;
+ * here the compressed JPEG bytes (ReDWeb's images, dataloader.py:28) go to nvJPEG (loaded with dlopen at the first create; the library has
+ * no link-time dependency on it), which decodes on the GPU, and a kernel widens the planar B | G | R bytes to out_bgr[3,H,W] float32 - a
+ * frame crosses PCIe once, as compressed bytes.  JPEG decoders are not bit-specified: the result is within a few grey levels of cv2's
+ * (libjpeg-turbo), see tests.  ofd_jpeg_info reads H, W (and the component count) from the header; ofd_jpeg_decode checks them against the
+ * tensor it is given.  data_host is HOST memory.  PNG (deflate) stays on the host.
+ * ofd_resize_bilinear_aa: T.Resize(size)(depth) of dataloader.py:31-32,57-58 = torchvision's antialiased bilinear resize (ATen
+ * upsample_bilinear2d_aa, align_corners = false) of src[B,H,W] (f32|f64) to dst[B,H_out,W_out]; tmp holds B*H*W_out elements when both axes
+ * change.  Bit-identical to torchvision when upscaling, within 2 ulp when downscaling.
+ */
+typedef struct ofd_jpeg_decoder ofd_jpeg_decoder;
+int ofd_jpeg_decoder_create(int device, ofd_jpeg_decoder** out);
+int ofd_jpeg_info(ofd_jpeg_decoder* d, const uint8_t* data_host, size_t nbytes, int* H, int* W, int* components);
+int ofd_jpeg_decode(ofd_jpeg_decoder* d, const uint8_t* data_host, size_t nbytes, float* out_bgr, int H, int W,
+                    ofd_stream_t stream);
+void ofd_jpeg_decoder_destroy(ofd_jpeg_decoder* d);
+int ofd_resize_bilinear_aa(const void* src, int dtype, int B, int H, int W, int H_out, int W_out, void* dst, void* tmp,
+                           ofd_stream_t stream);
+
+/*
  * ofd_inpaint_telea — the fill of utils.inpaint (utils.py:136-151: cv2.inpaint(img_u8, mask, 3, cv2.INPAINT_TELEA) on the host, 95
  * calls per frame in preprocess.py) on the device, for a batch: img[B,3,H,W] float32 (truncated to uint8 like .astype(np.uint8),
  * utils.py:147), mask[B,1,H,W] uint8 (!= 0 = fill; ofd_inpaint_mask produces it), range = inpaint radius (the reference uses 3)

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libofd_b200.so"
 STAMP = PKG / ".libofd_b200.stamp"
-SOURCES = ["ofd_abi.cu", "ofd_splat.cu", "ofd_splat_f64.cu", "ofd_pair.cu", "ofd_flow.cu", "ofd_bilateral.cu", "ofd_host.cu", "ofd_inpaint.cu"]
+SOURCES = ["ofd_abi.cu", "ofd_splat.cu", "ofd_splat_f64.cu", "ofd_pair.cu", "ofd_flow.cu", "ofd_bilateral.cu", "ofd_host.cu", "ofd_inpaint.cu", "ofd_decode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -47,7 +47,7 @@ def build_variant(name: str, defines: list[str]) -> Path:
     vdir = PKG / "build" / "variants"
     vdir.mkdir(parents=True, exist_ok=True)
     out = vdir / f"{name}.so"
-    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", str(out), *[str(CSRC / s) for s in SOURCES], "-lcudart"]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", str(out), *[str(CSRC / s) for s in SOURCES], "-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(r.stdout)
@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (objdir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

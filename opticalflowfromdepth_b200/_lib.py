@@ -51,6 +51,11 @@ SIGNATURES = {
     "ofd_pair_pipeline_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "ofd_pair_pipeline_run": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "ofd_pair_pipeline_run_flags": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint]),
+    "ofd_jpeg_decoder_create": (_i, [_i, C.POINTER(_p)]),
+    "ofd_jpeg_info": (_i, [_p, _p, _sz, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ofd_jpeg_decode": (_i, [_p, _p, _sz, _p, _i, _i, _p]),
+    "ofd_jpeg_decoder_destroy": (None, [_p]),
+    "ofd_resize_bilinear_aa": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ofd_inpaint_workspace_bytes": (_sz, [_i, _i, _i]),
     "ofd_inpaint_telea": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p, _p]),
     "ofd_copy_rows_to_host": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),

@@ -365,6 +365,58 @@ def inpaint_mask(valid, collision):
     return mask
 
 
+@_on_device
+def resize_bilinear_aa(t, size):
+    """torchvision's T.Resize(size) of a float tensor (antialiased bilinear, dataloader.py:31-32,57-58) on the device:
+    t[..., H, W] float32|float64 CUDA -> [..., H_out, W_out] (ofd_resize_bilinear_aa)."""
+    _check("t", t, dtype=(torch.float32, torch.float64))
+    if t.dim() < 2:
+        raise ValueError("t must be [..., H, W]")
+    H, W = t.shape[-2:]
+    Ho, Wo = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    B = t.numel() // (H * W) if H * W else 0
+    out = torch.empty(t.shape[:-2] + (Ho, Wo), dtype=t.dtype, device=t.device)
+    tmp = torch.empty((B, H, Wo), dtype=t.dtype, device=t.device) if (Ho != H and Wo != W) else None
+    _lib.call("ofd_resize_bilinear_aa", _ptr(t), _DT[t.dtype], B, H, W, Ho, Wo, _ptr(out), _ptr(tmp), _stream(t.device))
+    return out
+
+
+class JpegDecoder:
+    """nvJPEG on the device (ofd_jpeg_*): `decode(jpeg_bytes)` -> float32 [3,H,W] CUDA tensor in B, G, R channel order - what
+    utils.get_img (utils.py:17-25: cv2.imread(path, -1) -> float32 CHW) returns, decoded on the GPU from the compressed bytes."""
+
+    def __init__(self, device=0):
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self._h = C.c_void_p(0)
+        _lib.call("ofd_jpeg_decoder_create", int(self.device.index or 0), C.byref(self._h))
+
+    def info(self, data: bytes):
+        h, w, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        _lib.call("ofd_jpeg_info", self._h, buf, C.c_size_t(len(data)), C.byref(h), C.byref(w), C.byref(c))
+        return h.value, w.value, c.value
+
+    def decode(self, data: bytes) -> torch.Tensor:
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        h, w, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        _lib.call("ofd_jpeg_info", self._h, buf, C.c_size_t(len(data)), C.byref(h), C.byref(w), C.byref(c))
+        out = torch.empty((3, h.value, w.value), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("ofd_jpeg_decode", self._h, buf, C.c_size_t(len(data)), _ptr(out), h.value, w.value, _stream(self.device))
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.load().ofd_jpeg_decoder_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _inpaint_ws = {}
 
 

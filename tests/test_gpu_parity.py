@@ -1364,6 +1364,82 @@ def test_inpaint_telea_vs_cv2_on_pipeline_masks(pkg, golden):
     assert dh.mean() <= 3.0
 
 
+def test_resize_bilinear_aa_vs_torchvision(pkg):
+    """8f-4: ofd_resize_bilinear_aa against torchvision's T.Resize of a float tensor on the CPU (what dataloader.py:31-32,57-58 applies to
+    the float64 depth / disparity when its size differs from the image's): bit-identical when upscaling, within 2 ulp when downscaling
+    (ATen's vectorised reduction order), float64 and float32, one- and two-axis resizes, identity."""
+    import torchvision.transforms as T
+
+    rng = np.random.default_rng(0)
+    for dt, ulp in ((np.float64, 2.3e-16), (np.float32, 1.2e-7)):
+        for (h, w), (oh, ow), exact in (((24, 40), (37, 53), True), ((31, 47), (62, 94), True), ((30, 30), (30, 45), True),
+                                        ((37, 53), (24, 40), False), ((480, 640), (375, 1242), False), ((100, 80), (33, 27), False),
+                                        ((20, 20), (20, 20), True)):
+            a = (rng.random((2, h, w)) * 100).astype(dt)
+            ref = T.Resize((oh, ow))(torch.from_numpy(a)).numpy()
+            got = pkg.ops.resize_bilinear_aa(cu(a), (oh, ow)).cpu().numpy()
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+            if exact:
+                assert np.array_equal(got, ref), (dt.__name__, (h, w), (oh, ow), float(np.abs(got - ref).max()))
+            else:
+                assert np.abs(got - ref).max() <= 4 * ulp * 100, (dt.__name__, (h, w), (oh, ow), float(np.abs(got - ref).max()))
+
+
+def test_device_loaders_jpeg_decode_and_redweb_items(pkg, tmp_path):
+    """8f-4: the reference's loaders with the decode on the device.  A ReDWeb-shaped directory (Imgs/*.jpg, RDs/*.png) is written with
+    cv2; loaders.ReDWeb must return what dataloader.ReDWeb (dataloader.py:14-34) returns: the image = cv2.imread(path, -1) as float32 CHW
+    (nvJPEG vs libjpeg-turbo: JPEG decoders are not bit-specified - the stated bound is mean |difference| <= 1 grey level and <= 1 % of the
+    bytes off by more than 3 levels, measured and printed), the depth payload bit-exact, and with a depth map of another size the float64
+    T.Resize result within 2 ulp."""
+    cv2 = pytest.importorskip("cv2")
+    import torchvision.transforms as T
+    from opticalflowfromdepth_b200 import loaders
+
+    root = tmp_path / "ReDWeb_V1"
+    (root / "Imgs").mkdir(parents=True)
+    (root / "RDs").mkdir()
+    rng = np.random.default_rng(4)
+    names = []
+    for k, (h, w, dh, dw, q) in enumerate(((240, 320, 240, 320, 95), (301, 403, 150, 200, 85), (128, 96, 128, 96, 75))):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([(x * 2 + y) % 256, 128 + 100 * np.sin(x / 23.0) * np.cos(y / 17.0), (x + 3 * y) % 256], -1)
+        img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+        cv2.imwrite(str(root / "Imgs" / f"f{k}.jpg"), img, [cv2.IMWRITE_JPEG_QUALITY, q])
+        yy, xx = np.mgrid[0:dh, 0:dw]
+        rel = np.clip(120 + 100 * np.sin(xx / 31.0) + 30 * np.cos(yy / 11.0), 0, 255).astype(np.uint8)
+        cv2.imwrite(str(root / "RDs" / f"f{k}.png"), rel)
+        names.append(f"f{k}.jpg")
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    ds = loaders.ReDWeb(str(root), str(tmp_path / "list.txt"), device=0)
+    assert len(ds) == 3
+    for k in range(3):
+        img, depth = ds[k]
+        ref_img = torch.from_numpy(cv2.imread(str(root / "Imgs" / f"f{k}.jpg"), -1)).type(torch.float32).permute(2, 0, 1)  # utils.py:17-25
+        assert img.is_cuda and img.dtype == torch.float32 and tuple(img.shape) == tuple(ref_img.shape)
+        d = (img.cpu() - ref_img).abs()
+        print(f"[jpeg] frame {k}: nvJPEG vs cv2 mean |d| {float(d.mean()):.3f} levels, > 3 levels {float((d > 3).float().mean()):.4f}, max {float(d.max()):.0f}")
+        assert float(d.mean()) <= 1.0 and float((d > 3).float().mean()) <= 0.01
+        ref_d = cv2.imread(str(root / "RDs" / f"f{k}.png"), cv2.IMREAD_GRAYSCALE).astype(float)                          # utils.py:48
+        ref_d[ref_d > 240] = 240
+        with np.errstate(divide="ignore"):
+            ref_d = torch.from_numpy(1 / (255 - ref_d)).unsqueeze(0)                                                   # utils.py:118-121
+        if ref_d.shape[-2:] != ref_img.shape[-2:]:
+            ref_d = T.Resize(tuple(ref_img.shape[-2:]))(ref_d)                                                          # dataloader.py:31-32
+            assert depth.dtype == torch.float64 and tuple(depth.shape) == tuple(ref_d.shape)
+            assert float((depth.cpu() - ref_d).abs().max()) <= 1e-15
+        else:
+            assert depth.dtype == torch.uint8
+            assert torch.equal(pkg.ops.depth_from_png(depth, "reldepth").cpu(), ref_d)
+    # the items feed the driver directly
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    ppa = pp.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    pkg.synthesis.set_seed(5)
+    grp = ppa.synthesize(ds[0], is_stereo=False)
+    ppa.close()
+    assert grp["img1"].shape == (1, 3, 240, 320) and bool(torch.isfinite(grp["flow12"]).all())
+
+
 def test_depth_loaders_arithmetic_on_the_device(pkg):
     """8f-4: ofd_depth_from_png == utils.get_depth(smooth=True) / utils.get_disparity + Convert.disparity_to_depth evaluated
     by numpy / torch in float64 on every 8-bit code and a sample of 16-bit ones (bit-exact), and the float32 output is that
