@@ -32,7 +32,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W = 480, 640
-GROUP_BYTES_PER_PX = 56 + 64 + 56 + 2 * 40 + 12 + 2 * 60   # 388: SURVEY 8d rows of the 7 splats of one frame group
+# SURVEY 8d rows of the 7 splats of one frame group WITHOUT the five collision planes: they only feed utils.inpaint's
+# mask and are not produced when the group runs without a fill, as here (388 with them)
+GROUP_BYTES_PER_PX = 52 + 60 + 52 + 2 * 40 + 12 + 2 * 56   # 368
 PAIR_BYTES_PER_PX = 56          # img 3 + depth 1 in; img1 3, depth1 1, back_flow 2, flow 2, valid 1, collision 1 out
 FW_BYTES_PER_PX = lambda C: 4 * (2 * C + 5)  # noqa: E731  splat at the FW.forward boundary
 POOL = 16                       # distinct synthetic frames; the batch cycles through them
@@ -319,7 +321,8 @@ def run_ours(args):
                                      "algorithmic_bytes_per_px": GROUP_BYTES_PER_PX,
                                      "counters": sweep.reduce_counters(g_counters),
                                      "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats); bytes = SURVEY 8d rows summed: "
-                                             "56 (0->1) + 64 (1->2) + 56 (0->3) + 2 x 40 (ConcatFlow) + 12 (flow13_valid * valid1) + 2 x 60 (C=7 frame splats)"}
+                                             "52 (0->1) + 60 (1->2) + 52 (0->3) + 2 x 40 (ConcatFlow) + 12 (flow13_valid * valid1) + 2 x 56 (C=7 frame splats); the "
+                                             "collision planes (4 B/px per image splat) are not produced without an inpaint hook and not credited"}
             del camq
         except Exception as e:
             line["group_480x640"] = {"error": repr(e)}

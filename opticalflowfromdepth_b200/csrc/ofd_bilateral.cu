@@ -22,9 +22,41 @@
 // Variants: a ragged batch (one launch for images of different sizes) and the reference's binary-mask path.
 // The kernel is instruction-bound, not HBM-bound; a TMA 2-D tiled load for step 1 (the north star
 // suggests it) would not change that: a 42x42 float tile is 7 plain coalesced loads per thread and needs no tensor map.
+#include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
+#include <cstdlib>
+
 #include "ofd_common.cuh"
 
 namespace ofd {
+
+// ---- TMA 2-D tiled load of the raw tile (EXPERIMENT, OFD_BIL_TMA=1; VERDICT r1 next #7b) -----------------------------------------------
+__device__ __forceinline__ uint32_t bil_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bil_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bil_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bil_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bil_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bil_mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}" ::"r"(bil_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one box of the tensor map at element coordinates (x, y) - out-of-image elements arrive as zeros
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     bil_smem_u32(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(bil_smem_u32(bar))
+                 : "memory");
+}
 
 // Tile = 32 x (8 * BIL_RPT) outputs for a block of 32 x 8 threads: every thread owns BIL_RPT output rows.  A taller tile
 // amortises the halo (window 7: 2.95 staged cells per output at 32x8, 2.13 at 32x16, 1.72 at 32x32).
@@ -145,19 +177,23 @@ static KRank make_krank(int window, bool coef_f64 = false) {
 // counts only between two unmasked pixels, masked pixels are never discontinuities and keep their depth, masked taps and taps
 // outside the image (the mask is zero-padded, not ring-replicated) are left out of the median.  Flag byte: bit 0 discontinuity,
 // bit 1 depth_orig == 0, bit 2 unmasked.
-template <typename DT, int WS, bool MASK = false>
+template <typename DT, int WS, bool MASK = false, bool TMA = false>
 __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const DT* __restrict__ dorig, int H, int W,
                                                int win_rt, DT thr, DT* __restrict__ dout, int tile_x, int tile_y,
-                                               const KRank& kr, const unsigned char* __restrict__ mask = nullptr) {
+                                               const KRank& kr, const unsigned char* __restrict__ mask = nullptr,
+                                               const CUtensorMap* tm_in = nullptr, const CUtensorMap* tm_orig = nullptr) {
     static_assert(!MASK || WS > 0, "the mask path is built for the compile-time windows");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(!TMA || (WS > 0 && !MASK && sizeof(DT) == 4), "the TMA experiment covers the float32 compile-time windows");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int win = WS > 0 ? WS : win_rt;
     const int m = win / 2;
-    const int RW = BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4;  // raw tile: window halo + a ring of 2 (neighbour differences + clamping)
+    // raw tile: window halo + a ring of 2 (neighbour differences + clamping); the TMA box is padded to a multiple of 16 bytes per row
+    const int RW = TMA ? ((BT_W + 2 * m + 4 + 3) & ~3) : BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4;
     const int TW = BT_W + 2 * m, TH = BT_H + 2 * m;          // window tile
+    const int CELLS_P = TMA ? ((RW * RH + 31) & ~31) : RW * RH;  // TMA destinations start on 128-byte boundaries
     DT* sraw = reinterpret_cast<DT*>(smem_raw);               // raw depth
-    DT* sinv = sraw + RW * RH;                                // 1 / depth, formed once per cell
-    DT* sdep = sinv + RW * RH;                                // replicated depth at window coordinates (border tiles only)
+    DT* sinv = sraw + CELLS_P;                                // 1 / depth, formed once per cell
+    DT* sdep = sinv + CELLS_P;                                // replicated depth at window coordinates (border tiles only)
     unsigned char* sflag = reinterpret_cast<unsigned char*>(sdep + TW * TH);  // raw-tile discontinuity flags
     unsigned char* sdisc = sflag + RW * RH;                                   // replicated flags (border tiles only)
     __shared__ unsigned char s_k[MAX_WIN * MAX_WIN + 3];
@@ -173,7 +209,27 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
 
     // 1. raw tile: depth, 1/depth, depth_orig == 0 (zero outside the image; those cells are never consumed).  For a
     //    compile-time window all global loads of a thread are issued before the first use.
-    if constexpr (WS > 0) {
+    if constexpr (TMA) {
+        // EXPERIMENT: both raw tiles (depth, depth_orig) arrive by ONE tensor-map copy each (cp.async.bulk.tensor.2d, SASS UTMALDG; cells
+        // outside the image are zero-filled by the TMA unit); the threads then form 1/d and the forced flags in a pass over shared memory.
+        __shared__ __align__(8) uint64_t s_bar;
+        if (tid == 0) bil_mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            bil_mbar_expect_tx(&s_bar, 2u * (unsigned)(RW * RH) * (unsigned)sizeof(DT));
+            tma_load_2d(sraw, tm_in, c0, r0, &s_bar);
+            tma_load_2d(sinv, tm_orig, c0, r0, &s_bar);
+        }
+        bil_mbar_wait(&s_bar, 0);
+        for (int e = tid; e < RW * RH; e += nthr) {
+            const int tr = e / RW, tc = e - tr * RW;
+            const int r = r0 + tr, c = c0 + tc;
+            const bool inb = r >= 0 && r < H && c >= 0 && c < W;
+            const DT ov = sinv[e];
+            sflag[e] = (inb && ov == (DT)0) ? 2 : 0;  // out-of-image cells arrive as zeros: they are not depth_orig == 0 pixels
+            sinv[e] = (DT)1.0 / sraw[e];
+        }
+    } else if constexpr (WS > 0) {
         constexpr int CELLS = (BT_W + 2 * (WS / 2) + 4) * (BT_H + 2 * (WS / 2) + 4);
         constexpr int NL = (CELLS + nthr - 1) / nthr;
         DT dv[NL], ov[NL];
@@ -430,6 +486,53 @@ __global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 
     bilateral_tile<DT, WS>(din, dorig, H, W, win_rt, thr, dout, blockIdx.x, blockIdx.y, kr);
 }
 
+template <int WS>
+__global__ void __launch_bounds__(BT_W* BT_TY, OFD_BIL_MINB) bilateral_iter_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                                    const __grid_constant__ CUtensorMap tm_orig, int H, int W,
+                                                                                    float thr, float* __restrict__ dout,
+                                                                                    const __grid_constant__ KRank kr) {
+    bilateral_tile<float, WS, false, true>(nullptr, nullptr, H, W, WS, thr, dout, blockIdx.x, blockIdx.y, kr, nullptr, &tm_in, &tm_orig);
+}
+
+typedef CUresult (*pfn_cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static pfn_cuTensorMapEncodeTiled tensor_map_encoder() {
+    static pfn_cuTensorMapEncodeTiled fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (pfn_cuTensorMapEncodeTiled)p;
+    }();
+    return fn;
+}
+
+// returns false when the experiment does not apply (the caller then takes the default path)
+template <int WS>
+static bool launch_bilateral_tma(const float* din, const float* dorig, int H, int W, float thr, float* dout, cudaStream_t st) {
+    pfn_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc || W % 4 != 0 || (((uintptr_t)din | (uintptr_t)dorig) & 15)) return false;
+    constexpr int m = WS / 2;
+    constexpr int RW = (BT_W + 2 * m + 4 + 3) & ~3, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
+    constexpr int CELLS_P = (RW * RH + 31) & ~31;
+    CUtensorMap maps[2];
+    const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)W * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)RW, (cuuint32_t)RH};
+    const cuuint32_t estr[2] = {1, 1};
+    const float* ptrs[2] = {din, dorig};
+    for (int k = 0; k < 2; ++k)
+        if (enc(&maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptrs[k], gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    const size_t smem = (size_t)CELLS_P * 2 * sizeof(float) + (size_t)TW * TH * (sizeof(float) + 1) + (size_t)RW * RH + 64;
+    dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H), block(BT_W, BT_TY);
+    ensure_dynamic_smem("bilateral_iter_tma_kernel", (const void*)bilateral_iter_tma_kernel<WS>, smem);
+    bilateral_iter_tma_kernel<WS><<<grid, block, smem, st>>>(maps[0], maps[1], H, W, thr, dout, make_krank(WS));
+    return true;
+}
+
 template <typename DT, int WS>
 __global__ void __launch_bounds__(BT_W* BT_TY, sizeof(DT) == 4 ? OFD_BIL_MINB : 1) bilateral_masked_kernel(
     const DT* __restrict__ din, const DT* __restrict__ dorig, const unsigned char* __restrict__ mask, int H, int W, DT thr,
@@ -518,6 +621,16 @@ static void launch_bilateral(const DT* din, const DT* dorig, int H, int W, int w
 
 template <typename DT>
 static void dispatch_bilateral(const DT* din, const DT* dorig, int H, int W, int window, DT thr, DT* dout, cudaStream_t st) {
+    if constexpr (sizeof(DT) == 4) {
+        const char* e = std::getenv("OFD_BIL_TMA");  // experiment, default off (profiles/r2/tune_bilateral_tma.txt)
+        if (e && std::atoi(e) != 0) {
+            bool done = false;
+            if (window == 3) done = launch_bilateral_tma<3>(din, dorig, H, W, thr, dout, st);
+            if (window == 5) done = launch_bilateral_tma<5>(din, dorig, H, W, thr, dout, st);
+            if (window == 7) done = launch_bilateral_tma<7>(din, dorig, H, W, thr, dout, st);
+            if (done) return;
+        }
+    }
     switch (window) {
         case 3: launch_bilateral<DT, 3>(din, dorig, H, W, window, thr, dout, st); break;
         case 5: launch_bilateral<DT, 5>(din, dorig, H, W, window, thr, dout, st); break;

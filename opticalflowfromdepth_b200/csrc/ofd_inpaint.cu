@@ -39,15 +39,15 @@ struct TeleaParams {
     int B, H, W, range;
     // workspace (per batch)
     unsigned char* u8;         // [B,3,H,W] working image
+    unsigned char* u8o;        // [B,3,H,W] the original bytes (read where OpenCV's border index shifts hit a cell that is still unknown)
     unsigned short* L;         // [B,(H+2),(W+2)] layer: 0 known, 0xFFFF unfilled hole, k filled in layer k
     float* T;                  // [B,(H+2),(W+2)]
     unsigned char* G;          // [B,(H+2),(W+2)] outward march: 0 other, 1 band, 255 ring (uncomputed), k+1 computed in out-layer k
     unsigned int* Q;           // [B,(H+2),(W+2)] 1 = already enqueued
-    unsigned int* list[2];     // frontier lists: (b << 24) | extended pixel index ... stored as two words when large
-    unsigned int* listb[2];    // frame index of each entry
-    float* stageT;             // per entry: T
-    uchar4* stageC;            // per entry: colour
-    unsigned int* count;       // [2] list sizes, [2] = layers done, [3] = filled pixels
+    unsigned int* list[3];     // rotating frontier lists: extended pixel index of each entry
+    unsigned int* listb[3];    // frame index of each entry
+    float* stageT;             // ring march: staged T per extended pixel
+    unsigned int* count;       // [0..2] list sizes, [3] = layers done, [4] = filled pixels
 };
 
 // inpaint.cpp FastMarching_solve: upwind quadrant solve from the two neighbours (i1,j1), (i2,j2); `known(q)` = f != INSIDE
@@ -74,7 +74,7 @@ __device__ __forceinline__ float fmm_solve(float a11, bool k1, float a22, bool k
 
 __device__ __forceinline__ float min4(float a, float b, float c, float d) { return fminf(fminf(a, b), fminf(c, d)); }
 
-__global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ TeleaParams P) {
+__global__ void __launch_bounds__(256, 3) telea_kernel(const __grid_constant__ TeleaParams P) {
     cg::grid_group grid = cg::this_grid();
     const int H = P.H, W = P.W, EW = W + 2, EH = H + 2, range = P.range;
     const size_t hw = (size_t)H * W, ehw = (size_t)EH * EW;
@@ -99,9 +99,11 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
     for (size_t e = tid; e < (size_t)P.B * 3 * hw; e += nth) {
         float v = P.img[e];
         v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
-        P.u8[e] = (unsigned char)(int)v;  // .astype(np.uint8): truncation (utils.py:147)
+        const unsigned char u = (unsigned char)(int)v;  // .astype(np.uint8): truncation (utils.py:147)
+        P.u8[e] = u;
+        P.u8o[e] = u;
     }
-    if (tid < 4) P.count[tid] = 0;
+    if (tid < 8) P.count[tid] = 0;
     for (size_t e = tid; e < (size_t)P.B * ehw; e += nth) {
         const int b = (int)(e / ehw);
         const int p = (int)(e - (size_t)b * ehw);
@@ -180,37 +182,47 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
     grid.sync();
 
     // ---- phase 2: inward layers (icvTeleaInpaintFMM) -------------------------------------------------------------------------------------
-    int cur = 0;
+    // ONE grid-wide barrier per layer.  A layer's pixels are computed from the state at the layer's start and committed at once (T, colour,
+    // L = layer, next frontier): that is race-free because a reader never consumes a cell of the current layer - it tests L[q] < layer
+    // first (a cell being committed reads as 0xFFFF or as `layer`, unknown either way), takes T = 1e6 for unknown cells (what they hold at
+    // the layer's start) and, where OpenCV's border index shifts make it read the IMAGE of a cell that is still unknown, takes the cell's
+    // original byte from `u8o` (again what `u8` holds at the layer's start).  Three frontier lists rotate: read k % 3, append (k+1) % 3, and
+    // the counter of (k+2) % 3 - the next layer's append target, untouched during this layer - is zeroed.
     for (unsigned int layer = 1; layer < L_INSIDE; ++layer) {
+        const int cur = (int)((layer - 1) % 3u), nxt = (int)(layer % 3u), zro = (int)((layer + 1) % 3u);
         const unsigned int n = P.count[cur];
         if (n == 0) break;
-        // (a) compute T and colour of every frontier pixel from pixels of earlier layers.  ONE WARP PER PIXEL: the lanes evaluate the
-        //     (2 range + 1)^2 taps in parallel (flags, weights, gradients: the expensive part) into a per-warp shared-memory table; lanes
-        //     0-2 (one per colour) then add the tap contributions in OpenCV's tap order (k outer, l inner), so every float32 sum is
-        //     formed in the same order as the serial code - the result does not depend on the lane layout.  (A thread per pixel ran a
-        //     layer of a few thousand pixels at ~1 warp per SM: 130 us per layer; profiles/r2/inpaint_report_v1_thread_per_pixel.json.)
-        if (tid == 0) P.count[cur ^ 1] = 0;  // nobody reads the other list's counter during this layer; ordered by the barrier below
+        if (tid == 0) P.count[zro] = 0, P.count[3] = layer, P.count[4] += n;
+        // one WARP per pixel: the lanes evaluate the (2 range + 1)^2 taps in parallel (flags, weights, gradients: the expensive part) into a
+        // per-warp shared-memory table; lanes 0-2 (one per colour) then add the tap contributions in OpenCV's tap order (k outer, l inner),
+        // so every float32 sum is formed in the same order as the serial code - the result does not depend on the lane layout.  (A thread per
+        // pixel ran a layer of a few thousand pixels at ~1 warp per SM: 130 us per layer; profiles/r2/inpaint_report_v1_thread_per_pixel.json.)
         for (size_t e = gwarp; e < n; e += nwarps) {
             const int b = (int)P.listb[cur][e];
             const int p = (int)P.list[cur][e];
             const int i = p / EW, j = p - i * EW;
-            const unsigned short* L = P.L + (size_t)b * ehw;
-            const float* T = P.T + (size_t)b * ehw;
-            const unsigned char* I = P.u8 + (size_t)b * 3 * hw;
+            const size_t eb = (size_t)b * ehw;
+            unsigned short* L = P.L + eb;
+            float* T = P.T + eb;
+            unsigned char* I = P.u8 + (size_t)b * 3 * hw;
+            const unsigned char* Io = P.u8o + (size_t)b * 3 * hw;
             auto known = [&](int q) -> bool { return L[q] < layer; };  // f != INSIDE
+            auto Tk = [&](int q) -> float { return known(q) ? T[q] : T_FAR; };
             const int up = p - EW, dn = p + EW, lf = p - 1, rt = p + 1;
-            const float dist = min4(fmm_solve(T[up], known(up), T[lf], known(lf)), fmm_solve(T[dn], known(dn), T[lf], known(lf)),
-                                    fmm_solve(T[up], known(up), T[rt], known(rt)), fmm_solve(T[dn], known(dn), T[rt], known(rt)));
+            const bool k_up = known(up), k_dn = known(dn), k_lf = known(lf), k_rt = known(rt);
+            const float t_up = k_up ? T[up] : T_FAR, t_dn = k_dn ? T[dn] : T_FAR, t_lf = k_lf ? T[lf] : T_FAR, t_rt = k_rt ? T[rt] : T_FAR;
+            const float dist = min4(fmm_solve(t_up, k_up, t_lf, k_lf), fmm_solve(t_dn, k_dn, t_lf, k_lf), fmm_solve(t_up, k_up, t_rt, k_rt),
+                                    fmm_solve(t_dn, k_dn, t_rt, k_rt));
             // gradT (t(i,j) is the value just computed)
             float gx, gy;
-            if (known(rt))
-                gx = known(lf) ? (T[rt] - T[lf]) * 0.5f : (T[rt] - dist);
+            if (k_rt)
+                gx = k_lf ? (t_rt - t_lf) * 0.5f : (t_rt - dist);
             else
-                gx = known(lf) ? (dist - T[lf]) : 0.0f;
-            if (known(dn))
-                gy = known(up) ? (T[dn] - T[up]) * 0.5f : (T[dn] - dist);
+                gx = k_lf ? (dist - t_lf) : 0.0f;
+            if (k_dn)
+                gy = k_up ? (t_dn - t_up) * 0.5f : (t_dn - dist);
             else
-                gy = known(up) ? (dist - T[up]) : 0.0f;
+                gy = k_up ? (dist - t_up) : 0.0f;
             for (int t = lane; t < NT; t += 32) {
                 const int dk = t / D, dl = t - dk * D;
                 const int k = i - range + dk, l = j - range + dl;
@@ -223,31 +235,39 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
                 const int km = k - 1 + (k == 1), kp = k - 1 - (k == EH - 2);
                 const int lm = l - 1 + (l == 1), lp = l - 1 - (l == EW - 2);
                 const float ry = (float)(i - k), rx = (float)(j - l);
-                const float lev = (float)(1. / (1 + fabs((double)(T[q] - dist))));
+                const float lev = (float)(1. / (1 + fabs((double)(Tk(q) - dist))));
                 float dir = rx * gx + ry * gy;
                 if (fabsf(dir) <= 0.01f) dir = 0.000001f;
                 const float w = fabsf(s_dst[t] * lev * dir);
                 const bool kr = known(q + 1), kl = known(q - 1), kd = known(q + EW), ku = known(q - EW);
                 slot[0] = w;
+                // image position (r, col) -> element offset, and whether the cell is known (else its original byte is read); the row /
+                // column clamps only matter for frames with H < 2 or W < 2, where inpaint.cpp's km / lm shifts leave the image
+                auto at = [&](int r, int col, bool& kn) -> size_t {
+                    r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
+                    col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+                    kn = L[(r + 1) * EW + (col + 1)] < layer;
+                    return (size_t)r * W + col;
+                };
+                bool nA, nB, nC, nD, nE, nF, nG;
+                const size_t oA = at(km, lp + 1, nA), oB = at(km, lm - 1, nB), oC = at(km, lm, nC), oD = at(km, lp, nD);
+                const size_t oE = at(kp + 1, lm, nE), oF = at(km - 1, lm, nF), oG = at(kp, lm, nG);
+                const size_t oZ = (size_t)(k - 1) * W + (l - 1);  // the tap's own pixel: known
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const unsigned char* Ic = I + (size_t)c * hw;
-                    // (row / column clamps only matter for frames with H < 2 or W < 2, where inpaint.cpp's km / lm shifts leave the image)
-                    auto px = [&](int r, int col) -> float {
-                        r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
-                        col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
-                        return (float)Ic[(size_t)r * W + col];
-                    };
+                    const unsigned char* Oc = Io + (size_t)c * hw;
+                    auto px = [&](size_t o, bool kn) -> float { return (float)(kn ? Ic[o] : Oc[o]); };
                     float gix, giy;
                     if (kr)
-                        gix = kl ? (px(km, lp + 1) - px(km, lm - 1)) * 2.0f : (px(km, lp + 1) - px(km, lm));
+                        gix = kl ? (px(oA, nA) - px(oB, nB)) * 2.0f : (px(oA, nA) - px(oC, nC));
                     else
-                        gix = kl ? (px(km, lp) - px(km, lm - 1)) : 0.0f;
+                        gix = kl ? (px(oD, nD) - px(oB, nB)) : 0.0f;
                     if (kd)
-                        giy = ku ? (px(kp + 1, lm) - px(km - 1, lm)) * 2.0f : (px(kp + 1, lm) - px(km, lm));
+                        giy = ku ? (px(oE, nE) - px(oF, nF)) * 2.0f : (px(oE, nE) - px(oC, nC));
                     else
-                        giy = ku ? (px(kp, lm) - px(km - 1, lm)) : 0.0f;
-                    slot[1 + c] = w * px(k - 1, l - 1);  // the tap's own pixel; the km / lm shifts apply to the gradients only
+                        giy = ku ? (px(oG, nG) - px(oF, nF)) : 0.0f;
+                    slot[1 + c] = w * (float)Ic[oZ];  // the tap's own pixel; the km / lm shifts apply to the gradients only
                     slot[4 + c] = w * (gix * rx);
                     slot[7 + c] = w * (giy * ry);
                 }
@@ -270,42 +290,28 @@ __global__ void __launch_bounds__(256) telea_kernel(const __grid_constant__ Tele
                 int v = __float2int_rn(sat);  // saturate_cast<uchar>(float): round to nearest even, saturate
                 if (!(sat == sat)) v = 0;
                 byte = (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v));
+                I[(size_t)c * hw + (size_t)(i - 1) * W + (j - 1)] = (unsigned char)byte;  // commit the colour
             }
-            const unsigned int c0 = __shfl_sync(0xFFFFFFFFu, byte, 0), c1 = __shfl_sync(0xFFFFFFFFu, byte, 1), c2 = __shfl_sync(0xFFFFFFFFu, byte, 2);
-            if (lane == 0) {
-                P.stageT[e] = dist;
-                P.stageC[e] = make_uchar4((unsigned char)c0, (unsigned char)c1, (unsigned char)c2, 0);
+            __syncwarp();
+            if (lane == 0) {  // commit T and the layer, enqueue the unfilled 4-neighbours for the next layer
+                T[p] = dist;
+                L[p] = (unsigned short)layer;
+                const int nb[4] = {up, lf, dn, rt};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int q = nb[t];
+                    const int qi = q / EW, qj = q - qi * EW;
+                    if (qi <= 0 || qj <= 0 || qi > EH - 1 || qj > EW - 1) continue;  // inpaint.cpp: (i<=0)||(j<=0)||(i>rows-1)||(j>cols-1)
+                    if (L[q] == L_INSIDE && atomicExch(&P.Q[eb + q], 1u) == 0u) {
+                        const unsigned int slot_n = atomicAdd(&P.count[nxt], 1u);
+                        P.list[nxt][slot_n] = (unsigned int)q;
+                        P.listb[nxt][slot_n] = (unsigned int)b;
+                    }
+                }
             }
             __syncwarp();
         }
         grid.sync();
-        // (b) commit the layer and enqueue its unfilled 4-neighbours for the next one
-        for (size_t e = tid; e < n; e += nth) {
-            const int b = (int)P.listb[cur][e];
-            const int p = (int)P.list[cur][e];
-            const int i = p / EW, j = p - i * EW;
-            const size_t eb = (size_t)b * ehw;
-            P.T[eb + p] = P.stageT[e];
-            P.L[eb + p] = (unsigned short)layer;
-            const uchar4 col = P.stageC[e];
-            unsigned char* I = P.u8 + (size_t)b * 3 * hw + (size_t)(i - 1) * W + (j - 1);
-            I[0] = col.x, I[hw] = col.y, I[2 * hw] = col.z;
-            const int nb[4] = {p - EW, p - 1, p + EW, p + 1};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int q = nb[t];
-                const int qi = q / EW, qj = q - qi * EW;
-                if (qi <= 0 || qj <= 0 || qi > EH - 1 || qj > EW - 1) continue;  // inpaint.cpp: (i<=0)||(j<=0)||(i>rows-1)||(j>cols-1)
-                if (P.L[eb + q] == L_INSIDE && atomicExch(&P.Q[eb + q], 1u) == 0u) {
-                    const unsigned int slot = atomicAdd(&P.count[cur ^ 1], 1u);
-                    P.list[cur ^ 1][slot] = (unsigned int)q;
-                    P.listb[cur ^ 1][slot] = (unsigned int)b;
-                }
-            }
-        }
-        if (tid == 0) P.count[2] = layer, atomicAdd(&P.count[3], n);
-        grid.sync();
-        cur ^= 1;
     }
     // ---- result ------------------------------------------------------------------------------------------------------------------------------
     for (size_t e = tid; e < (size_t)P.B * 3 * hw; e += nth) P.out[e] = (float)P.u8[e];
@@ -323,14 +329,13 @@ size_t ofd_inpaint_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const size_t hw = (size_t)H * W, ehw = (size_t)(H + 2) * (W + 2), nb = (size_t)B;
     size_t n = 256;
-    n += align256(nb * 3 * hw);                 // u8
+    n += 2 * align256(nb * 3 * hw);             // u8, u8o
     n += align256(nb * ehw * 2);                // L
     n += align256(nb * ehw * 4);                // T
     n += align256(nb * ehw);                    // G
     n += align256(nb * ehw * 4);                // Q
-    n += 4 * align256(nb * hw * 4);             // list[2], listb[2]
-    n += align256(nb * ehw * 4);                // stageT (also indexed by extended pixel in the ring march)
-    n += align256(nb * hw * 4);                 // stageC
+    n += 6 * align256(nb * hw * 4);             // list[3], listb[3]
+    n += align256(nb * ehw * 4);                // stageT (indexed by extended pixel in the ring march)
     return n;
 }
 
@@ -352,14 +357,14 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     P.img = img, P.mask = mask, P.out = out, P.B = B, P.H = H, P.W = W, P.range = range;
     P.count = (unsigned int*)w, w += 256;
     P.u8 = w, w += align256(nb * 3 * hw);
+    P.u8o = w, w += align256(nb * 3 * hw);
     P.L = (unsigned short*)w, w += align256(nb * ehw * 2);
     P.T = (float*)w, w += align256(nb * ehw * 4);
     P.G = w, w += align256(nb * ehw);
     P.Q = (unsigned int*)w, w += align256(nb * ehw * 4);
-    for (int k = 0; k < 2; ++k) P.list[k] = (unsigned int*)w, w += align256(nb * hw * 4);
-    for (int k = 0; k < 2; ++k) P.listb[k] = (unsigned int*)w, w += align256(nb * hw * 4);
+    for (int k = 0; k < 3; ++k) P.list[k] = (unsigned int*)w, w += align256(nb * hw * 4);
+    for (int k = 0; k < 3; ++k) P.listb[k] = (unsigned int*)w, w += align256(nb * hw * 4);
     P.stageT = (float*)w, w += align256(nb * ehw * 4);
-    P.stageC = (uchar4*)w, w += align256(nb * hw * 4);
     int sms = 0, per_sm = 0;
     const int NT = (2 * range + 1) * (2 * range + 1);
     const size_t smem = ((size_t)((NT + 3) & ~3) + (size_t)8 * NT * 11) * sizeof(float);  // dst table + 8 warps x NT taps x 11 floats
@@ -380,7 +385,7 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)telea_kernel, dim3((unsigned)blocks), dim3(256), args, smem, st);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchCooperativeKernel: %s", fn, cudaGetErrorString(e));
     if (stats_host_or_null) {  // layers marched / pixels filled: a synchronising read, for tests and reports only
-        e = cudaMemcpyAsync(stats_host_or_null, P.count + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(stats_host_or_null, P.count + 3, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail((int)e, "%s: %s", fn, cudaGetErrorString(e));
     }

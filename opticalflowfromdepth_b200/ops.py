@@ -129,8 +129,9 @@ def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
 
 
 @_on_device
-def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None):
-    """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32."""
+def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None, want_collision=True):
+    """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32.
+    want_collision=False skips the collision plane (returned as None): 4 B/px less for callers that only use valid."""
     _check("obj", obj, dtype=torch.float32)
     if obj.dim() != 4:
         raise ValueError("obj must be [B,C,H,W]")
@@ -141,7 +142,7 @@ def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False,
         _check("aux", aux, dtype=torch.float32, shape=(B, Cc, H, W))
     out = torch.empty_like(obj)
     valid = torch.empty_like(depth)
-    collision = torch.empty_like(depth)
+    collision = torch.empty_like(depth) if want_collision else None
     winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
     ws = workspace.get(obj.device, B, H, W)
     _run_splat("ofd_splat_flow", obj.device, _ptr(obj), _ptr(flow), _DT[flow.dtype], _ptr(depth), B, Cc, H, W,

@@ -488,24 +488,25 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         return _synthesize_group_f64(img0, depth0, sBf, cam, inpaint, counters)
     dev = img0.device
     fill = (lambda im, v, c: im) if inpaint is None else inpaint
+    wc = inpaint is not None  # the collision planes only feed utils.inpaint's mask: without a fill they are not produced (4 B/px per splat)
     with torch.cuda.device(dev):
         # pair 0->1: virtual stereo (preprocess.py:356-366)
-        img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, True, counters)
+        img1, depth1, back01, flow01, valid1, coll1 = ops.disparity_pair(img0, depth0, sBf, True, wc, counters)
         img1 = fill(img1, valid1, coll1)
         # pair 1->2: random camera motion from view 1 (preprocess.py:372-382); flow computed inside the z-test
-        img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
+        img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, want_collision=wc, counters=counters)
         img2 = fill(img2, valid2, coll2)
         # pair 0->3: the same motion from view 0 (preprocess.py:385-394)
-        img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, counters=counters)
+        img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, want_collision=wc, counters=counters)
         img3 = fill(img3, valid3, coll3)
         # pair 0->2': concatenated flow (preprocess.py:400-411)
-        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01)
-        img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, counters=counters)
+        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False)
+        img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
         img2p = fill(img2p, valid2p, coll2p)
         # pair 1->3': (preprocess.py:414-424)
-        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
+        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False)
         flow13_valid = flow13_valid * valid1
-        img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, counters=counters)
+        img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
         img3p = fill(img3p, valid3p, coll3p)
     return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,
                 img2_prime=img2p, depth2_prime=depth2p, img3_prime=img3p, depth3_prime=depth3p,

@@ -749,6 +749,28 @@ def test_bilateral_mask_path_sizes_vs_oracle(pkg):
             assert np.array_equal(got, want, equal_nan=True), (h, w, kind)
 
 
+def test_bilateral_tma_tile_load_variant_is_bit_identical(pkg):
+    """OFD_BIL_TMA=1 (experiment, VERDICT r1 next #7b): the raw tile arrives by cp.async.bulk.tensor.2d tensor-map copies instead of
+    per-thread loads; same results as the default path on interior and border tiles, windows 3 / 5 / 7, with depth_orig == 0 pixels next
+    to the image border (out-of-image cells are zero-filled by the TMA unit and must not count as forced discontinuities)."""
+    import os
+
+    for h, w in ((96, 128), (70, 44), (33, 36)):
+        _, depth = pkg.synthetic.redweb_frame(2, h, w)
+        d = pkg.ops.normalize_depth(cu(depth)[None])[0, 0].contiguous()
+        d[0:3, 0:4] = 0
+        d[h - 1, w - 5:] = 0
+        d[h // 2, w // 2] = 0
+        for win in (7, 5, 3):
+            want = pkg.ops.bilateral_iter(d, d, win, 0.04)
+            os.environ["OFD_BIL_TMA"] = "1"
+            try:
+                got = pkg.ops.bilateral_iter(d, d, win, 0.04)
+            finally:
+                del os.environ["OFD_BIL_TMA"]
+            assert torch.equal(got, want), (h, w, win)
+
+
 def test_bilateral_redweb_size_vs_oracle(pkg):
     (h, w), = pkg.synthetic.redweb_sizes(1, seed=3)
     _, depth = pkg.synthetic.redweb_frame(0, h, w)
@@ -1400,11 +1422,17 @@ def test_device_loaders_jpeg_decode_and_redweb_items(pkg, tmp_path):
     (root / "RDs").mkdir()
     rng = np.random.default_rng(4)
     names = []
-    for k, (h, w, dh, dw, q) in enumerate(((240, 320, 240, 320, 95), (301, 403, 150, 200, 85), (128, 96, 128, 96, 75))):
+    # (h, w, depth h, depth w, JPEG quality, chroma sampling): 4:4:4 isolates the IDCT difference between the decoders; 4:2:0 (cv2's and
+    # most cameras' default) adds the chroma up-sampling filter, where libjpeg-turbo ("fancy" triangle filter) and nvJPEG differ most
+    specs = ((240, 320, 240, 320, 95, "444"), (301, 403, 150, 200, 85, "420"), (128, 96, 128, 96, 75, "420"))
+    for k, (h, w, dh, dw, q, samp) in enumerate(specs):
         y, x = np.mgrid[0:h, 0:w]
-        img = np.stack([(x * 2 + y) % 256, 128 + 100 * np.sin(x / 23.0) * np.cos(y / 17.0), (x + 3 * y) % 256], -1)
-        img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
-        cv2.imwrite(str(root / "Imgs" / f"f{k}.jpg"), img, [cv2.IMWRITE_JPEG_QUALITY, q])
+        img = np.stack([128 + 90 * np.sin(x / 37.0 + y / 53.0), 128 + 100 * np.sin(x / 23.0) * np.cos(y / 17.0), 100 + 80 * np.cos(y / 41.0)], -1)
+        img = np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+        flags = [cv2.IMWRITE_JPEG_QUALITY, q]
+        if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+            flags += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444 if samp == "444" else cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420]
+        cv2.imwrite(str(root / "Imgs" / f"f{k}.jpg"), img, flags)
         yy, xx = np.mgrid[0:dh, 0:dw]
         rel = np.clip(120 + 100 * np.sin(xx / 31.0) + 30 * np.cos(yy / 11.0), 0, 255).astype(np.uint8)
         cv2.imwrite(str(root / "RDs" / f"f{k}.png"), rel)
@@ -1417,8 +1445,13 @@ def test_device_loaders_jpeg_decode_and_redweb_items(pkg, tmp_path):
         ref_img = torch.from_numpy(cv2.imread(str(root / "Imgs" / f"f{k}.jpg"), -1)).type(torch.float32).permute(2, 0, 1)  # utils.py:17-25
         assert img.is_cuda and img.dtype == torch.float32 and tuple(img.shape) == tuple(ref_img.shape)
         d = (img.cpu() - ref_img).abs()
-        print(f"[jpeg] frame {k}: nvJPEG vs cv2 mean |d| {float(d.mean()):.3f} levels, > 3 levels {float((d > 3).float().mean()):.4f}, max {float(d.max()):.0f}")
-        assert float(d.mean()) <= 1.0 and float((d > 3).float().mean()) <= 0.01
+        print(f"[jpeg] frame {k} ({specs[k][5]}, q{specs[k][4]}): nvJPEG vs cv2 mean |d| {float(d.mean()):.3f} levels, > 3 levels {float((d > 3).float().mean()):.4f}, max {float(d.max()):.0f}")
+        # stated bound: 4:4:4 (IDCT rounding only) mean <= 1 level and <= 1 % of the bytes off by more than 3; 4:2:0 adds the decoders'
+        # different chroma up-sampling: mean <= 3 levels
+        if specs[k][5] == "444" and hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+            assert float(d.mean()) <= 1.0 and float((d > 3).float().mean()) <= 0.01
+        else:
+            assert float(d.mean()) <= 3.0
         ref_d = cv2.imread(str(root / "RDs" / f"f{k}.png"), cv2.IMREAD_GRAYSCALE).astype(float)                          # utils.py:48
         ref_d[ref_d > 240] = 240
         with np.errstate(divide="ignore"):
@@ -1759,7 +1792,7 @@ def test_bench_cfg5_legs_small(pkg):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     g = d["group_480x640"]
     assert "error" not in g, g
-    assert g["frames_per_rank"] >= 32 and g["algorithmic_bytes_per_px"] == 388 and 0 < g["frac_of_measured_peak"] < 1.0
+    assert g["frames_per_rank"] >= 32 and g["algorithmic_bytes_per_px"] == 368 and 0 < g["frac_of_measured_peak"] < 1.0
     assert g["counters"]["pairs"] == 5 * g["counters"]["frames"]
     sw = d["cfg5_sweep_e2e"]
     assert "error" not in sw, sw
