@@ -187,8 +187,11 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int win = WS > 0 ? WS : win_rt;
     const int m = win / 2;
-    // raw tile: window halo + a ring of 2 (neighbour differences + clamping); the TMA box is padded to a multiple of 16 bytes per row
-    const int RW = TMA ? ((BT_W + 2 * m + 4 + 3) & ~3) : BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4;
+    // raw tile: window halo + a ring of 2 (neighbour differences + clamping).  A TMA box must START on a 16-byte boundary of the tensor row
+    // and span a multiple of 16 bytes (an unaligned start coordinate raises an illegal-instruction fault: tools/probes/tma_probe.cu), so the
+    // TMA variant widens the tile by LP columns on the left and rounds the row up to a multiple of 4 floats; CX = first window-tile column
+    const int LP = TMA ? (4 - ((m + 2) & 3)) & 3 : 0, CX = 2 + LP;
+    const int RW = TMA ? ((BT_W + 2 * m + 4 + LP + 3) & ~3) : BT_W + 2 * m + 4, RH = BT_H + 2 * m + 4;
     const int TW = BT_W + 2 * m, TH = BT_H + 2 * m;          // window tile
     const int CELLS_P = TMA ? ((RW * RH + 31) & ~31) : RW * RH;  // TMA destinations start on 128-byte boundaries
     DT* sraw = reinterpret_cast<DT*>(smem_raw);               // raw depth
@@ -205,7 +208,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     constexpr int nthr = BT_W * BT_TY;
     if (tid == 0) s_count = 0;
     if (tid <= MAX_WIN * MAX_WIN) s_k[tid] = kr.k[tid];
-    const int r0 = tile_y * BT_H - m - 2, c0 = tile_x * BT_W - m - 2;  // raw coordinate of raw-tile cell (0,0)
+    const int r0 = tile_y * BT_H - m - 2, c0 = tile_x * BT_W - m - 2 - LP;  // raw coordinate of raw-tile cell (0,0)
 
     // 1. raw tile: depth, 1/depth, depth_orig == 0 (zero outside the image; those cells are never consumed).  For a
     //    compile-time window all global loads of a thread are issued before the first use.
@@ -325,14 +328,14 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
     // 3. the reference's border rule (:141-147): every tap reads row clamp(r,1,H-2), column clamp(c,1,W-2).  A tile whose
     //    window tile lies inside [1,H-2] x [1,W-2] needs no clamping: its taps read the raw tile in place.  Only tiles
     //    on the image border run the replication pass.
-    const bool interior = (r0 + 2 >= 1) && (r0 + 2 + TH - 1 <= H - 2) && (c0 + 2 >= 1) && (c0 + 2 + TW - 1 <= W - 2);
-    const DT* wdep = sraw + 2 * RW + 2;             // window-tile cell (tr,tc) -> wdep[tr * wstride + tc]
-    const unsigned char* wdisc = sflag + 2 * RW + 2;  // non-zero = discontinuity
+    const bool interior = (r0 + 2 >= 1) && (r0 + 2 + TH - 1 <= H - 2) && (c0 + CX >= 1) && (c0 + CX + TW - 1 <= W - 2);
+    const DT* wdep = sraw + 2 * RW + CX;             // window-tile cell (tr,tc) -> wdep[tr * wstride + tc]
+    const unsigned char* wdisc = sflag + 2 * RW + CX;  // non-zero = discontinuity
     int wstride = RW;
     if (!interior) {  // block-uniform
         for (int e = tid; e < TW * TH; e += nthr) {
             const int tr = e / TW, tc = e - tr * TW;
-            int r = r0 + 2 + tr, c = c0 + 2 + tc;
+            int r = r0 + 2 + tr, c = c0 + CX + tc;
             r = r < 1 ? 1 : (r > H - 2 ? H - 2 : r);
             c = c < 1 ? 1 : (c > W - 2 ? W - 2 : c);
             const int src = (r - r0) * RW + (c - c0);
@@ -354,7 +357,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
             if (lane == 0) s_rowmask[tr] = ((unsigned long long)hi << 32) | lo;
             if constexpr (MASK) {
                 // the mask of a tap is read at its OWN coordinates (raw cell tr + 2, tc + 2), never ring-replicated
-                const unsigned char* mrow = sflag + (tr + 2) * RW + 2;
+                const unsigned char* mrow = sflag + (tr + 2) * RW + CX;
                 const unsigned xlo = __ballot_sync(0xFFFFFFFFu, d_lo || !(mrow[lane] & 4));
                 const unsigned xhi = __ballot_sync(0xFFFFFFFFu, (32 + lane < TW) && (d_hi || !(mrow[32 + lane] & 4)));
                 if (lane == 0) s_rowexcl[tr] = ((unsigned long long)xhi << 32) | xlo;
@@ -410,7 +413,7 @@ __device__ __forceinline__ void bilateral_tile(const DT* __restrict__ din, const
         const bool inside = r < H && c < W;
         bool need = inside && n_disc_row[rr] > 0 && n_disc_row[rr] < win * win;
         if constexpr (MASK)  // masked pixels are skipped (:169-170); the median needs at least one tap that is neither (:188-190)
-            need = inside && n_disc_row[rr] > 0 && n_excl_row[rr] < win * win && (sflag[(ty + m + 2) * RW + threadIdx.x + m + 2] & 4) != 0;
+            need = inside && n_disc_row[rr] > 0 && n_excl_row[rr] < win * win && (sflag[(ty + m + 2) * RW + threadIdx.x + m + CX] & 4) != 0;
         if (inside && !need) dout[(size_t)r * W + c] = wdep[(ty + m) * wstride + threadIdx.x + m];
         const unsigned lane = tid & 31u;
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
@@ -514,7 +517,8 @@ static bool launch_bilateral_tma(const float* din, const float* dorig, int H, in
     pfn_cuTensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc || W % 4 != 0 || (((uintptr_t)din | (uintptr_t)dorig) & 15)) return false;
     constexpr int m = WS / 2;
-    constexpr int RW = (BT_W + 2 * m + 4 + 3) & ~3, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
+    constexpr int LP = (4 - ((m + 2) & 3)) & 3;
+    constexpr int RW = (BT_W + 2 * m + 4 + LP + 3) & ~3, RH = BT_H + 2 * m + 4, TW = BT_W + 2 * m, TH = BT_H + 2 * m;
     constexpr int CELLS_P = (RW * RH + 31) & ~31;
     CUtensorMap maps[2];
     const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)H};
