@@ -20,8 +20,13 @@
 //      odd-even merge-sort network over exactly 9/25/49 keys (28/140/394 compare-exchanges of 2 FMNMX each; the half of the
 //      outputs that can never be selected is dead code); other window sizes use a rank count in shared memory.
 // Variants: a ragged batch (one launch for images of different sizes) and the reference's binary-mask path.
-// The kernel is instruction-bound, not HBM-bound; a TMA 2-D tiled load for step 1 (the north star
-// suggests it) would not change that: a 42x42 float tile is 7 plain coalesced loads per thread and needs no tensor map.
+// The kernel is instruction-bound, not HBM-bound.  The north star's "TMA-loaded halo tiles" were built and MEASURED
+// (OFD_BIL_TMA=1: both raw tiles by cp.async.bulk.tensor.2d, SASS UTMALDG, 1/d and forced flags formed in a pass over shared memory;
+// bit-identical): 5 iterations on one dense frame take 0.124 ms against 0.117 ms at 1080p (6 % slower) and 0.345 against 0.368 ms at
+// 2160x3840 (6 % faster) - profiles/r2/tune_bilateral_tma.txt.  The per-thread loads it replaces are 7-8 coalesced LDGs per thread whose
+// address arithmetic is a few instructions per cell; the TMA variant trades them for a second pass over shared memory, a wider tile (the box
+// must start on a 16-byte boundary of the row: 48 instead of 42 columns at window 7) and one tensor map per image (ragged batches would need
+// one per frame).  A wash: the SIMT staging stays the default, the TMA path stays behind OFD_BIL_TMA for dense float32 frames.
 #include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 #include <cstdlib>
