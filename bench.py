@@ -627,6 +627,21 @@ def run_ours(args):
             line["cpu_baseline"]["geometry_6dof_flow_480x640_ms"] = 1e3 * t_geo
             line["cpu_baseline"]["bilateral_5iter_480x640_ms"] = 1e3 * t_bil
             line["cpu_baseline"]["geometry_bilateral_kind"] = f"port: torch CPU ops, {cores} threads / vectorised numpy, 1 thread"
+            # the reference's OWN sparse_bilateral_filtering (bilateral_filter.py:13-60, per-pixel Python loop, staged
+            # unmodified in baseline/_ref by build()), one 480x640 frame, 5 iterations - a bounded sample of a few seconds
+            ref_bil_path = ROOT / "baseline" / "_ref" / "bilateral_filter.py"
+            if ref_bil_path.exists():
+                import importlib.util
+
+                spec = importlib.util.spec_from_file_location("ref_bilateral_filter", str(ref_bil_path))
+                ref_bil = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(ref_bil)
+                t0 = time.perf_counter()
+                ref_out = ref_bil.sparse_bilateral_filtering(cd[0, 0].copy(), np.zeros((H, W, 3), np.uint8), [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5)
+                line["cpu_baseline"]["reference_numpy_bilateral_5iter_480x640_ms"] = 1e3 * (time.perf_counter() - t0)
+                from opticalflowfromdepth_b200 import bilateral_filter as bfm2
+                ours = bfm2.sparse_bilateral_filtering(torch.from_numpy(cd[0, 0]).to(dev).contiguous(), None, [7, 7, 5, 5, 5], depth_threshold=0.04, num_iter=5)
+                line["cpu_baseline"]["reference_numpy_bilateral_equals_cuda"] = bool(np.array_equal(np.asarray(ref_out, dtype=np.float32), ours.cpu().numpy()))
         except Exception as e:  # secondary
             line["cpu_baseline"]["geometry_bilateral_error"] = repr(e)
 
