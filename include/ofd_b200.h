@@ -96,6 +96,15 @@ int ofd_splat_targets(const void* obj, const void* safe_y, const void* safe_x, c
 int ofd_splat_flow(const float* obj, const void* flow, int flow_dtype, const float* depth, int B, int C, int H,
                    int W, float* out, float* valid, float* collision, int32_t* winner, int epilogue,
                    const float* aux, uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+/*
+ * ofd_splat_flow_rows — ofd_splat_flow for a HORIZONTAL warp flow: the caller guarantees flow[:,1] == +-0 everywhere (it is not read), as
+ * the pipeline's disparity flows flow01 / back_flow01 are by construction (preprocess.py:253,361-363) - the warp flow of the two ConcatFlow
+ * splats of a frame group (preprocess.py:400,414).  Sources then stay in their row: the z-buffer of a row lives in shared memory (two
+ * 32-bit shared-memory atomicMin passes = the serial loop's winner), no global atomics, no key workspace, ONE launch, 40 B/px instead of
+ * 72 for a ConcatFlow.  float32 only, C == 2 (flow payloads), W <= 2048; same results as ofd_splat_flow on such flows (tested bit for bit).
+ */
+int ofd_splat_flow_rows(const float* obj, const float* flow, const float* depth, int B, int C, int H, int W, float* out,
+                        float* valid, float* collision /*nullable*/, int epilogue, const float* aux, ofd_stream_t stream);
 
 /*
  * ofd_disparity_flow — Convert.depth_to_disparity + disparity_to_flow(random_sign=False)

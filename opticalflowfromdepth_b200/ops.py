@@ -129,9 +129,11 @@ def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
 
 
 @_on_device
-def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None, want_collision=True):
+def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None, want_collision=True, horizontal=False):
     """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32.
-    want_collision=False skips the collision plane (returned as None): 4 B/px less for callers that only use valid."""
+    want_collision=False skips the collision plane (returned as None): 4 B/px less for callers that only use valid.
+    horizontal=True is the caller's promise that flow[:,1] is +-0 everywhere (the pipeline's disparity flows): C == 2 float32 splats
+    then take the row-local shared-memory kernel (ofd_splat_flow_rows: one launch, no key plane); anything else ignores the hint."""
     _check("obj", obj, dtype=torch.float32)
     if obj.dim() != 4:
         raise ValueError("obj must be [B,C,H,W]")
@@ -143,6 +145,10 @@ def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False,
     out = torch.empty_like(obj)
     valid = torch.empty_like(depth)
     collision = torch.empty_like(depth) if want_collision else None
+    if horizontal and Cc == 2 and flow.dtype == torch.float32 and not want_winner and counters is None and W <= 2048 and H <= 65535 and B <= 65535:
+        _lib.call("ofd_splat_flow_rows", _ptr(obj), _ptr(flow), _ptr(depth), B, Cc, H, W, _ptr(out), _ptr(valid), _ptr(collision),
+                  int(epilogue), _ptr(aux), _stream(obj.device))
+        return out, valid, collision
     winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
     ws = workspace.get(obj.device, B, H, W)
     _run_splat("ofd_splat_flow", obj.device, _ptr(obj), _ptr(flow), _DT[flow.dtype], _ptr(depth), B, Cc, H, W,

@@ -500,11 +500,13 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, want_collision=wc, counters=counters)
         img3 = fill(img3, valid3, coll3)
         # pair 0->2': concatenated flow (preprocess.py:400-411)
-        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False)
+        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False,
+                                                    horizontal=True)  # back01.y == +0: row-local kernel, unless counters ask for the tie census
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
         img2p = fill(img2p, valid2p, coll2p)
         # pair 1->3': (preprocess.py:414-424)
-        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False)
+        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False,
+                                                    horizontal=True)  # flow01.y == -0
         flow13_valid = flow13_valid * valid1
         img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
         img3p = fill(img3p, valid3p, coll3p)

@@ -83,3 +83,26 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+@pytest.mark.parametrize("name,args,code", [
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 6, 4, 4, 1, 1, None, 0, None, None), -2),                       # C != 2
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4096, 1, 1, None, 0, None, None), -2),                    # W > 2048
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4, 1, 1, None, 1, None, None), -1),                       # concat without aux
+    ("ofd_inpaint_telea", (1, 1, 1, 8, 8, 9, 1, 256, 1 << 20, None, None), -4),                          # range 9
+    ("ofd_inpaint_telea", (1, 1, 1, 8, 8, 3, 1, 256, 16, None, None), -5),                               # workspace too small
+    ("ofd_inpaint_telea", (None, 1, 1, 8, 8, 3, 1, 256, 1 << 20, None, None), -1),                       # NULL image
+    ("ofd_copy_rows_to_host", (1, 8, 1, 16, 32, 2, None), -4),                                           # pitch < width
+    ("ofd_resize_bilinear_aa", (1, 5, 1, 4, 4, 8, 8, 1, 1, None), -3),                                   # bad dtype
+    ("ofd_resize_bilinear_aa", (1, 0, 1, 4, 4, 8, 8, 1, None, None), -1),                                # two-axis resize without tmp
+    ("ofd_resize_bilinear_aa", (1, 0, 1, 4, 4, 0, 8, 1, 1, None), -2),                                   # empty output
+    ("ofd_pair_pipeline_run_flags", (None, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0), -1),                        # NULL pipeline
+])
+def test_round2_entry_points_reject_bad_arguments(name, args, code):
+    """The entry points added in round 2 validate before touching CUDA (no GPU needed)."""
+    lib = _lib.load()
+    fn = getattr(lib, name)
+    conv = []
+    for a, t in zip(args, fn.argtypes):
+        conv.append(None if a is None and t in (C.c_void_p,) else a)
+    assert fn(*conv) == code, lib.ofd_last_error_string()

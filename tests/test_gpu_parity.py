@@ -270,6 +270,40 @@ def test_against_the_reference_fw_forward_at_baseline_sizes(pkg, h, w, C):
     assert 0.3 < float(r_valid.mean()) < 1.0 and out.shape == (C, h, w)
 
 
+def test_splat_flow_rows_equals_the_general_path(pkg):
+    """ofd_splat_flow_rows (row-local shared-memory z-buffer for horizontal warp flows: the two ConcatFlow splats of a frame group) against
+    the packed-key path on the same inputs: output, valid and collision bit-exact for the three epilogues - ties (quantised depths), sources
+    that cannot win (depth >= 1000, NaN depth), NaN flow (dropped), flows that leave the row on both sides (clamped pile-ups), -0.0 / +0.0
+    y planes, widths up to the 2048 limit, one-pixel frames."""
+    rng = np.random.default_rng(17)
+    for (b, h, w) in ((2, 480, 640), (3, 37, 53), (1, 5, 2048), (2, 3, 1), (1, 64, 7)):
+        obj = cu(rng.normal(0, 20, (b, 2, h, w)).astype(np.float32))
+        aux = cu(rng.normal(0, 20, (b, 2, h, w)).astype(np.float32))
+        fx = rng.normal(0, 30, (b, 1, h, w)).astype(np.float32)
+        fx[rng.random(fx.shape) < 0.02] *= 100          # far out of the row: clamped to the borders
+        fx[rng.random(fx.shape) < 0.01] = np.nan        # dropped sources
+        fy = np.where(rng.random(fx.shape) < 0.5, np.float32(-0.0), np.float32(0.0)).astype(np.float32)
+        flow = cu(np.concatenate([fx, fy], 1))
+        depth = rng.integers(1, 6, (b, 1, h, w)).astype(np.float32)   # quantised: many ties
+        depth[rng.random(depth.shape) < 0.03] = 1000.0                # hit but cannot win -> collision where alone
+        depth[rng.random(depth.shape) < 0.01] = np.nan
+        depth = cu(depth)
+        for epi, ax in ((pkg.ops.EPI_NONE, None), (pkg.ops.EPI_CONCAT, aux), (pkg.ops.EPI_BACK, None)):
+            want = pkg.ops.splat_flow(obj, flow, depth, epilogue=epi, aux=ax)
+            got = pkg.ops.splat_flow(obj, flow, depth, epilogue=epi, aux=ax, horizontal=True)
+            for g, wnt, name in zip(got, want, ("out", "valid", "collision")):
+                assert np.array_equal(g.cpu().numpy(), wnt.cpu().numpy(), equal_nan=True), (b, h, w, epi, name)
+            got2 = pkg.ops.splat_flow(obj, flow, depth, epilogue=epi, aux=ax, horizontal=True, want_collision=False)
+            assert got2[2] is None and torch.equal(got2[1], want[1])
+        assert float(want[2].sum()) > 0 or h * w < 50
+    # the hint is ignored where the kernel does not apply (C != 2, float64 flow)
+    obj6 = torch.rand(1, 6, 8, 16, device=DEV)
+    fl = torch.zeros(1, 2, 8, 16, device=DEV)
+    dp = torch.ones(1, 1, 8, 16, device=DEV)
+    a = pkg.ops.splat_flow(obj6, fl, dp, horizontal=True)
+    assert torch.equal(a[0], obj6)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # fused virtual-stereo pair
 # ---------------------------------------------------------------------------------------------------------------
