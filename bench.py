@@ -556,15 +556,20 @@ def run_ours(args):
             pipe.run(h_img, h_depth, h_s, *h_out, keep_const_planes=True)
         tk = max_over_ranks(time.perf_counter() - t0)
         pipe.close()
+        img_bytes = os.environ.get("OFD_HOST_IMG_BYTES", "1") != "0" and os.environ.get("OFD_HOST_MASK_BYTES", "1") != "0"
+        # what crosses PCIe down per pixel: depth1, back_flow.x, flow.x as float planes (12 B), valid|collision as one packed byte, and
+        # img1 as 3 bytes (the frames are uint8-valued like the reference's loader output; verified on the device per chunk) or 12
+        d2h_px = 12 + 1 + (3 if img_bytes else 12)
         line["e2e"] = {"value": world * Fe * Ke / te, "unit": "pairs/s",
-                       "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * (6 * H * W * 4 + H * W),
-                       "host_filled_bytes_per_step": Fe * 4 * H * W * 4,
+                       "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * d2h_px * H * W,
+                       "host_filled_bytes_per_step": Fe * (4 + (3 if img_bytes else 0)) * H * W * 4,
                        "frames_per_step": Fe, "steps": Ke, "host_cores_per_rank": len(cores_mine),
                        "host_workers": int(os.environ.get("OFD_HOST_WORKERS", "2")),
                        "recycled_buffers_value": world * Fe * Ke / tk,
                        "api": "ofd_pair_pipeline_run (C ABI, pinned float32 host buffers in and out - all 10 result planes, 3-slot H2D/kernel/D2H pipeline; "
                               "the two constant planes flow.y / back_flow.y are written by the pipeline's persistent host threads instead of crossing PCIe, "
-                              "valid / collision cross as one packed byte per pixel and are expanded into the float planes by the same threads; every rank is "
+                              "valid / collision cross as one packed byte per pixel and img1 - uint8-valued whenever img0 is, checked on the device chunk by chunk, "
+                              "float planes otherwise - as three bytes per pixel, all widened into the caller's float planes by the same threads; every rank is "
                               "pinned to its own core slice).  recycled_buffers_value: OFD_PIPE_KEEP_CONST_PLANES (constant planes left as the previous run wrote them)"}
 
     if "e2e" not in skip and "compact" not in skip:

@@ -17,9 +17,10 @@
 struct ofd_host_job {
     int B = 0, K = 0, chunk = 0;
     size_t hw = 0;
-    bool mask_bytes = false, fill_const = true;
-    float *back_flow = nullptr, *flow = nullptr, *valid = nullptr, *collision = nullptr;
+    bool mask_bytes = false, fill_const = true, img_bytes = false;
+    float *back_flow = nullptr, *flow = nullptr, *valid = nullptr, *collision = nullptr, *img1 = nullptr;
     const unsigned char* h_mask = nullptr;
+    const unsigned char* h_img8 = nullptr;
     const cudaEvent_t* ev = nullptr;
 };
 
@@ -36,6 +37,16 @@ struct ofd_pair_pipeline {
     // expanded into the caller's float planes by host threads (grow-only, B * H * W bytes)
     unsigned char* h_mask;
     size_t h_mask_cap;
+    // img1 is a selection of img0's pixels (or 0): when img0 holds uint8 values - what the reference's loader delivers (cv2.imread ->
+    // float32, utils.py:17-25) - img1 does too, and its three planes cross PCIe as bytes (3 instead of 12 B/px) and are widened into the
+    // caller's float planes by the host threads.  OPTIMISTIC and VERIFIED: the packing kernel flags every chunk that holds a value a byte
+    // cannot carry exactly; such chunks are redone with float planes at the end of the run and the pipeline stops trying (img_bytes_ok).
+    unsigned char* h_img8;
+    size_t h_img8_cap;
+    int* h_flags;
+    size_t h_flags_cap;
+    int* d_flags[NSLOT];
+    bool img_bytes_enabled, img_bytes_ok;
     std::vector<cudaEvent_t> ev;  // one per chunk of a run: "this chunk's mask bytes have landed"
     bool mask_bytes_enabled;
     bool spin_sync;  // default: spinning event waits; OFD_HOST_SYNC=block uses blocking-sync events (sleeping waits, ~4 % slower)
@@ -60,6 +71,23 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const unsigned char* __r
 __global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (unsigned char)__float2uint_rn(fminf(fmaxf(in[i], 0.0f), 255.0f));
+}
+// float planes -> bytes, four values per thread; *flag is raised when a value is not exactly a uint8 (the chunk is then redone as floats)
+__global__ void __launch_bounds__(256) pack_img_u8_kernel(const float4* __restrict__ in, uchar4* __restrict__ out, size_t n4, int* __restrict__ flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        uchar4 o;
+        o.x = (unsigned char)(int)fminf(fmaxf(v.x, 0.0f), 255.0f);
+        o.y = (unsigned char)(int)fminf(fmaxf(v.y, 0.0f), 255.0f);
+        o.z = (unsigned char)(int)fminf(fmaxf(v.z, 0.0f), 255.0f);
+        o.w = (unsigned char)(int)fminf(fmaxf(v.w, 0.0f), 255.0f);
+        // exact round trip, bit pattern included (-0.0f would come back as +0.0f)
+        bad |= __float_as_uint((float)o.x) != __float_as_uint(v.x) || __float_as_uint((float)o.y) != __float_as_uint(v.y) ||
+               __float_as_uint((float)o.z) != __float_as_uint(v.z) || __float_as_uint((float)o.w) != __float_as_uint(v.w);
+        out[i] = o;
+    }
+    if (bad) *flag = 1;
 }
 // valid (bit 0) and collision (bit 1) of four pixels per thread
 __global__ void __launch_bounds__(256) pack_masks_kernel(const float4* __restrict__ valid, const float4* __restrict__ collision,
@@ -108,6 +136,23 @@ static void expand_plane(const unsigned char* m, size_t n, int shift, float* dst
     _mm_sfence();
 }
 
+// 16 bytes -> 16 floats, non-temporal stores (dst 16-byte aligned)
+static void widen_plane(const unsigned char* m, size_t n, float* dst) {
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15)) dst[i] = (float)m[i], ++i;
+    const __m128i z = _mm_setzero_si128();
+    for (; i + 16 <= n; i += 16) {
+        const __m128i b = _mm_loadu_si128((const __m128i*)(m + i));
+        const __m128i lo = _mm_unpacklo_epi8(b, z), hi = _mm_unpackhi_epi8(b, z);
+        _mm_stream_ps(dst + i, _mm_cvtepi32_ps(_mm_unpacklo_epi16(lo, z)));
+        _mm_stream_ps(dst + i + 4, _mm_cvtepi32_ps(_mm_unpackhi_epi16(lo, z)));
+        _mm_stream_ps(dst + i + 8, _mm_cvtepi32_ps(_mm_unpacklo_epi16(hi, z)));
+        _mm_stream_ps(dst + i + 12, _mm_cvtepi32_ps(_mm_unpackhi_epi16(hi, z)));
+    }
+    for (; i < n; ++i) dst[i] = (float)m[i];
+    _mm_sfence();
+}
+
 static int env_int(const char* name, int dflt, int lo, int hi) {
     const char* e = getenv(name);
     if (!e || !*e) return dflt;
@@ -145,6 +190,11 @@ static void worker_body(ofd_pair_pipeline* p, int t, const ofd_host_job& J) {
             const size_t o = (size_t)b0 * J.hw + lo;
             expand_plane(J.h_mask + o, hi - lo, 0, J.valid + o);
             if (J.collision) expand_plane(J.h_mask + o, hi - lo, 1, J.collision + o);
+        }
+        if (J.img_bytes) {  // this worker's share of the chunk's 3 * n * hw image bytes
+            const size_t len3 = 3 * len, per3 = ((len3 + nw - 1) / nw + 15) & ~(size_t)15;
+            const size_t lo3 = per3 * t < len3 ? per3 * t : len3, hi3 = lo3 + per3 < len3 ? lo3 + per3 : len3;
+            if (hi3 > lo3) widen_plane(J.h_img8 + 3 * (size_t)b0 * J.hw + lo3, hi3 - lo3, J.img1 + 3 * (size_t)b0 * J.hw + lo3);
         }
     }
 }
@@ -222,6 +272,9 @@ void ofd_pair_pipeline_destroy(ofd_pair_pipeline* p) {
     }
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     if (p->h_mask) cudaFreeHost(p->h_mask);
+    if (p->h_img8) cudaFreeHost(p->h_img8);
+    if (p->h_flags) cudaFreeHost(p->h_flags);
+    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) cudaFree(p->d_flags[s]);
     delete p;
 }
 
@@ -234,6 +287,8 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     if (!p) return fail(OFD_E_ARG, "ofd_pair_pipeline_create: out of host memory");
     p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
     p->h_mask = nullptr, p->h_mask_cap = 0;
+    p->h_img8 = nullptr, p->h_img8_cap = 0, p->h_flags = nullptr, p->h_flags_cap = 0;
+    p->img_bytes_enabled = env_int("OFD_HOST_IMG_BYTES", 1, 0, 1) != 0, p->img_bytes_ok = true;
     // the knobs are read per pipeline (not once per process): a caller can build pipelines with different settings
     p->n_workers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
     p->mask_bytes_enabled = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
@@ -244,7 +299,7 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     }
     const size_t hw = (size_t)H * W, n = (size_t)chunk_frames;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s)
-        p->st[s] = nullptr, p->done[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr;
+        p->st[s] = nullptr, p->done[s] = nullptr, p->d_in[s] = p->d_out[s] = p->d_s[s] = nullptr, p->d_u8[s] = nullptr, p->d_flags[s] = nullptr;
     for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) {
         cudaError_t e = cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking);
         if (e == cudaSuccess)
@@ -253,6 +308,7 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
         if (e == cudaSuccess) e = cudaMalloc(&p->d_out[s], n * 10 * hw * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_s[s], n * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_u8[s], n * 8 * hw);
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_flags[s], sizeof(int));
         if (e != cudaSuccess) {
             int rc = fail((int)e, "ofd_pair_pipeline_create: %s", cudaGetErrorString(e));
             ofd_pair_pipeline_destroy(p);
@@ -290,6 +346,10 @@ int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, co
     //    pipeline's pinned staging buffer and are expanded into the caller's float planes by the same host threads,
     //    chunk by chunk, as soon as a chunk's event fires.   OFD_HOST_MASK_BYTES=0 sends them as float planes instead.
     const bool mask_bytes = p->mask_bytes_enabled && hw % 4 == 0;
+    //  - img1 is a selection of img0's pixels: uint8-valued whenever img0 is (the reference's loader output).  Its planes cross as
+    //    bytes, verified by the packing kernel chunk by chunk; a chunk a byte cannot carry exactly is redone with float planes below
+    //    and the pipeline then stops trying.  OFD_HOST_IMG_BYTES=0 disables it.  Rides on the mask events (needs the byte-mask path).
+    const bool img_bytes = mask_bytes && p->img_bytes_enabled && p->img_bytes_ok;
     const int K = (B + p->chunk - 1) / p->chunk;
     if (mask_bytes) {
         if (p->h_mask_cap < (size_t)B * hw) {
@@ -304,58 +364,107 @@ int ofd_pair_pipeline_run_flags(ofd_pair_pipeline* p, const float* img0_host, co
             p->ev.push_back(e);
         }
     }
-    ofd_host_job J;
-    J.B = B, J.K = K, J.chunk = p->chunk, J.hw = hw;
-    J.mask_bytes = mask_bytes, J.fill_const = !(flags & OFD_PIPE_KEEP_CONST_PLANES);
-    J.back_flow = back_flow_host, J.flow = flow_host, J.valid = valid_host, J.collision = collision_host;
-    J.h_mask = p->h_mask, J.ev = p->ev.data();
-    HostRun host(p, J);
-    for (int k = 0, b0 = 0; b0 < B; b0 += p->chunk, ++k) {
-        const int s = k % ofd_pair_pipeline::NSLOT;
-        const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
-        cudaStream_t st = p->st[s];
-        float* din = p->d_in[s];
-        float* dimg = din;
-        float* ddep = din + n * 3 * hw;
-        float* dout = p->d_out[s];
-        float* o_img = dout;
-        float* o_dep = o_img + n * 3 * hw;
-        float* o_bf = o_dep + n * hw;
-        float* o_fl = o_bf + n * 2 * hw;
-        float* o_val = o_fl + n * 2 * hw;
-        float* o_col = o_val + n * hw;
-        OFD_CUDA(cudaMemcpyAsync(dimg, img0_host + (size_t)b0 * 3 * hw, n * 3 * hw * F, cudaMemcpyHostToDevice, st));
-        OFD_CUDA(cudaMemcpyAsync(ddep, depth0_host + (size_t)b0 * hw, n * hw * F, cudaMemcpyHostToDevice, st));
-        OFD_CUDA(cudaMemcpyAsync(p->d_s[s], sBf_host + b0, n * F, cudaMemcpyHostToDevice, st));
-        int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[s], (int)n, p->H, p->W, o_img, o_dep, o_bf,
-                                    flow_host ? o_fl : nullptr, o_val, collision_host ? o_col : nullptr, nullptr, st);
-        if (rc) return rc;
-        if (mask_bytes) {
-            pack_masks_kernel<<<296, 256, 0, st>>>((const float4*)o_val, collision_host ? (const float4*)o_col : nullptr,
-                                                   (uchar4*)p->d_u8[s], n * hw / 4);
-            rc = check_launch(fn);
-            if (rc) return rc;
-            // masks first: the host expansion of this chunk overlaps the float planes' copies
-            OFD_CUDA(cudaMemcpyAsync(p->h_mask + (size_t)b0 * hw, p->d_u8[s], n * hw, cudaMemcpyDeviceToHost, st));
-            OFD_CUDA(cudaEventRecord(p->ev[(size_t)k], st));
-            host.chunk_issued(k);
+    if (img_bytes) {
+        if (p->h_img8_cap < (size_t)B * 3 * hw) {
+            if (p->h_img8) cudaFreeHost(p->h_img8);
+            p->h_img8 = nullptr, p->h_img8_cap = 0;
+            OFD_CUDA(cudaHostAlloc((void**)&p->h_img8, (size_t)B * 3 * hw, cudaHostAllocDefault));
+            p->h_img8_cap = (size_t)B * 3 * hw;
         }
-        OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
-        OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
-        // x planes only: plane 0 of every [2,H,W] frame (pitch 2*hw floats on both sides)
-        OFD_CUDA(cudaMemcpy2DAsync(back_flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_bf, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
-        if (flow_host)
-            OFD_CUDA(cudaMemcpy2DAsync(flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_fl, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
-        if (!mask_bytes) {
-            OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
-            if (collision_host)
-                OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+        if (p->h_flags_cap < (size_t)K) {
+            if (p->h_flags) cudaFreeHost(p->h_flags);
+            p->h_flags = nullptr, p->h_flags_cap = 0;
+            OFD_CUDA(cudaHostAlloc((void**)&p->h_flags, (size_t)K * sizeof(int), cudaHostAllocDefault));
+            p->h_flags_cap = (size_t)K;
         }
     }
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventRecord(p->done[s], p->st[s]));
-    for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventSynchronize(p->done[s]));
-    host.ok = true;
-    return OFD_OK;  // ~HostRun waits for the host fills and mask expansions
+    {
+        ofd_host_job J;
+        J.B = B, J.K = K, J.chunk = p->chunk, J.hw = hw;
+        J.mask_bytes = mask_bytes, J.fill_const = !(flags & OFD_PIPE_KEEP_CONST_PLANES), J.img_bytes = img_bytes;
+        J.back_flow = back_flow_host, J.flow = flow_host, J.valid = valid_host, J.collision = collision_host, J.img1 = img1_host;
+        J.h_mask = p->h_mask, J.h_img8 = p->h_img8, J.ev = p->ev.data();
+        HostRun host(p, J);
+        for (int k = 0, b0 = 0; b0 < B; b0 += p->chunk, ++k) {
+            const int s = k % ofd_pair_pipeline::NSLOT;
+            const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
+            cudaStream_t st = p->st[s];
+            float* din = p->d_in[s];
+            float* dimg = din;
+            float* ddep = din + n * 3 * hw;
+            float* dout = p->d_out[s];
+            float* o_img = dout;
+            float* o_dep = o_img + n * 3 * hw;
+            float* o_bf = o_dep + n * hw;
+            float* o_fl = o_bf + n * 2 * hw;
+            float* o_val = o_fl + n * 2 * hw;
+            float* o_col = o_val + n * hw;
+            OFD_CUDA(cudaMemcpyAsync(dimg, img0_host + (size_t)b0 * 3 * hw, n * 3 * hw * F, cudaMemcpyHostToDevice, st));
+            OFD_CUDA(cudaMemcpyAsync(ddep, depth0_host + (size_t)b0 * hw, n * hw * F, cudaMemcpyHostToDevice, st));
+            OFD_CUDA(cudaMemcpyAsync(p->d_s[s], sBf_host + b0, n * F, cudaMemcpyHostToDevice, st));
+            int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[s], (int)n, p->H, p->W, o_img, o_dep, o_bf,
+                                        flow_host ? o_fl : nullptr, o_val, collision_host ? o_col : nullptr, nullptr, st);
+            if (rc) return rc;
+            if (mask_bytes) {
+                unsigned char* u_mask = p->d_u8[s];
+                unsigned char* u_img = u_mask + n * hw;
+                pack_masks_kernel<<<296, 256, 0, st>>>((const float4*)o_val, collision_host ? (const float4*)o_col : nullptr, (uchar4*)u_mask,
+                                                       n * hw / 4);
+                if (img_bytes) {
+                    OFD_CUDA(cudaMemsetAsync(p->d_flags[s], 0, sizeof(int), st));
+                    pack_img_u8_kernel<<<592, 256, 0, st>>>((const float4*)o_img, (uchar4*)u_img, n * 3 * hw / 4, p->d_flags[s]);
+                }
+                rc = check_launch(fn);
+                if (rc) return rc;
+                // bytes first: the host expansion of this chunk overlaps the float planes' copies
+                OFD_CUDA(cudaMemcpyAsync(p->h_mask + (size_t)b0 * hw, u_mask, n * hw, cudaMemcpyDeviceToHost, st));
+                if (img_bytes) {
+                    OFD_CUDA(cudaMemcpyAsync(p->h_img8 + (size_t)b0 * 3 * hw, u_img, n * 3 * hw, cudaMemcpyDeviceToHost, st));
+                    OFD_CUDA(cudaMemcpyAsync(p->h_flags + k, p->d_flags[s], sizeof(int), cudaMemcpyDeviceToHost, st));
+                }
+                OFD_CUDA(cudaEventRecord(p->ev[(size_t)k], st));
+                host.chunk_issued(k);
+            }
+            if (!img_bytes)
+                OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
+            OFD_CUDA(cudaMemcpyAsync(depth1_host + (size_t)b0 * hw, o_dep, n * hw * F, cudaMemcpyDeviceToHost, st));
+            // x planes only: plane 0 of every [2,H,W] frame (pitch 2*hw floats on both sides)
+            OFD_CUDA(cudaMemcpy2DAsync(back_flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_bf, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
+            if (flow_host)
+                OFD_CUDA(cudaMemcpy2DAsync(flow_host + (size_t)b0 * 2 * hw, 2 * hw * F, o_fl, 2 * hw * F, hw * F, n, cudaMemcpyDeviceToHost, st));
+            if (!mask_bytes) {
+                OFD_CUDA(cudaMemcpyAsync(valid_host + (size_t)b0 * hw, o_val, n * hw * F, cudaMemcpyDeviceToHost, st));
+                if (collision_host)
+                    OFD_CUDA(cudaMemcpyAsync(collision_host + (size_t)b0 * hw, o_col, n * hw * F, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventRecord(p->done[s], p->st[s]));
+        for (int s = 0; s < ofd_pair_pipeline::NSLOT; ++s) OFD_CUDA(cudaEventSynchronize(p->done[s]));
+        host.ok = true;
+    }  // ~HostRun waits for the host fills and expansions
+    if (img_bytes) {
+        // verification: chunks whose image a byte cannot carry exactly are redone with float planes (img1 only; the rest is in place)
+        for (int k = 0, b0 = 0; b0 < B; b0 += p->chunk, ++k) {
+            if (!p->h_flags[k]) continue;
+            p->img_bytes_ok = false;  // this caller's images are not uint8-valued: later runs send float planes straight away
+            const size_t n = (size_t)((B - b0) < p->chunk ? (B - b0) : p->chunk);
+            cudaStream_t st = p->st[0];
+            float* dimg = p->d_in[0];
+            float* ddep = dimg + n * 3 * hw;
+            float* o_img = p->d_out[0];
+            float* o_dep = o_img + n * 3 * hw;
+            float* o_bf = o_dep + n * hw;
+            float* o_val = o_bf + 4 * n * hw;
+            OFD_CUDA(cudaMemcpyAsync(dimg, img0_host + (size_t)b0 * 3 * hw, n * 3 * hw * F, cudaMemcpyHostToDevice, st));
+            OFD_CUDA(cudaMemcpyAsync(ddep, depth0_host + (size_t)b0 * hw, n * hw * F, cudaMemcpyHostToDevice, st));
+            OFD_CUDA(cudaMemcpyAsync(p->d_s[0], sBf_host + b0, n * F, cudaMemcpyHostToDevice, st));
+            int rc = ofd_disparity_pair(dimg, ddep, OFD_F32, p->d_s[0], (int)n, p->H, p->W, o_img, o_dep, o_bf, nullptr, o_val, nullptr, nullptr, st);
+            if (rc) return rc;
+            OFD_CUDA(cudaMemcpyAsync(img1_host + (size_t)b0 * 3 * hw, o_img, n * 3 * hw * F, cudaMemcpyDeviceToHost, st));
+            OFD_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return OFD_OK;
 }
 
 int ofd_pair_pipeline_run(ofd_pair_pipeline* p, const float* img0_host, const float* depth0_host, const float* sBf_host,

@@ -551,6 +551,47 @@ def test_pair_pipeline_options_validation_and_repeat_runs(pkg):
         pipe.close()
 
 
+def test_pair_pipeline_image_bytes_are_verified_and_fall_back(pkg):
+    """The float32 host pipeline sends img1 as bytes when a byte carries every value exactly (uint8-valued frames, the reference's loader
+    output) - verified on the device chunk by chunk.  Frames with fractional values, values above 255, negatives or -0.0 in ONE chunk make
+    that chunk fall back to float planes inside the same call (results still bit-exact), and the pipeline then sends floats straight away;
+    OFD_HOST_IMG_BYTES=0 never tries."""
+    import os
+
+    h, w, B = 40, 56, 7
+    rng = np.random.default_rng(33)
+    base = rng.integers(0, 256, (B, 3, h, w)).astype(np.float32)
+    depth = torch.from_numpy(rng.integers(1, 60, (B, 1, h, w)).astype(np.float32)).pin_memory()
+    sBf = torch.from_numpy(rng.uniform(40, 55, B).astype(np.float32))
+
+    def run(pipe, img_np):
+        img = torch.from_numpy(img_np).pin_memory()
+        outs = [torch.full((B, c, h, w), 7.0).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+        pipe.run(img, depth, sBf, *outs)
+        want = oracle.disparity_pair(img_np, depth.numpy(), sBf.numpy())
+        for o, wnt, name in zip(outs, want, ("img1", "depth1", "back_flow", "flow", "valid", "collision")):
+            assert np.array_equal(o.numpy(), wnt), name
+            assert np.array_equal(np.signbit(o.numpy()), np.signbit(wnt)), name   # -0.0 stays -0.0
+
+    for poison in (None, 0.5, 300.0, -3.0, -0.0):
+        pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=2)
+        img_np = base.copy()
+        run(pipe, img_np)                       # uint8-valued: byte path
+        if poison is not None:
+            img_np[4, 1, 7, 9:30] = poison      # only the third chunk (frames 4-5) needs floats
+            run(pipe, img_np)                   # verified fallback inside the call
+            run(pipe, img_np)                   # the pipeline has stopped trying
+            run(pipe, base)
+        pipe.close()
+    os.environ["OFD_HOST_IMG_BYTES"] = "0"
+    try:
+        pipe = pkg.ops.PairPipeline(0, h, w, chunk_frames=3)
+    finally:
+        del os.environ["OFD_HOST_IMG_BYTES"]
+    run(pipe, base)
+    pipe.close()
+
+
 def test_pair_pipeline_mask_bytes_edge_cases(pkg):
     """The float32 host pipeline sends valid / collision as packed bytes and expands them on the host: growing batches on one
     pipeline (staging buffer and events regrow), host planes that are only 4-byte aligned (scalar head / tail of the
@@ -1875,8 +1916,8 @@ def test_bench_default_arm_prints_the_contract_line():
     assert rf["traffic"] is None or rf["traffic"] > 0
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16 * (4 * 480 * 640 * 4 + 4)
-    # every result plane lands in host memory: 6 float planes + one byte of packed masks cross PCIe, 4 planes are written by host threads
-    assert e["d2h_bytes_per_step"] == 16 * (6 * 4 + 1) * 480 * 640 and e["host_filled_bytes_per_step"] == 16 * 4 * 480 * 640 * 4
+    # every result plane lands in host memory: 3 float planes + one byte of packed masks + 3 image bytes cross PCIe, 7 planes are written by host threads
+    assert e["d2h_bytes_per_step"] == 16 * (3 * 4 + 1 + 3) * 480 * 640 and e["host_filled_bytes_per_step"] == 16 * 7 * 480 * 640 * 4
     assert e["value"] < d["value"]  # host buffers cross PCIe: never the device-resident number
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["counters"]["frames"] == 32 and d["counters"]["hit"] + d["counters"]["hole"] == 32 * 480 * 640
