@@ -41,10 +41,7 @@ def run(label, env, K=10, stir=False):
 
 
 for rep in range(2):
-    for sync in ("block", "spin"):
-        for w in ("1", "2", "3", "4"):
-            run(f"sync={sync} workers={w}", {"OFD_HOST_SYNC": sync, "OFD_HOST_WORKERS": w})
-    run("sync=block workers=2 after a torch CPU op", {"OFD_HOST_SYNC": "block", "OFD_HOST_WORKERS": "2"}, stir=True)
-    run("sync=spin workers=2 after a torch CPU op", {"OFD_HOST_SYNC": "spin", "OFD_HOST_WORKERS": "2"}, stir=True)
-torch.set_num_threads(1)
-run("sync=block workers=2, torch threads = 1, after a CPU op", {"OFD_HOST_SYNC": "block", "OFD_HOST_WORKERS": "2"}, stir=True)
+    for img_bytes in ("1", "0"):
+        for w in ("1", "2", "3", "4", "6"):
+            run(f"img1 as {'verified bytes' if img_bytes == '1' else 'float planes'} workers={w}", {"OFD_HOST_IMG_BYTES": img_bytes, "OFD_HOST_WORKERS": w})
+    run("sync=block img bytes workers=3", {"OFD_HOST_SYNC": "block", "OFD_HOST_WORKERS": "3"})
