@@ -564,7 +564,7 @@ def run_ours(args):
                        "h2d_bytes_per_step": Fe * (4 * H * W * 4 + 4), "d2h_bytes_per_step": Fe * d2h_px * H * W,
                        "host_filled_bytes_per_step": Fe * (4 + (3 if img_bytes else 0)) * H * W * 4,
                        "frames_per_step": Fe, "steps": Ke, "host_cores_per_rank": len(cores_mine),
-                       "host_workers": int(os.environ.get("OFD_HOST_WORKERS", "2")),
+                       "host_workers": int(os.environ.get("OFD_HOST_WORKERS", str(min(max(len(cores_mine) - 1, 2), 4)))),
                        "recycled_buffers_value": world * Fe * Ke / tk,
                        "api": "ofd_pair_pipeline_run (C ABI, pinned float32 host buffers in and out - all 10 result planes, 3-slot H2D/kernel/D2H pipeline; "
                               "the two constant planes flow.y / back_flow.y are written by the pipeline's persistent host threads instead of crossing PCIe, "

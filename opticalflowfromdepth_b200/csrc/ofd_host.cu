@@ -2,7 +2,8 @@
 // binds (the reference moves every frame host->device->host around its FW call, preprocess.py:350-366,437-447).
 // A pipeline owns NSLOT device staging slots, each with its own stream; chunk k runs H2D -> pair kernel -> D2H
 // on slot k % NSLOT, so the two copy engines and the SMs overlap across chunks.
-#include <emmintrin.h>
+#include <immintrin.h>
+#include <sched.h>
 
 #include <condition_variable>
 #include <cstdlib>
@@ -136,8 +137,9 @@ static void expand_plane(const unsigned char* m, size_t n, int shift, float* dst
     _mm_sfence();
 }
 
-// 16 bytes -> 16 floats, non-temporal stores (dst 16-byte aligned)
-static void widen_plane(const unsigned char* m, size_t n, float* dst) {
+// bytes -> floats with non-temporal stores.  Two builds of the inner loop: SSE2 (baseline x86-64) and AVX2 (32 bytes per step, picked at
+// run time with __builtin_cpu_supports) - one host thread widens ~14 GB/s of floats with the former, about twice that with the latter
+static void widen_sse2(const unsigned char* m, size_t n, float* dst) {
     size_t i = 0;
     while (i < n && ((uintptr_t)(dst + i) & 15)) dst[i] = (float)m[i], ++i;
     const __m128i z = _mm_setzero_si128();
@@ -151,6 +153,28 @@ static void widen_plane(const unsigned char* m, size_t n, float* dst) {
     }
     for (; i < n; ++i) dst[i] = (float)m[i];
     _mm_sfence();
+}
+
+__attribute__((target("avx2"))) static void widen_avx2(const unsigned char* m, size_t n, float* dst) {
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) dst[i] = (float)m[i], ++i;
+    for (; i + 32 <= n; i += 32) {
+        const __m128i b0 = _mm_loadu_si128((const __m128i*)(m + i)), b1 = _mm_loadu_si128((const __m128i*)(m + i + 16));
+        _mm256_stream_ps(dst + i, _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(b0)));
+        _mm256_stream_ps(dst + i + 8, _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(_mm_srli_si128(b0, 8))));
+        _mm256_stream_ps(dst + i + 16, _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(b1)));
+        _mm256_stream_ps(dst + i + 24, _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(_mm_srli_si128(b1, 8))));
+    }
+    for (; i < n; ++i) dst[i] = (float)m[i];
+    _mm_sfence();
+}
+
+static void widen_plane(const unsigned char* m, size_t n, float* dst) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2)
+        widen_avx2(m, n, dst);
+    else
+        widen_sse2(m, n, dst);
 }
 
 static int env_int(const char* name, int dflt, int lo, int hi) {
@@ -290,7 +314,18 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     p->h_img8 = nullptr, p->h_img8_cap = 0, p->h_flags = nullptr, p->h_flags_cap = 0;
     p->img_bytes_enabled = env_int("OFD_HOST_IMG_BYTES", 1, 0, 1) != 0, p->img_bytes_ok = true;
     // the knobs are read per pipeline (not once per process): a caller can build pipelines with different settings
-    p->n_workers = env_int("OFD_HOST_WORKERS", 2, 1, 64);
+    // default: one worker per core of this thread's affinity mask minus the issuing thread, between 2 and 4 (the byte-widening of img1
+    // wants 3-4: profiles/r2/tune_e2e_img_bytes.txt; under torchrun a rank pinned to 4 cores gets 3)
+    int dflt_workers = 2;
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+            const int cores = CPU_COUNT(&set);
+            dflt_workers = cores - 1 < 2 ? 2 : (cores - 1 > 4 ? 4 : cores - 1);
+        }
+    }
+    p->n_workers = env_int("OFD_HOST_WORKERS", dflt_workers, 1, 64);
     p->mask_bytes_enabled = env_int("OFD_HOST_MASK_BYTES", 1, 0, 1) != 0;
     {
         // measured on B200 boxes (profiles/r2/tune_e2e.txt): spinning waits 6.35 k pairs/s, blocking-sync events 6.12 k
