@@ -556,7 +556,8 @@ def run_ours(args):
             pipe.run(h_img, h_depth, h_s, *h_out, keep_const_planes=True)
         tk = max_over_ranks(time.perf_counter() - t0)
         pipe.close()
-        img_bytes = os.environ.get("OFD_HOST_IMG_BYTES", "1") != "0" and os.environ.get("OFD_HOST_MASK_BYTES", "1") != "0"
+        img_bytes = os.environ.get("OFD_HOST_IMG_BYTES", "1" if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2 else "0") != "0" \
+            and os.environ.get("OFD_HOST_MASK_BYTES", "1") != "0"
         # what crosses PCIe down per pixel: depth1, back_flow.x, flow.x as float planes (12 B), valid|collision as one packed byte, and
         # img1 as 3 bytes (the frames are uint8-valued like the reference's loader output; verified on the device per chunk) or 12
         d2h_px = 12 + 1 + (3 if img_bytes else 12)

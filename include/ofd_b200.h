@@ -316,8 +316,13 @@ int ofd_bilateral_iter_batch(const void* depth_in, const void* depth_orig, int d
  * flow and back_flow are constants of the virtual-stereo pair (-0.0 / +0.0): they are not transferred (8 of the 40 result bytes per
  * pixel) but written into the host buffers by host threads while the copies run; valid / collision (0.0f / 1.0f planes) cross PCIe as
  * one packed byte per pixel and are expanded into the caller's float planes by the same threads (25 instead of 40 B/px on the wire,
- * H*W a multiple of 4) - the buffers end up complete and bit-identical either way.
- * Host threads: OFD_HOST_WORKERS (default 2, read when the pipeline is CREATED) persistent threads per pipeline; they sleep on a
+ * H*W a multiple of 4) - the buffers end up complete and bit-identical either way.  img1 is a selection of img0's pixels: when a byte
+ * carries every value of a chunk exactly (uint8-valued frames - what the reference's loader delivers, utils.py:17-25), its three planes
+ * cross as bytes too (16 instead of 25 B/px on the wire) and are widened by the host threads; the packing kernel verifies every chunk on
+ * the device and a chunk that fails is redone with float planes inside the same call (the pipeline then stops trying).  On by default
+ * unless more than two ranks share the node (LOCAL_WORLD_SIZE > 2: host memory, not PCIe, is the limit there); OFD_HOST_IMG_BYTES=0/1.
+ * Host threads: OFD_HOST_WORKERS (default: cores of the creating thread's affinity mask minus one, clamped to 2..4; read when the pipeline is
+ * CREATED) persistent threads per pipeline; they sleep on a
  * condition variable between runs and chunks and inherit the CPU affinity of the creating thread.  OFD_HOST_MASK_BYTES=0 (read at
  * creation) sends the masks as float planes.
  * ofd_pair_pipeline_run_flags: the same call with option bits.  OFD_PIPE_KEEP_CONST_PLANES: the caller recycles result buffers

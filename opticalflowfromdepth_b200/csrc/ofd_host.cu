@@ -312,7 +312,10 @@ int ofd_pair_pipeline_create(int device, int H, int W, int chunk_frames, ofd_pai
     p->device = device, p->H = H, p->W = W, p->chunk = chunk_frames;
     p->h_mask = nullptr, p->h_mask_cap = 0;
     p->h_img8 = nullptr, p->h_img8_cap = 0, p->h_flags = nullptr, p->h_flags_cap = 0;
-    p->img_bytes_enabled = env_int("OFD_HOST_IMG_BYTES", 1, 0, 1) != 0, p->img_bytes_ok = true;
+    // Bytes for img1 trade 9 B/px of PCIe for 12 B/px of host stores: a win while PCIe is the limit (1-2 GPUs per host: 6.0 -> 6.8 k
+    // pairs/s), a loss once the node's host memory is (the D2H total of these boxes is flat from 2 to 8 GPUs).  Default:
+    // on unless more than two ranks share the node (torchrun's LOCAL_WORLD_SIZE); OFD_HOST_IMG_BYTES=0/1 overrides.
+    p->img_bytes_enabled = env_int("OFD_HOST_IMG_BYTES", env_int("LOCAL_WORLD_SIZE", 1, 1, 1 << 20) <= 2 ? 1 : 0, 0, 1) != 0, p->img_bytes_ok = true;
     // the knobs are read per pipeline (not once per process): a caller can build pipelines with different settings
     // default: one worker per core of this thread's affinity mask minus the issuing thread, between 2 and 4 (the byte-widening of img1
     // wants 3-4: profiles/r2/tune_e2e_img_bytes.txt; under torchrun a rank pinned to 4 cores gets 3)
