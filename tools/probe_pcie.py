@@ -12,7 +12,7 @@ Per mode the table shows GB/s per rank (min / max over ranks) and the node total
                    (ofd_host_stream_fill: the store pattern of the pipeline's host threads); fill GB/s listed separately
     fill T         the host threads alone (host memory write bandwidth, no DMA)
 Then the pair pipeline itself (ofd_pair_pipeline_run, float32 contract) per rank at the bench's e2e size, with and without
-OFD_PIPE_KEEP_CONST_PLANES, and with the masks as float planes (no host threads at all).
+OFD_PIPE_KEEP_CONST_PLANES, with img1 as device-verified bytes or as float planes, and with the masks as float planes (no host threads at all).
 `--affinity` pins every rank to its own core slice first (sweep.bind_rank_cores)."""
 import argparse
 import ctypes as C
@@ -137,14 +137,16 @@ def main():
         return
     rng = np.random.default_rng(rank)
     Fe = args.frames
-    h_img = torch.from_numpy(rng.integers(0, 256, (Fe, 3, H, W)).astype(np.float32)).pin_memory()
+    h_img = torch.from_numpy(rng.integers(0, 256, (Fe, 3, H, W)).astype(np.float32)).pin_memory()  # uint8-valued, like the reference's loader
     h_dep = torch.from_numpy((rng.random((Fe, 1, H, W)) * 98 + 1).astype(np.float32)).pin_memory()
     h_s = torch.full((Fe,), 47.0)
     h_out = [torch.empty((Fe, c, H, W), dtype=torch.float32).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
-    for label, env, keep in (("pipeline default (2 workers, byte masks)", {}, False),
-                             ("pipeline keep_const_planes", {}, True),
-                             ("pipeline 1 worker", {"OFD_HOST_WORKERS": "1"}, False),
-                             ("pipeline 4 workers", {"OFD_HOST_WORKERS": "4"}, False),
+    for label, env, keep in (("pipeline default", {}, False),
+                             ("pipeline img1 as verified bytes", {"OFD_HOST_IMG_BYTES": "1"}, False),
+                             ("pipeline img1 as float planes", {"OFD_HOST_IMG_BYTES": "0"}, False),
+                             ("pipeline img1 bytes + keep_const_planes", {"OFD_HOST_IMG_BYTES": "1"}, True),
+                             ("pipeline img1 floats + keep_const_planes", {"OFD_HOST_IMG_BYTES": "0"}, True),
+                             ("pipeline img1 floats, 2 workers", {"OFD_HOST_IMG_BYTES": "0", "OFD_HOST_WORKERS": "2"}, False),
                              ("pipeline float masks + keep_const (no host stores)", {"OFD_HOST_MASK_BYTES": "0"}, True)):
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
