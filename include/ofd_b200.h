@@ -382,6 +382,12 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
  */
 int ofd_copy_rows_to_host(const void* src, size_t src_pitch_bytes, void* dst_host, size_t dst_pitch_bytes,
                           size_t width_bytes, size_t rows, ofd_stream_t stream);
+/* Lossless byte transport of uint8-valued float planes (the image channels of a frame group): ofd_pack_u8 narrows n device floats to bytes
+ * and raises *flag (device int, zeroed by the caller) if any value is not exactly a uint8 (sign of zero included); ofd_host_widen_u8 widens n
+ * HOST bytes into HOST floats with non-temporal stores on the calling thread.  sweep.PinnedGroupSink uses the pair: 18 of the 44 channels
+ * of a group cross PCIe at 1 B instead of 4 and a failed check falls back to the float planes. */
+int ofd_pack_u8(const float* src, uint8_t* dst, size_t n, int* flag, ofd_stream_t stream);
+int ofd_host_widen_u8(const uint8_t* src_host, size_t n, float* dst_host);
 /* Host-memory probe used by tools/probe_pcie.py: streams n floats of `value` into dst_host with non-temporal stores on the
  * calling thread (the store pattern of the pipeline's host threads); no CUDA call. */
 int ofd_host_stream_fill(float* dst_host, size_t n, float value);

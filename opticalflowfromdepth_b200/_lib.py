@@ -60,6 +60,8 @@ SIGNATURES = {
     "ofd_inpaint_workspace_bytes": (_sz, [_i, _i, _i]),
     "ofd_inpaint_telea": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p, _p]),
     "ofd_copy_rows_to_host": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
+    "ofd_pack_u8": (_i, [_p, _p, _sz, _p, _p]),
+    "ofd_host_widen_u8": (_i, [_p, _sz, _p]),
     "ofd_host_stream_fill": (_i, [_p, _sz, _f]),
     "ofd_pair_pipeline_run_u8": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "ofd_pair_pipeline_destroy": (None, [_p]),

@@ -522,6 +522,35 @@ int ofd_copy_rows_to_host(const void* src, size_t src_pitch_bytes, void* dst_hos
     return OFD_OK;
 }
 
+// float32 -> uint8 with verification (the sweep's group sink sends the 18 image channels of a group as bytes when they are uint8-valued)
+__global__ void __launch_bounds__(256) pack_u8_tail_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, size_t n, int* __restrict__ flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = in[i];
+        const unsigned char o = (unsigned char)(int)fminf(fmaxf(v, 0.0f), 255.0f);
+        if (__float_as_uint((float)o) != __float_as_uint(v)) *flag = 1;
+        out[i] = o;
+    }
+}
+
+int ofd_pack_u8(const float* src, uint8_t* dst, size_t n, int* flag, ofd_stream_t stream) {
+    const char* fn = "ofd_pack_u8";
+    if (!n) return OFD_OK;
+    if (!src || !dst || !flag) return fail(OFD_E_NULL, "%s: NULL pointer", fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (((uintptr_t)src & 15) == 0) && (((uintptr_t)dst & 3) == 0);
+    const size_t n4 = vec ? n / 4 : 0;
+    if (n4) pack_img_u8_kernel<<<592, 256, 0, st>>>((const float4*)src, (uchar4*)dst, n4, flag);
+    if (n - 4 * n4) pack_u8_tail_kernel<<<n4 ? 1 : 592, 256, 0, st>>>(src + 4 * n4, dst + 4 * n4, n - 4 * n4, flag);
+    return check_launch(fn);
+}
+
+int ofd_host_widen_u8(const uint8_t* src_host, size_t n, float* dst_host) {
+    if (!n) return OFD_OK;
+    if (!src_host || !dst_host) return fail(OFD_E_NULL, "ofd_host_widen_u8: NULL pointer");
+    widen_plane(src_host, n, dst_host);
+    return OFD_OK;
+}
+
 int ofd_host_stream_fill(float* dst_host, size_t n, float value) {
     if (!dst_host && n) return fail(OFD_E_NULL, "ofd_host_stream_fill: dst is NULL");
     fill_plane(dst_host, n, value);

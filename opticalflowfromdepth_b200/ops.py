@@ -560,19 +560,38 @@ def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, t
     return out
 
 
-def scatter_channels_to_host(t, host, c0: int, stream=None):
-    """Asynchronous D2H copy of t[B,c,H,W] (float32 CUDA, contiguous) into channels [c0, c0+c) of the page-locked CPU tensor
-    host[>=B,Ctot,H,W] (ofd_copy_rows_to_host: ONE strided DMA, no concatenation on the device).  Runs on `stream`
-    (default: torch's current stream of t's device); the caller synchronises before reading `host`."""
+def pack_u8(t, flag):
+    """float32 CUDA tensor -> uint8 tensor of the same shape (ofd_pack_u8); `flag` (int32 CUDA tensor, one element, zeroed by the
+    caller) is raised when some value is not exactly a uint8."""
     _check("t", t, dtype=torch.float32)
+    out = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.call("ofd_pack_u8", _ptr(t), _ptr(out), C.c_size_t(t.numel()), _ptr(flag), _stream(t.device))
+    return out
+
+
+def host_widen_u8(src, dst):
+    """uint8 CPU tensor -> float32 CPU tensor (same element count, both contiguous), non-temporal stores on the calling thread; the
+    native call releases the GIL, so several Python threads widen in parallel."""
+    if src.is_cuda or dst.is_cuda or src.dtype != torch.uint8 or dst.dtype != torch.float32 or src.numel() != dst.numel() \
+            or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("host_widen_u8 needs contiguous CPU tensors: uint8 source, float32 destination, equal element counts")
+    _lib.call("ofd_host_widen_u8", C.c_void_p(src.data_ptr()), C.c_size_t(src.numel()), C.c_void_p(dst.data_ptr()))
+
+
+def scatter_channels_to_host(t, host, c0: int, stream=None):
+    """Asynchronous D2H copy of t[B,c,H,W] (CUDA, contiguous; float32 or uint8) into channels [c0, c0+c) of the page-locked CPU tensor
+    host[>=B,Ctot,H,W] of the same dtype (ofd_copy_rows_to_host: ONE strided DMA, no concatenation on the device).  Runs on `stream`
+    (default: torch's current stream of t's device); the caller synchronises before reading `host`."""
+    _check("t", t, dtype=(torch.float32, torch.uint8))
     if t.dim() != 4 or host.dim() != 4:
         raise ValueError("t and host must be 4-D [B,C,H,W]")
     B, c, H, W = t.shape
-    if host.is_cuda or host.dtype != torch.float32 or not host.is_contiguous():
-        raise ValueError("host must be a contiguous float32 CPU tensor (page-locked for an asynchronous copy)")
+    if host.is_cuda or host.dtype != t.dtype or not host.is_contiguous():
+        raise ValueError("host must be a contiguous CPU tensor of t's dtype (page-locked for an asynchronous copy)")
     if host.shape[0] < B or tuple(host.shape[2:]) != (H, W) or not (0 <= c0 and c0 + c <= host.shape[1]):
         raise ValueError(f"host{tuple(host.shape)} cannot take channels [{c0},{c0 + c}) of a batch of {B} frames {H}x{W}")
-    hw4 = H * W * 4
+    hw4 = H * W * t.element_size()
     st = C.c_void_p(stream.cuda_stream) if stream is not None else _stream(t.device)
     with torch.cuda.device(t.device):
         _lib.call("ofd_copy_rows_to_host", _ptr(t), C.c_size_t(c * hw4), C.c_void_p(host.data_ptr() + c0 * hw4),

@@ -88,23 +88,38 @@ class PinnedGroupSink:
     copied by ONE strided DMA (ops.scatter_channels_to_host) straight into its channel slice of a page-locked [B,44,H,W] array,
     on a side stream, so the copies of batch k overlap the host-side preparation and the kernels of batch k+1.
 
+    byte_images: the 18 image channels of a group are uint8-valued whenever the source frames are (warps select pixels, the
+    fills produce bytes), so they can cross PCIe at 1 B instead of 4 (122 instead of 176 B/px per frame): the device narrows them
+    with a verifying kernel (ofd_pack_u8), the host widens them into the float array on a few threads when the batch is delivered
+    (ofd_host_widen_u8); a batch whose check fails is delivered from its float planes instead.  Default (None): on while PCIe is
+    the limit, i.e. unless more than two ranks share the node (LOCAL_WORLD_SIZE > 2: there the node's host memory is, and the extra
+    host stores cost more than the PCIe bytes they save - DESIGN.md section 6).
+
     `on_batch(idx_list, array[B,44,H,W], release)` receives the host array once its copies have landed (when the next-but-one
     batch arrives, or at flush()).  The consumer OWNS the array until it calls release() - it may hand it to asynchronous
     writers (preprocess.NpzWriter) and release it when they are done; the sink takes another page-locked buffer from its pool
     (allocating one if none is free) instead of overwriting a buffer that is still being read.  Without on_batch the sink
     only counts and recycles two buffers."""
 
-    def __init__(self, on_batch: Optional[Callable] = None):
-        self.on_batch = on_batch
-        self.frames = 0
-        self.bytes = 0
-        self.buffers_allocated = 0
-        self._inflight = []          # [(pinned tensor, event, idx_list, n)] oldest first, at most 2
-        self._free = []              # released page-locked buffers
+    def __init__(self, on_batch: Optional[Callable] = None, byte_images: Optional[bool] = None, widen_threads: int = 4):
+        import os
         import threading
 
+        self.on_batch = on_batch
+        if byte_images is None:
+            byte_images = int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2
+        self.byte_images = bool(byte_images)
+        self.frames = 0
+        self.bytes = 0               # bytes that crossed PCIe
+        self.buffers_allocated = 0
+        self.fallback_batches = 0    # batches whose image check failed (delivered from the float planes)
+        self._inflight = []          # oldest first, at most 2
+        self._free = []              # released page-locked float buffers
+        self._free8 = []             # page-locked byte staging buffers
         self._lock = threading.Lock()
         self._stream = None
+        self._pool = None
+        self._widen_threads = max(1, min(int(widen_threads), len(os.sched_getaffinity(0))))
 
     def _take(self, shape):
         with self._lock:
@@ -115,13 +130,40 @@ class PinnedGroupSink:
         self.buffers_allocated += 1
         return torch.empty(shape, dtype=torch.float32, pin_memory=True)
 
+    def _take8(self, shape):
+        for k, h in enumerate(self._free8):
+            if h.shape[0] >= shape[0] and tuple(h.shape[1:]) == tuple(shape[1:]):
+                return self._free8.pop(k)
+        self._free8.clear()
+        return torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+
     def _release(self, host):
         with self._lock:
             self._free.append(host)
 
     def _deliver_oldest(self):
-        host, event, idx_list, n = self._inflight.pop(0)
+        from . import ops
+
+        entry = self._inflight.pop(0)
+        host, event, idx_list, n = entry["host"], entry["event"], entry["idx"], entry["n"]
         event.synchronize()
+        if entry["host8"] is not None:
+            host8, spans = entry["host8"], entry["spans"]
+            if int(entry["flag_host"][0]) == 0:
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+
+                    self._pool = ThreadPoolExecutor(max_workers=self._widen_threads)
+                jobs = [(b, c8, c0, c) for b in range(n) for (c8, c0, c) in spans]
+                list(self._pool.map(lambda j: ops.host_widen_u8(host8[j[0], j[1]:j[1] + j[3]], host[j[0], j[2]:j[2] + j[3]]), jobs))
+            else:  # some image value is not a uint8: deliver the float planes (kept alive for this case)
+                self.fallback_batches += 1
+                self.byte_images = False
+                for t, c0 in entry["float_images"]:
+                    ops.scatter_channels_to_host(t, host, c0)
+                torch.cuda.current_stream(entry["float_images"][0][0].device).synchronize()
+            self._free8.append(host8)
+        entry["float_images"] = None
         if self.on_batch is None:
             self._release(host)
             return
@@ -145,26 +187,59 @@ class PinnedGroupSink:
             self._stream = torch.cuda.Stream(dev)
         while len(self._inflight) >= 2:  # at most two batches in flight: the older one has landed by now
             self._deliver_oldest()
-        host = self._take((B, sum(res[n].shape[1] for n in GROUP_CHANNELS), H, W))
+        ctot = sum(res[n].shape[1] for n in GROUP_CHANNELS)
+        host = self._take((B, ctot, H, W))
+        use_bytes = self.byte_images
+        images = [(n, res[n]) for n in GROUP_CHANNELS if n.startswith("img")] if use_bytes else []
+        host8 = flag = flag_host = None
+        packed = {}
+        if images:
+            # narrow the image tensors on the compute stream (they are ready there), verified by one device flag for the batch
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            for name, t in images:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                packed[name] = ops.pack_u8(t, flag)
+            host8 = self._take8((B, sum(t.shape[1] for _, t in images), H, W))
+            flag_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
         self._stream.wait_stream(torch.cuda.current_stream(dev))
-        c0 = 0
-        for name in GROUP_CHANNELS:
-            t = res[name]
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                t = t.float().contiguous()
-            ops.scatter_channels_to_host(t, host, c0, stream=self._stream)
-            t.record_stream(self._stream)
-            c0 += t.shape[1]
+        c0 = c8 = 0
+        spans, float_images, crossed = [], [], 0
+        with torch.cuda.stream(self._stream):
+            for name in GROUP_CHANNELS:
+                t = res[name]
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                if name in packed:
+                    u = packed[name]
+                    ops.scatter_channels_to_host(u, host8, c8, stream=self._stream)
+                    u.record_stream(self._stream)
+                    spans.append((c8, c0, t.shape[1]))
+                    float_images.append((t, c0))
+                    c8 += t.shape[1]
+                    crossed += u.numel()
+                else:
+                    ops.scatter_channels_to_host(t, host, c0, stream=self._stream)
+                    t.record_stream(self._stream)
+                    crossed += t.numel() * 4
+                c0 += t.shape[1]
+            if flag is not None:
+                flag_host.copy_(flag, non_blocking=True)
+                flag.record_stream(self._stream)
         event = torch.cuda.Event()
         event.record(self._stream)
-        self._inflight.append((host, event, list(idx_list), B))
+        self._inflight.append(dict(host=host, event=event, idx=list(idx_list), n=B, host8=host8, spans=spans, flag_host=flag_host,
+                                   float_images=float_images if images else None))
         self.frames += len(idx_list)
-        self.bytes += B * c0 * H * W * 4
+        self.bytes += crossed
 
     def flush(self):
         """Wait for the outstanding copies and hand their batches over (oldest first)."""
         while self._inflight:
             self._deliver_oldest()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
 
 
 def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device, batch: int = 32, epoch: int = 0,

@@ -1836,8 +1836,9 @@ def test_sweep_sink_scatters_the_group_without_a_device_concatenation(pkg):
             held.append((list(idx_list), arr, release))   # keep the VIEW, release nothing yet
 
     sink = sweep.PinnedGroupSink(on_batch)
+    assert sink.byte_images                      # one rank per node here: the image channels cross as verified bytes
     sweep.run_sweep(range(n), load, DEV, batch=3, dataset_len=n, sink=sink)
-    assert sink.frames == n and sink.bytes == n * 44 * h * w * 4
+    assert sink.frames == n and sink.bytes == n * (26 * 4 + 18) * h * w and sink.fallback_batches == 0
     assert sum(len(i) for i, _, _ in held) == n
     for idx_list, arr, release in held:          # all four batches still intact although nothing was released
         for k, i in enumerate(idx_list):
@@ -1849,6 +1850,33 @@ def test_sweep_sink_scatters_the_group_without_a_device_concatenation(pkg):
     before = sink.buffers_allocated
     sweep.run_sweep(range(3), load, DEV, batch=3, dataset_len=n, sink=sink)
     assert sink.buffers_allocated == before      # released buffers are reused
+    # float transport (what ranks sharing a node with more than one other rank default to): same arrays, 176 B/px on the wire
+    held.clear()
+    sink_f = sweep.PinnedGroupSink(on_batch, byte_images=False)
+    sweep.run_sweep(range(n), load, DEV, batch=4, dataset_len=n, sink=sink_f)
+    assert sink_f.bytes == n * 44 * 4 * h * w
+    for idx_list, arr, release in held:
+        for k, i in enumerate(idx_list):
+            assert np.array_equal(arr[k], want[i]), i
+        release()
+    # frames that are NOT uint8-valued: the device check fails, the batch is delivered from its float planes and the sink stops trying
+    held.clear()
+    want_frac = {}
+    load_frac = lambda i: (load(i)[0] + np.float32(0.25), load(i)[1])  # noqa: E731
+
+    def ref_sink_frac(idx_list, res):
+        stack = torch.cat([res[name].float() for name in pp.GROUP_CHANNELS], 1).cpu().numpy()
+        for k, i in enumerate(idx_list):
+            want_frac[i] = stack[k]
+
+    sweep.run_sweep(range(5), load_frac, DEV, batch=2, dataset_len=n, sink=ref_sink_frac)
+    sink_b = sweep.PinnedGroupSink(on_batch, byte_images=True)
+    sweep.run_sweep(range(5), load_frac, DEV, batch=2, dataset_len=n, sink=sink_b)
+    assert sink_b.fallback_batches >= 1 and not sink_b.byte_images
+    for idx_list, arr, release in held:
+        for k, i in enumerate(idx_list):
+            assert np.array_equal(arr[k], want_frac[i]), i
+        release()
     with pytest.raises(ValueError):
         pkg.ops.scatter_channels_to_host(torch.zeros(2, 3, h, w, device=DEV), torch.zeros(2, 4, h, w), 2)  # channels 2..5 of 4
 
@@ -1871,7 +1899,7 @@ def test_bench_cfg5_legs_small(pkg):
     assert g["counters"]["pairs"] == 5 * g["counters"]["frames"]
     sw = d["cfg5_sweep_e2e"]
     assert "error" not in sw, sw
-    assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == 44 * 480 * 640 * 4 and sw["counters"]["frames"] == 48
+    assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == (26 * 4 + 18) * 480 * 640 and sw["counters"]["frames"] == 48
 
 
 @pytest.mark.parametrize("tag", ["cfg1_480x640", "cfg4_368x496", "cfg2_redweb", "cfg3_1080p"])
