@@ -1,5 +1,6 @@
 """Randomised parity soak (not part of the test suite): random shapes / batches / flows through the fused pair kernel, the
-general splat, the ragged bilateral, the fused 6-DoF pair and the batched augmentation, each checked against the CPU oracle
+general splat, the row-local splat, the ragged bilateral, the fused 6-DoF pair, the batched augmentation, the Telea fill and the
+host-buffer pipeline, each checked against the CPU oracle
 (bit-exact; the 6-DoF flow within the path's 1e-5 coordinate-relative tolerance).  `python tools/soak_parity.py SECONDS`."""
 import sys
 import time
@@ -193,11 +194,75 @@ def trial_augment(rng):
     return ok, f"augment {b}x{h}x{w} kinds {kinds}"
 
 
+def trial_splat_rows(rng):
+    """Row-local splat for horizontal warp flows against the oracle's FW.forward (ConcatFlow / BackFlow / plain), C = 2."""
+    h, w, b = int(rng.integers(1, 60)), int(rng.choice([rng.integers(1, 2049), rng.integers(1, 70)])), int(rng.integers(1, 4))
+    obj = rng.normal(0, 30, (b, 2, h, w)).astype(np.float32)
+    aux = rng.normal(0, 30, (b, 2, h, w)).astype(np.float32)
+    fx = rng.normal(0, rng.choice([2.0, 40.0]), (b, 1, h, w)).astype(np.float32)
+    if rng.random() < 0.5:
+        fx[rng.random(fx.shape) < 0.02] = np.nan
+    flow = np.concatenate([fx, np.where(rng.random(fx.shape) < 0.5, np.float32(-0.0), np.float32(0.0)).astype(np.float32)], 1)
+    depth = np.stack([depth_field(rng, h, w, rng.random() < 0.7) for _ in range(b)])[:, None]
+    if rng.random() < 0.4:
+        depth[rng.random(depth.shape) < 0.02] = 1000.0
+    epi = int(rng.integers(0, 3))
+    got = ops.splat_flow(cu(obj), cu(flow), cu(depth), epilogue=epi, aux=cu(aux) if epi == ops.EPI_CONCAT else None, horizontal=True)
+    ok = True
+    for k in range(b):
+        o, v, c, _, _ = oracle.fw_forward(obj[k], flow[k], depth[k])
+        want = (o + aux[k]) * v if epi == ops.EPI_CONCAT else ((o * -1.0) * v if epi == ops.EPI_BACK else o)
+        ok &= eq(got[0][k], want) and eq(got[1][k], v) and eq(got[2][k], c)
+    return ok, f"splat_rows {b}x{h}x{w} epilogue {epi}"
+
+
+def trial_telea(rng):
+    """Telea fill kernel against the layer-order restatement (small frames: the restatement is pure Python)."""
+    from oracle import inpaint as oinp
+
+    h, w, b = int(rng.integers(2, 28)), int(rng.integers(2, 36)), int(rng.integers(1, 4))
+    imgs = rng.integers(0, 256, (b, h, w, 3)).astype(np.uint8)
+    masks = (rng.random((b, h, w)) < rng.choice([0.05, 0.3, 0.6])).astype(np.uint8)
+    for k in range(b):
+        if rng.random() < 0.5:
+            r0, c0 = rng.integers(0, h), rng.integers(0, w)
+            masks[k, r0:r0 + rng.integers(1, h + 1), c0:c0 + rng.integers(1, w + 1)] = 1
+    radius = int(rng.choice([1, 2, 3, 3, 3, 4]))
+    got = ops.inpaint_telea(cu(np.ascontiguousarray(imgs.transpose(0, 3, 1, 2)).astype(np.float32)), cu(masks[:, None]), radius)
+    ok = True
+    for k in range(b):
+        want = oinp.telea(imgs[k], masks[k], radius, order="layer").transpose(2, 0, 1).astype(np.float32)
+        ok &= eq(got[k], want)
+    return ok, f"telea {b}x{h}x{w} radius {radius}"
+
+
+_pipes = {}
+
+
+def trial_pipeline(rng):
+    """Host-buffer pipeline (byte masks, verified image bytes with float fallback) against the oracle."""
+    h, w = int(rng.choice([8, 12, 20])), int(rng.choice([16, 24, 40]))
+    b = int(rng.integers(1, 9))
+    img = rng.integers(0, 256, (b, 3, h, w)).astype(np.float32)
+    if rng.random() < 0.3:
+        img[rng.integers(0, b)] += np.float32(rng.choice([0.5, 300.0, -2.0]))  # one frame a byte cannot carry
+    depth = np.stack([depth_field(rng, h, w, True) for _ in range(b)])[:, None]
+    sBf = rng.uniform(40, 55, b).astype(np.float32)
+    key = (h, w, int(rng.integers(0, 2)))
+    if key not in _pipes:
+        _pipes[key] = ops.PairPipeline(0, h, w, chunk_frames=int(rng.integers(1, 4)))
+    outs = [torch.full((b, c, h, w), 7.0).pin_memory() for c in (3, 1, 2, 2, 1, 1)]
+    _pipes[key].run(torch.from_numpy(img).pin_memory(), torch.from_numpy(depth).pin_memory(), torch.from_numpy(sBf), *outs)
+    want = oracle.disparity_pair(img, depth, sBf, nthreads=2)
+    return all(np.array_equal(o.numpy(), wv) for o, wv in zip(outs, want)), f"pipeline {b}x{h}x{w}"
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, counts, fails = time.time(), {}, []
-    trials = (trial_pair, trial_pair_ragged, trial_splat, trial_bilateral, trial_bilateral_masked, trial_reproject_pair, trial_augment)
+    trials = (trial_pair, trial_pair_ragged, trial_splat, trial_bilateral, trial_bilateral_masked, trial_reproject_pair, trial_augment,
+              trial_splat_rows, trial_telea, trial_pipeline)
     k = 0
     while time.time() - t0 < budget:
         fn = trials[k % len(trials)]
