@@ -54,9 +54,21 @@ packed_img = torch.cat([img[0].reshape(-1), img[1, :, :100, :150].reshape(-1)]) 
 packed = ops.disparity_pair_ragged(packed_img, packed_depth, torch.full((2,), 47.0, device=dev), shapes, offsets)
 print("ragged pairs:", [tuple(v.shape) for v in ops.ragged_views(packed[0], 3, shapes, offsets)])
 
+# 5c. utils.inpaint with the Telea fill on the device (cv2 on the host stays available: backend="cv2")
+filled = synthesis.inpaint(pair["img1"], pair["valid"], pair["collision"], backend="cuda")
+print("inpainted:", tuple(filled.shape), "holes filled:", int((pair["valid"] == 0).sum()))
+
+# 5d. host frames in, the reference's 44-channel group arrays out (page-locked host memory), sharded by image index
+from opticalflowfromdepth_b200 import sweep, synthetic  # noqa: E402
+
+got = []
+sink = sweep.PinnedGroupSink(lambda idx, arr, release: (got.append((idx, arr.shape)), release()))
+sweep.run_sweep(range(4), lambda i: synthetic.diml_frame(i, H, W), dev, batch=2, dataset_len=4, sink=sink)
+print("sweep:", got)
+
 # 6. the reference's driver: 121 .npz files per frame, then read one sample back like the training loader does
 with tempfile.TemporaryDirectory() as tmp:
-    driver = pp.PreprocessPlusAugment(dev, inpaint=None, quiet=True, compress=1, reader_compat=True)
+    driver = pp.PreprocessPlusAugment(dev, inpaint="cuda", quiet=True, compress=1, reader_compat=True)
     synthesis.set_seed(12345)
     driver(pp.SyntheticDataset(1, H, W)[0], f"{tmp}/0", is_stereo=False)
     driver.close()
