@@ -353,3 +353,26 @@ def test_frame_draws_batch_equals_per_frame_draws():
             for j in range(sBf.shape[0]):
                 w = want[k + j]
                 assert torch.equal(sBf[j], w[0]) and torch.equal(cam[j], w[1]) and torch.equal(T[j], w[2]), (bs, k + j)
+
+
+def test_group_sink_transport_default_follows_the_ranks_per_node():
+    """sweep.PinnedGroupSink: the image channels cross PCIe as verified bytes while PCIe is the limit (one or two ranks per node) and as
+    float planes when more ranks share the node's host memory (LOCAL_WORLD_SIZE > 2); an explicit argument wins."""
+    import os
+
+    from opticalflowfromdepth_b200 import sweep
+
+    saved = os.environ.get("LOCAL_WORLD_SIZE")
+    try:
+        for lws, want in ((None, True), ("1", True), ("2", True), ("4", False), ("8", False)):
+            if lws is None:
+                os.environ.pop("LOCAL_WORLD_SIZE", None)
+            else:
+                os.environ["LOCAL_WORLD_SIZE"] = lws
+            assert sweep.PinnedGroupSink().byte_images is want, lws
+            assert sweep.PinnedGroupSink(byte_images=True).byte_images is True and sweep.PinnedGroupSink(byte_images=False).byte_images is False
+    finally:
+        if saved is None:
+            os.environ.pop("LOCAL_WORLD_SIZE", None)
+        else:
+            os.environ["LOCAL_WORLD_SIZE"] = saved
