@@ -82,16 +82,31 @@ __global__ void __launch_bounds__(256, 3) telea_kernel(const __grid_constant__ T
     // per-warp tap table of phase 2: (2 range + 1)^2 taps x TAP_F floats {w, w*I[3], w*gix*rx[3], w*giy*ry[3], used}
     constexpr int TAP_F = 11;
     extern __shared__ float s_dyn[];
-    const int D = 2 * range + 1, NT = D * D;
+    // the taps of a pixel: the offsets (dk, dl) inside the circle dk^2 + dl^2 <= range^2 WITHOUT the centre (always a hole pixel), in
+    // OpenCV's loop order (k outer, l inner): 28 of the 49 window cells at range 3, so one round of the warp's lanes covers them all
+    const int D = 2 * range + 1;
+    int NT = 0;
+    for (int t = 0; t < D * D; ++t) {
+        const int dk = t / D - range, dl = t - (t / D) * D - range;
+        NT += (dk * dk + dl * dl <= range * range) && (dk | dl) != 0;
+    }
     const int lane = threadIdx.x & 31;
     const size_t gwarp = tid >> 5, nwarps = nth >> 5;
+    const int NTP = (D * D + 3) & ~3;                                 // table stride (>= NT, the host's allocation unit)
     float* s_dst = s_dyn;                                              // [NT]  distance factor of every tap offset
-    float* tw = s_dyn + ((NT + 3) & ~3) + (size_t)(threadIdx.x >> 5) * NT * TAP_F;
-    for (int t = threadIdx.x; t < NT; t += blockDim.x) {
-        const int dk = t / D - range, dl = t - (t / D) * D - range;
-        const float ry = (float)(-dk), rx = (float)(-dl);
-        const float len2 = rx * rx + ry * ry;
-        s_dst[t] = len2 > 0.f ? (float)(1. / ((double)len2 * sqrt((double)len2))) : 0.f;  // inpaint.cpp: 1 / (|r|^2 * sqrt(|r|^2))
+    int* s_off = reinterpret_cast<int*>(s_dyn + NTP);                 // [NT]  (dk << 16) | (dl & 0xFFFF)
+    float* tw = s_dyn + 2 * NTP + (size_t)(threadIdx.x >> 5) * NT * TAP_F;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int t = 0; t < D * D; ++t) {
+            const int dk = t / D - range, dl = t - (t / D) * D - range;
+            if (dk * dk + dl * dl > range * range || (dk | dl) == 0) continue;
+            const float ry = (float)(-dk), rx = (float)(-dl);
+            const float len2 = rx * rx + ry * ry;
+            s_dst[n] = (float)(1. / ((double)len2 * sqrt((double)len2)));  // inpaint.cpp: 1 / (|r|^2 * sqrt(|r|^2))
+            s_off[n] = (dk << 16) | (dl & 0xFFFF);
+            ++n;
+        }
     }
     __syncthreads();
 
@@ -224,10 +239,10 @@ __global__ void __launch_bounds__(256, 3) telea_kernel(const __grid_constant__ T
             else
                 gy = k_up ? (dist - t_up) : 0.0f;
             for (int t = lane; t < NT; t += 32) {
-                const int dk = t / D, dl = t - dk * D;
-                const int k = i - range + dk, l = j - range + dl;
+                const int off = s_off[t];
+                const int k = i + (off >> 16), l = j + (int)(short)(off & 0xFFFF);
                 float* slot = tw + t * TAP_F;
-                bool use = k > 0 && k < EH - 1 && l > 0 && l < EW - 1 && (l - j) * (l - j) + (k - i) * (k - i) <= range * range;
+                bool use = k > 0 && k < EH - 1 && l > 0 && l < EW - 1;
                 const int q = k * EW + l;
                 use = use && known(q);
                 slot[10] = use ? 1.0f : 0.0f;
@@ -273,24 +288,25 @@ __global__ void __launch_bounds__(256, 3) telea_kernel(const __grid_constant__ T
                 }
             }
             __syncwarp();
-            unsigned int byte = 0;
-            if (lane < 3) {
-                const int c = lane;
-                float Ia = 0.f, Jx = 0.f, Jy = 0.f, sw = 1.0e-20f;
+            // twelve lanes add up the taps, one running sum each (colour c = lane / 4; sum 0 = Ia, 1 = Jx, 2 = Jy, 3 = s), in tap order
+            float acc = (lane & 3) == 3 ? 1.0e-20f : 0.0f;
+            if (lane < 12) {
+                const int c = lane >> 2, a = lane & 3;
+                const int col = a == 0 ? 1 + c : (a == 1 ? 4 + c : (a == 2 ? 7 + c : 0));
                 for (int t = 0; t < NT; ++t) {
                     const float* slot = tw + t * TAP_F;
-                    if (slot[10] != 0.0f) {
-                        Ia += slot[1 + c];
-                        Jx -= slot[4 + c];
-                        Jy -= slot[7 + c];
-                        sw += slot[0];
-                    }
+                    if (slot[10] != 0.0f) acc = (a == 1 || a == 2) ? acc - slot[col] : acc + slot[col];
                 }
+            }
+            const int base = (lane < 12 ? lane : 0) & ~3;
+            const float Ia = __shfl_sync(0xFFFFFFFFu, acc, base), Jx = __shfl_sync(0xFFFFFFFFu, acc, base + 1);
+            const float Jy = __shfl_sync(0xFFFFFFFFu, acc, base + 2), sw = __shfl_sync(0xFFFFFFFFu, acc, base + 3);
+            if (lane < 12 && (lane & 3) == 0) {
+                const int c = lane >> 2;
                 const float sat = (float)(Ia / sw + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f) + 0.5f);
                 int v = __float2int_rn(sat);  // saturate_cast<uchar>(float): round to nearest even, saturate
                 if (!(sat == sat)) v = 0;
-                byte = (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v));
-                I[(size_t)c * hw + (size_t)(i - 1) * W + (j - 1)] = (unsigned char)byte;  // commit the colour
+                I[(size_t)c * hw + (size_t)(i - 1) * W + (j - 1)] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));  // commit the colour
             }
             __syncwarp();
             if (lane == 0) {  // commit T and the layer, enqueue the unfilled 4-neighbours for the next layer
@@ -366,8 +382,11 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
     for (int k = 0; k < 3; ++k) P.listb[k] = (unsigned int*)w, w += align256(nb * hw * 4);
     P.stageT = (float*)w, w += align256(nb * ehw * 4);
     int sms = 0, per_sm = 0;
-    const int NT = (2 * range + 1) * (2 * range + 1);
-    const size_t smem = ((size_t)((NT + 3) & ~3) + (size_t)8 * NT * 11) * sizeof(float);  // dst table + 8 warps x NT taps x 11 floats
+    const int D2 = (2 * range + 1) * (2 * range + 1);
+    int NT = 0;  // taps inside the circle, centre excluded
+    for (int dk = -range; dk <= range; ++dk)
+        for (int dl = -range; dl <= range; ++dl) NT += (dk * dk + dl * dl <= range * range) && (dk | dl) != 0;
+    const size_t smem = ((size_t)2 * ((D2 + 3) & ~3) + (size_t)8 * NT * 11) * sizeof(float);  // dst + offset tables, 8 warps x NT taps x 11 floats
     int rc = launch_plan(fn, (const void*)telea_kernel, 256, smem, &sms, &per_sm);
     if (rc) return rc;
     int dev = 0, coop = 0;
