@@ -1000,6 +1000,42 @@ def test_reproject_pair_equals_unfused_path(pkg):
                 assert torch.equal(x, y)
 
 
+def test_reproject_pair_guarded_divisions_extreme_operands(pkg):
+    """ztest_reproject_kernel shares one refined reciprocal between the four divisions of the projection and guards them with one
+    range test per pixel; a pixel outside the guarded range is recomputed with the IEEE division.  Depths and cameras that drive
+    z + eps and the projected coordinates to 0, denormals, 1e+-30, inf and NaN must still give the flow of reproject_flow bit for bit
+    (NaN payloads included) and the same splat - in both grid shapes (row-looping for big batches, 64-pixel segments for small
+    ones), with and without the counter block."""
+    rng = np.random.default_rng(77)
+    for (h, w, n) in ((64, 130, 2), (40, 72, 160)):
+        img = cu(rng.integers(0, 256, (n, 3, h, w)).astype(np.float32))
+        depth = rng.uniform(1, 99, (n, 1, h, w)).astype(np.float32)
+        special = np.array([0.0, -0.0, 1e-45, 1e-38, 1e-30, 1e-13, 1e13, 1e30, 3e38, np.inf, -np.inf, np.nan, -5.0, 1000.0, 100.0], np.float32)
+        pick = rng.random(depth.shape) < 0.2
+        depth[pick] = special[rng.integers(0, len(special), int(pick.sum()))]
+        depth = cu(depth)
+        K, invK = pkg.synthesis.Plausible.K((h, w))
+        cams = []
+        for k in range(n):
+            torch.manual_seed(900 + k)
+            c = pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0])
+            if k % 4 == 1:
+                c[0, 9 + 8:9 + 12] = torch.tensor([0.0, 0.0, 0.0, 0.0])      # P row 2 = 0: z + eps = eps = 1e-7 for every pixel
+            if k % 4 == 2:
+                c[0, 9 + 8:9 + 12] = torch.tensor([0.0, 0.0, 1e-20, -1e-7])  # z + eps ~ 0 / denormal / tiny
+            if k % 4 == 3:
+                c[0, 9:9 + 4] *= 1e25                                          # projected x overflows / huge
+            cams.append(c)
+        cam = torch.cat(cams).to(DEV)
+        flow = pkg.ops.reproject_flow(depth, cam)
+        a = pkg.ops.frame_splat(img, depth, flow, None, want_raw_valid=True)
+        for counters in (None, pkg.ops.new_counters(torch.device(DEV))):
+            b = pkg.ops.reproject_pair(img, depth, cam, None, want_raw_valid=True, counters=counters)
+            assert torch.equal(b[3].view(torch.int32), flow.view(torch.int32)), "flow bits differ"
+            for x, y in zip(a, (b[0], b[1], b[2], b[4], b[5], b[6])):
+                assert torch.equal(x.view(torch.int32), y.view(torch.int32))
+
+
 def test_cfg3_full_size_1080p_batch32_properties_and_sampled_frames(pkg):
     """BASELINE config 3 at its full size (32 x 1080x1920, random 6-DoF pose per frame, C=7 splat + hole mask): counters
     account for every pixel; masks are 0/1 and consistent; the batch result does not depend on the batch (frame b of the
