@@ -480,6 +480,21 @@ def run_ours(args):
                                                      "what": "augment_flow_batch -> ofd_augment_pairs: geometric branch (flip/rotate/shear per sample), one native call = "
                                                              "1 batched special-flow launch + 6 batched splats; parameters from sample_special_params (2 generator calls "
                                                              "per batch); *_reference_draw_order draws per sample in the reference's get_random order (host-bound)"}
+                # cfg4 as BASELINE.json states it: the augmentation FUSED WITH FLOW SYNTHESIS - raw frames in, the trainers' 9-tuple out
+                # (inloop.InLoopSampler: normalize_depth -> 5-pair group -> per-sample pair / augmentation -> tuple; host draws included)
+                from opticalflowfromdepth_b200 import inloop
+                raw_dep = torch.from_numpy(np.stack([f[1] for f in fr])).to(dev)
+                sampler = inloop.InLoopSampler(dev, seed=4)
+
+                def istep():
+                    sampler(a_img, raw_dep).raft_tuple()
+
+                ti = timed(istep, 30, 5, sync, barrier) / 30
+                extras["cfg4_inloop_368x496_b8"] = {"samples_per_s": Fa / ti, "ms_per_step": 1e3 * ti, "samples_per_step": Fa,
+                                                    "what": "inloop.InLoopSampler: raw RGB-D frames -> normalize_depth -> 5-pair group (7 splats) -> per sample a random "
+                                                            "pair group 0..2, augmentation slot 0..11 (geometric 5-7 through ofd_augment_pairs, photometric 0-2) and "
+                                                            "augmented image -> (img1, img2, flow, back_flow, depth1, depth2, valid, back_valid, label) on the device; "
+                                                            "replaces writing and re-reading 121 .npz files per frame (preprocess.py:453-476, dataloader.py:60-157)"}
             except Exception as e:
                 extras["cfg4_augment_368x496_b8"] = {"error": repr(e)}
         if "ref" not in skip:

@@ -11,6 +11,7 @@ Product layout (only what the path needs):
     sweep.py             multi-GPU sharding of frames by image index + end-of-run counter reduction, host-in / host-out sweep
     preprocess.py        the reference's driver (PreprocessPlusAugment, CLI) over the fused path, asynchronous .npz writer
     dataloader.py        the training-side reader of those files (host code)
+    inloop.py            in-loop alternative to writing / reading those files: frames -> training samples per batch on the GPU (cfg4)
     synthetic.py         seeded DIML- / ReDWeb-shaped synthetic frames for tests and benches
 """
 from . import _lib, ops  # noqa: F401

@@ -170,6 +170,15 @@ def frame_draws_batch(seeds, size):
         rows_s.append(sg)
     u = torch.tensor(rows_u, dtype=torch.float32).reshape(n, 7)
     sg = torch.tensor(rows_s, dtype=torch.int64).reshape(n, 6)
+    return frame_params_from_uniforms(u, sg, size)
+
+
+def frame_params_from_uniforms(u, sg, size):
+    """The float32 arithmetic of frame_draws_batch on given draws: u[n,7] uniforms in [0,1) (disparity scale, 3 axis-angle and 3
+    translation magnitudes) and sg[n,6] signs (+-1) -> (sBf[n], cam[n,21], T1[n,4,4]).  inloop.InLoopSampler draws u and sg in two
+    generator calls per batch (the distributions of the reference's draws, not its per-frame call sequence)."""
+    h, w = size
+    n = u.shape[0]
     sBf = (u[:, 0] * 0.3 + torch.tensor(0.8)) * Plausible.B() * Plausible.f()
     ang = sg[:, 0:3] * (u[:, 1:4] * (math.pi * (1. / 36.)) + torch.tensor(math.pi * (1. / 36.)))
     tr = sg[:, 3:6] * (u[:, 4:7] * 0.1 + torch.tensor(0.1))

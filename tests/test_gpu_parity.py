@@ -1985,3 +1985,56 @@ def test_bench_default_arm_prints_the_contract_line():
     assert e["value"] < d["value"]  # host buffers cross PCIe: never the device-resident number
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["counters"]["frames"] == 32 and d["counters"]["hit"] + d["counters"]["hole"] == 32 * 480 * 640
+
+
+# BASELINE config 4 as stated: in-loop augmentation fused with flow synthesis (frames -> training samples on the GPU)
+def test_inloop_sampler_equals_the_prebaked_files(pkg):
+    """inloop.InLoopSampler: sample b of a batch == the 8-channel array preprocess.PreprocessPlusAugment would store in
+    {g}_{a}_{which+1}.npz for that frame with the same draws (preprocess.py:453-476), for every pair group the trainers read (0..2),
+    geometric and photometric types, both sets; plus the trainers' 9-tuple conventions (adjusted_RAFT/core/datasets.py:281-288)."""
+    from opticalflowfromdepth_b200 import inloop, preprocess
+    h, w, B = 64, 96, 12
+    fr = [pkg.synthetic.diml_frame(300 + k, h, w) for k in range(B)]
+    img = cu(np.stack([f[0] for f in fr]))
+    depth = cu(np.stack([f[1] for f in fr]))
+    sampler = inloop.InLoopSampler(DEV, seed=5)
+    plan = sampler.draw(B, (h, w))
+    plan.group = [0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2]
+    plan.slot = [1, 2, 3, 0, 4, 8, 5, 6, 7, 9, 10, 11]           # types 5 6 7 0 1 2 5 6 7 5 6 7
+    plan.which = [0, 1, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0]
+    types = plan.types
+    gen = torch.Generator().manual_seed(11)
+    special = pkg.synthesis.sample_special_params([t for t in types if t >= 5], (h, w), gen)
+    it = iter(special)
+    plan.draws = [next(it) if t >= 5 else inloop._photometric_draws(t, gen) for t in types]
+    batch = sampler(img, depth, plan)
+    assert batch.flow.shape == (B, 2, h, w) and batch.label.shape == (B, 4)
+    ppa = preprocess.PreprocessPlusAugment(DEV, inpaint=None, quiet=True)
+    try:
+        depth0 = pkg.ops.normalize_depth(depth)
+        for b in range(B):
+            group = pkg.synthesis.synthesize_group(img[b:b + 1], depth0[b:b + 1], plan.sBf[b:b + 1].to(DEV), plan.cam[b:b + 1].to(DEV))
+            torch.manual_seed(1000 + b)
+            row = preprocess.PreprocessPlusAugment.draw_augmentations(h, w)[0]
+            row[plan.slot[b]] = plan.draws[b]
+            block = ppa.augment_pair_block(group, plan.group[b], row)
+            want = block[plan.slot[b], plan.which[b]]
+            got = batch.file_arrays(b)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (b, plan.group[b], types[b], plan.which[b])
+            # the untouched half of the sample is the pair's other image / depth
+            names = preprocess.GROUP_PAIRS[plan.group[b]]
+            if plan.which[b] == 0:
+                assert torch.equal(batch.img2[b], group[names[2]][0]) and torch.equal(batch.img2_depth[b], group[names[3]][0])
+            else:
+                assert torch.equal(batch.img1[b], group[names[0]][0]) and torch.equal(batch.img1_depth[b], group[names[1]][0])
+            assert int(batch.label[b].argmax()) == max(0, types[b] - 4) and float(batch.label[b].sum()) == 1.0
+    finally:
+        ppa.close()
+    i1, i2, fl, bf, d1, d2, valid, back_valid, label = batch.raft_tuple()
+    assert valid.shape == (B, h, w) and bool(((valid == 0) | (valid == 1)).all())
+    assert bool((valid[d1[:, 0] == 100] == 0).all()) and bool((back_valid[d2[:, 0] == 100] == 0).all())
+    # a fresh draw works end to end and is reproducible from the seed
+    a = inloop.InLoopSampler(DEV, seed=9)(img, depth)
+    b2 = inloop.InLoopSampler(DEV, seed=9)(img, depth)
+    assert a.plan.slot == b2.plan.slot and torch.equal(a.flow, b2.flow) and torch.equal(a.img1, b2.img1)
+
