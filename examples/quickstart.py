@@ -76,5 +76,11 @@ with tempfile.TemporaryDirectory() as tmp:
     np.random.seed(0)
     img0, img1, flow, d0, label = dataloader.AugmentedFolder(tmp, 1, crop_size=(128, 160))[0]
     print("sample:", tuple(img0.shape), tuple(flow.shape), label.tolist())
+# 7. ... or skip the files: synthesise the trainers' samples inside the training loop (BASELINE config 4)
+from opticalflowfromdepth_b200 import inloop  # noqa: E402
+
+raw = torch.from_numpy(np.stack([synthetic.diml_frame(k, H, W)[1] for k in range(B)])).to(dev)  # un-normalised depth
+i1, i2, fl, bfl, d1, d2, valid, back_valid, label = inloop.InLoopSampler(dev, seed=0)(img, raw).raft_tuple()
+print("in-loop batch:", tuple(i1.shape), tuple(fl.shape), label.argmax(1).tolist())
 torch.cuda.synchronize()
 print("ok")

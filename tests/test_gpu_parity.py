@@ -981,8 +981,9 @@ def test_frame_splat_vs_oracle_composition(pkg):
 
 
 def test_reproject_pair_equals_unfused_path(pkg):
-    """Flow computed inside the z-test == reproject_flow -> frame_splat."""
-    for (h, w, n) in ((480, 640, 3), (97, 131, 2)):
+    """Flow computed inside the z-test == reproject_flow -> frame_splat.  Frames of a megapixel and more take the z-test variant that
+    looks at the key before the atomic of a border-clamped source (1080p case)."""
+    for (h, w, n) in ((480, 640, 3), (97, 131, 2), (1080, 1920, 2)):
         img, depth = _cfg1_inputs(pkg, n, h, w)
         K, invK = pkg.synthesis.Plausible.K((h, w))
         cams = []
