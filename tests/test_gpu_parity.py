@@ -1037,6 +1037,40 @@ def test_reproject_pair_guarded_divisions_extreme_operands(pkg):
                 assert torch.equal(x.view(torch.int32), y.view(torch.int32))
 
 
+def test_reproject_pair_row_constant_rays_and_general_inv_k(pkg):
+    """The fused 6-DoF z-test must not assume a pinhole inv_K: signed zeros in inv_K[1][0] / inv_K[2][0], a skewed inv_K and one with x and
+    y terms in every row must all give reproject_flow's flow bit for bit and the same splat (a variant of the kernel that hoisted the two
+    x-free rays out of the row walk was measured and dropped - profiles/r2/tune_rearm.txt - this is the case that guarded it)."""
+    rng = np.random.default_rng(78)
+    h, w, n = 56, 200, 12
+    img = cu(rng.integers(0, 256, (n, 3, h, w)).astype(np.float32))
+    depth = cu(rng.uniform(1, 99, (n, 1, h, w)).astype(np.float32))
+    K, invK = pkg.synthesis.Plausible.K((h, w))
+    cams = []
+    for k in range(n):
+        torch.manual_seed(1200 + k)
+        c = pkg.geometry.camera_constants(K, invK, pkg.synthesis.Plausible.random_motion(1. / 36., 1. / 36., 0.1, 0.1)[0])
+        m = k % 6
+        if m == 1:
+            c[0, 3], c[0, 6] = -0.0, -0.0            # hoisted, negative zeros
+        if m == 2:
+            c[0, 3], c[0, 6] = 0.0, -0.0
+        if m == 3:
+            c[0, 3] = 1e-4                           # general loop: ray 1 depends on x
+        if m == 4:
+            c[0, 6] = -3e-5                          # general loop: ray 2 depends on x
+        if m == 5:
+            c[0, 1], c[0, 7], c[0, 3], c[0, 6] = 2e-4, 1e-5, -1e-4, 2e-5
+        cams.append(c)
+    cam = torch.cat(cams).to(DEV)
+    flow = pkg.ops.reproject_flow(depth, cam)
+    a = pkg.ops.frame_splat(img, depth, flow, None, want_raw_valid=True)
+    b = pkg.ops.reproject_pair(img, depth, cam, None, want_raw_valid=True)
+    assert torch.equal(b[3].view(torch.int32), flow.view(torch.int32)), "flow bits differ"
+    for x, y in zip(a, (b[0], b[1], b[2], b[4], b[5], b[6])):
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32))
+
+
 def test_cfg3_full_size_1080p_batch32_properties_and_sampled_frames(pkg):
     """BASELINE config 3 at its full size (32 x 1080x1920, random 6-DoF pose per frame, C=7 splat + hole mask): counters
     account for every pixel; masks are 0/1 and consistent; the batch result does not depend on the batch (frame b of the

@@ -75,8 +75,8 @@ if __name__ == "__main__":
             env = dict(os.environ, OFD_ZREP_GENERIC=gen)
             print(f"== OFD_ZREP_GENERIC={gen} ({'generic ztest_rows_kernel<ProdReproject>' if gen == '1' else 'ztest_reproject_kernel'})", flush=True)
             subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
-        # compile-time variants built beforehand with _build.build_variant (opticalflowfromdepth_b200/build/variants/zrep_*.so)
+        # compile-time variants built beforehand with _build.build_variant (opticalflowfromdepth_b200/build/variants/*.so)
         vdir = ROOT / "opticalflowfromdepth_b200" / "build" / "variants"
-        for lib in sorted(vdir.glob("zrep_*.so")) if vdir.exists() else []:
+        for lib in sorted(vdir.glob("*.so")) if vdir.exists() else []:
             print(f"== variant {lib.name}", flush=True)
             subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, OFD_ZREP_GENERIC="0", OFD_LIB_PATH=str(lib)), check=False)
