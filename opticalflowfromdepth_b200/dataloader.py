@@ -21,10 +21,16 @@ from torch.utils import data
 num_classes = 1 + 3  # dataloader.py:11
 
 
-def _to_tensor(chw: np.ndarray) -> torch.Tensor:
-    """T.ToTensor() on the float HWC view of a CHW array (dataloader.py:74-77,104-106): a float array is not rescaled, so
-    the transform is the identity on CHW data."""
-    return torch.from_numpy(np.ascontiguousarray(chw))
+def _to_tensor(chw: np.ndarray, size=None) -> torch.Tensor:
+    """The reader's transform (dataloader.py:68-77,104-106,118): T.ToTensor() on the float HWC view of a CHW array - a float array
+    is not rescaled, so that part is the identity on CHW data - followed by T.Resize(size) when `size` is given (torchvision's
+    host-side resize with its default arguments, exactly the reference's call)."""
+    t = torch.from_numpy(np.ascontiguousarray(chw))
+    if size is not None:
+        import torchvision.transforms as T
+
+        t = T.Resize(size)(t)
+    return t
 
 
 def _flip_and_crop(img0, img1, img0_depth, flow, h, w, do_flip, h_flip_prob, v_flip_prob, crop_size):
@@ -50,11 +56,11 @@ def _one_hot(label_type: int) -> torch.Tensor:
 
 
 class AugmentedDataset(data.Dataset):
-    """dataloader.AugmentedDataset (dataloader.py:60-157).  `size` (a torchvision Resize in the reference) is not supported."""
+    """dataloader.AugmentedDataset (dataloader.py:60-157).  `size`: every tensor goes through T.Resize(size) after the channel slicing, as
+    in the reference (flips and crop offsets still use the file's h and w, dataloader.py:84,144-146)."""
 
     def __init__(self, normalize_dataset=True, size=None, crop_size=None, do_flip=True):
-        if size is not None:
-            raise NotImplementedError("size= (T.Resize) is not part of this reader")
+        self.size = size
         self.normalize_dataset = normalize_dataset
         self.crop_size = crop_size
         self.do_flip = do_flip
@@ -82,7 +88,7 @@ class AugmentedDataset(data.Dataset):
             img0, img0_depth, img1 = group[0:3], group[3:4], group[8:11]
         else:
             raise ValueError("random_group must be 0, 1 or 2")
-        img0, img1, img0_depth = _to_tensor(img0), _to_tensor(img1), _to_tensor(img0_depth)
+        img0, img1, img0_depth = _to_tensor(img0, self.size), _to_tensor(img1, self.size), _to_tensor(img0_depth, self.size)
         if self.normalize_dataset:  # :108-116 (flow.x / h and flow.y / w, as the reference has it)
             if augment_img == 0:
                 img_depth_flow[4] = img_depth_flow[4] / h
@@ -92,7 +98,7 @@ class AugmentedDataset(data.Dataset):
                 img_depth_flow[0] = img_depth_flow[0] / h
                 img_depth_flow[1] = img_depth_flow[1] / w
                 img_depth_flow[7] = img_depth_flow[7] / 100
-        t = _to_tensor(img_depth_flow)
+        t = _to_tensor(img_depth_flow, self.size)
         if augment_img == 0:  # :120-126
             img0, img0_depth, flow = t[0:3], t[3:4], t[4:6]
         else:
@@ -106,8 +112,7 @@ class DepthToFlowDataset(data.Dataset):
     """dataloader.DepthToFlowDataset (dataloader.py:160-232): pairs straight from group.npz, label 0."""
 
     def __init__(self, normalize_dataset=True, size=None, crop_size=None, do_flip=True):
-        if size is not None:
-            raise NotImplementedError("size= (T.Resize) is not part of this reader")
+        self.size = size
         self.normalize_dataset = normalize_dataset
         self.crop_size = crop_size
         self.do_flip = do_flip
@@ -125,7 +130,7 @@ class DepthToFlowDataset(data.Dataset):
             img0, img0_depth, img1, flow = group[0:3], group[3:4], group[8:11], group[20:22]
         else:
             raise ValueError("random_group must be 0, 1 or 2")
-        img0, img1, img0_depth, flow = (_to_tensor(np.array(a)) for a in (img0, img1, img0_depth, flow))
+        img0, img1, img0_depth, flow = (_to_tensor(np.array(a), self.size) for a in (img0, img1, img0_depth, flow))
         img0, img1, img0_depth, flow = _flip_and_crop(img0, img1, img0_depth, flow, h, w, self.do_flip, self.h_flip_prob,
                                                       self.v_flip_prob, self.crop_size)
         return img0, img1, flow, img0_depth, _one_hot(0)
@@ -135,8 +140,8 @@ class AugmentedFolder(AugmentedDataset):
     """AugmentedDIML / AugmentedReDWeb (dataloader.py:235-268) over any output directory of the preprocess driver:
     item idx draws a random pair group (0..2), augmentation (0..11) and set (1..2) from `{root}/{idx}/`."""
 
-    def __init__(self, root, n_frames, normalize_dataset=True, crop_size=None):
-        super().__init__(normalize_dataset=normalize_dataset, crop_size=crop_size)
+    def __init__(self, root, n_frames, normalize_dataset=True, size=None, crop_size=None):
+        super().__init__(normalize_dataset=normalize_dataset, size=size, crop_size=crop_size)
         self.root, self.n_frames = root, n_frames
 
     def __len__(self):

@@ -485,6 +485,38 @@ def reader_case(pp, ref_utils):
     return out
 
 
+def reader_size_case(pp, ref_utils):
+    """The reference's reader with `size=` (T.Compose([ToTensor, Resize(size)]), dataloader.py:68-72,168-172): one upscaling and one
+    downscaling AugmentedDataset case (the second with a crop, whose offsets the reference draws from the FILE's h and w) and one
+    DepthToFlowDataset case.  torchvision's defaults of this image (0.26: antialiased bilinear)."""
+    import tempfile
+
+    import dataloader as ref_dl
+
+    g = np.load(HERE / "preprocess_case.npz")
+    out = {}
+    cases = [("1_5_1", 1, 13, (45, 66), None, True), ("2_3_2", 2, 14, (20, 30), (12, 16), True)]
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(f"{tmp}/group.npz", img_depth_flow=g["group__data"])
+        for k, (stem, grp, seed, size, crop, norm) in enumerate(cases):
+            np.savez(f"{tmp}/{stem}.npz", img_depth_flow=g[f"{stem}__data"], augment_flow_type=g[f"{stem}__type"],
+                     augment_img=int(stem[-1]) - 1)
+            ds = ref_dl.AugmentedDataset(normalize_dataset=norm, size=size, crop_size=crop, do_flip=True)
+            np.random.seed(seed)
+            res = ds.getitem_from_npz(f"{tmp}/{stem}.npz", f"{tmp}/group.npz", grp, 0)
+            for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+                out[f"aug{k}_{name}"] = t.numpy()
+            out[f"aug{k}_meta"] = np.array([grp, seed, size[0], size[1], -1 if crop is None else crop[0], -1 if crop is None else crop[1], int(norm)])
+            out[f"aug{k}_stem"] = np.array(stem)
+        ds = ref_dl.DepthToFlowDataset(size=(33, 50), crop_size=None, do_flip=True)
+        np.random.seed(15)
+        res = ds.getitem_from_npz(f"{tmp}/group.npz", 1, 0)
+        for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+            out[f"d2f0_{name}"] = t.numpy()
+        out["d2f0_meta"] = np.array([1, 15, 33, 50])
+    return out
+
+
 def main():
     torch.set_num_threads(1)
     pp, ref_utils, ref_geo, ref_bil, RefFW = install_reference()
@@ -500,6 +532,7 @@ def main():
         "inpaint_case": lambda: inpaint_case(pp, ref_utils),
         "preprocess_case": lambda: preprocess_case(pp, ref_utils),
         "reader_case": lambda: reader_case(pp, ref_utils),
+        "reader_size_case": lambda: reader_size_case(pp, ref_utils),
     }
     only = set(sys.argv[1:])
     for name, job in jobs.items():

@@ -212,6 +212,35 @@ def test_reader_matches_the_reference_dataloader(golden, tmp_path):
     assert img0.shape == (3, 8, 12) and flow.shape == (2, 8, 12) and depth.shape == (1, 8, 12) and label.tolist() == [1, 0, 0, 0]
 
 
+def test_reader_size_option_matches_the_reference_dataloader(golden, tmp_path):
+    """`size=` (the reference's T.Compose([ToTensor, Resize(size)]), dataloader.py:68-72,168-172): up- and downscaling, with and
+    without a crop, against the reference's own reader on the same files and seed (golden reader_size_case): bit-exact."""
+    import numpy as np
+
+    from opticalflowfromdepth_b200 import dataloader as dl
+
+    g, pc = golden("reader_size_case"), golden("preprocess_case")
+    np.savez(tmp_path / "group.npz", img_depth_flow=pc["group__data"])
+    k = 0
+    while f"aug{k}_meta" in g:
+        grp, seed, sh, sw, ch, cw, norm = (int(v) for v in g[f"aug{k}_meta"])
+        stem = str(g[f"aug{k}_stem"])
+        np.savez(tmp_path / f"{stem}.npz", img_depth_flow=pc[f"{stem}__data"], augment_flow_type=pc[f"{stem}__type"])
+        ds = dl.AugmentedDataset(normalize_dataset=bool(norm), size=(sh, sw), crop_size=None if ch < 0 else (ch, cw), do_flip=True)
+        np.random.seed(seed)
+        res = ds.getitem_from_npz(tmp_path / f"{stem}.npz", tmp_path / "group.npz", grp, 0)
+        for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+            assert t.shape == g[f"aug{k}_{name}"].shape and np.array_equal(t.numpy(), g[f"aug{k}_{name}"]), (k, name)
+        k += 1
+    assert k == 2
+    grp, seed, sh, sw = (int(v) for v in g["d2f0_meta"])
+    np.random.seed(seed)
+    res = dl.DepthToFlowDataset(size=(sh, sw), crop_size=None).getitem_from_npz(tmp_path / "group.npz", grp, 0)
+    for name, t in zip(("img0", "img1", "flow", "depth", "label"), res):
+        assert np.array_equal(t.numpy(), g[f"d2f0_{name}"]), name
+    assert res[0].shape == (3, sh, sw)
+
+
 def test_npz_writer_files_read_back_with_numpy(tmp_path):
     """preprocess.NpzWriter / save_npz write the reference's container (np.savez_compressed: a zip of .npy members) at any deflate
     level: np.load returns the same keys, dtypes and values; level 6 is byte-compatible with what np.savez_compressed stores."""
