@@ -167,10 +167,12 @@ class PreprocessPlusAugment(nn.Module):
         return res
 
     # ---- the 60 augmentations (preprocess.py:453-476) ------------------------------------------------------------------
-    def augment_pair_block(self, group: Dict[str, torch.Tensor], gi: int, draws) -> torch.Tensor:
+    def augment_pair_block(self, group: Dict[str, torch.Tensor], gi: int, draws, defer_fill: bool = False):
         """All 12 augmentations of group pair `gi` as ONE device tensor [12, 2, 8, H, W]: [k, 0] is file {gi}_{k}_1
         (set1[0:4] = aug_img0, aug_depth0, aug0_flow, back_aug0_flow) and [k, 1] is file {gi}_{k}_2 (set2[2:6] = aug1_flow,
-        back_aug1_flow, aug_img1, aug_depth1), preprocess.py:459-476.  `draws[k]` are the pre-drawn host parameters."""
+        back_aug1_flow, aug_img1, aug_depth1), preprocess.py:459-476.  `draws[k]` are the pre-drawn host parameters.
+        defer_fill: the block comes back with the un-inpainted warped images in place together with what `fill_blocks` needs to
+        inpaint the images of several blocks in one batched call: returns (block, pending)."""
         fAB64 = group[GROUP_PAIRS[gi][4]] if group[GROUP_PAIRS[gi][4]].dtype == torch.float64 else None
         imgA, depA, imgB, depB, fAB, bAB = (group[n].float() for n in GROUP_PAIRS[gi])
         h, w = imgA.shape[-2:]
@@ -186,7 +188,7 @@ class PreprocessPlusAugment(nn.Module):
                 r = ops.augment_pairs(rep(imgA), rep(depA), rep(imgB), rep(depB), rep(fAB), rep(bAB),
                                       [AUGMENT_TYPES[k] for k in geo], [draws[k] for k in geo])
             a_img0, a_img1 = r["aug_img0"], r["aug_img1"]
-            if self.inpaint is not None:
+            if self.inpaint is not None and not defer_fill:
                 a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
                 a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
             block[geo, 0] = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)
@@ -197,7 +199,30 @@ class PreprocessPlusAugment(nn.Module):
                     pb = photometric_apply(imgB[0], float(t), draws[k])
                     block[k, 0] = torch.cat((pa, depA[0], fAB[0], bAB[0]), 0)
                     block[k, 1] = torch.cat((fAB[0], bAB[0], pb, depB[0]), 0)
+        if defer_fill:
+            return block, (geo, r["valid_img0"], r["collision_img0"], r["valid_img1"], r["collision_img1"])
         return block
+
+    def fill_blocks(self, blocks, pendings) -> None:
+        """utils.inpaint of every warped image of the given augmentation blocks (preprocess.py:127,133: 2 x 9 per group pair, 90 per
+        frame) in ONE call of the hook instead of ten: the device fill is bound by its per-layer grid barrier at 9 images per call
+        and costs half as much per image at 90 (profiles/r2/probe_telea_batch.txt); a fill never looks across images, so the files are
+        the same.  In place: block[geo, 0, 0:3] (aug_img0) and block[geo, 1, 4:7] (aug_img1)."""
+        if self.inpaint is None or not blocks:
+            return
+        with torch.cuda.device(self.device):
+            imgs, valids, colls, where = [], [], [], []
+            for b, (block, (geo, v0, c0, v1, c1)) in enumerate(zip(blocks, pendings)):
+                imgs += [block[geo, 0, 0:3], block[geo, 1, 4:7]]
+                valids += [v0, v1]
+                colls += [c0, c1]
+                where += [(b, 0, slice(0, 3)), (b, 1, slice(4, 7))]
+            filled = self.inpaint(torch.cat(imgs).contiguous(), torch.cat(valids), torch.cat(colls))
+            o = 0
+            for (b, which, ch), im in zip(where, imgs):
+                n = im.shape[0]
+                blocks[b][pendings[b][0], which, ch] = filled[o:o + n]
+                o += n
 
     @staticmethod
     def draw_augmentations(h: int, w: int):
@@ -245,8 +270,11 @@ class PreprocessPlusAugment(nn.Module):
             t1 = time.time()
             h, w = group["img0"].shape[-2:]
             plan = self.draw_augmentations(h, w)
+            built = [self.augment_pair_block(group, gi, plan[gi], defer_fill=True) for gi in range(len(GROUP_PAIRS))]
+            self.fill_blocks([b for b, _ in built], [p for _, p in built])
             for gi in range(len(GROUP_PAIRS)):
-                block = self._to_host(self.augment_pair_block(group, gi, plan[gi]))
+                block = self._to_host(built[gi][0])
+                built[gi] = None  # the device block goes back to the allocator once its copy has landed
                 for k, t in enumerate(AUGMENT_TYPES):
                     for which in (0, 1):
                         extra = {"augment_img": which} if self.reader_compat else {}

@@ -483,6 +483,18 @@ def synthesize_pairs(img0, depth0, sBf, want_flow=True, want_collision=True, cou
 
 
 @torch.no_grad()
+def _fill_leaves(inpaint, leaves):
+    """The inpainted images 2, 3, 2' and 3' of a group are results only - nothing downstream reads them (preprocess.py:381,393,410,423) -
+    so their four fills go out as ONE batched call: the device fill is bound by its per-layer grid barrier at small batches (a batch of
+    4 x B images costs little more than one of B, tools/probe_telea_batch.py), and a fill never looks across images, so the values are
+    those of four separate calls.  leaves: [(img, valid, collision)] x 4 -> [img] x 4."""
+    if inpaint is None:
+        return [im for im, _, _ in leaves]
+    n = leaves[0][0].shape[0]
+    out = inpaint(torch.cat([im for im, _, _ in leaves]), torch.cat([v for _, v, _ in leaves]), torch.cat([c for _, _, c in leaves]))
+    return list(out.split(n))
+
+
 def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
     """The reference's 5-pair group of one frame batch (preprocess.py:356-432), inpaint optional, all on the GPU:
     7 splats with the flow producers and consumers fused into them = 13 kernel launches per batch chunk
@@ -504,21 +516,19 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         img1 = fill(img1, valid1, coll1)
         # pair 1->2: random camera motion from view 1 (preprocess.py:372-382); flow computed inside the z-test
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, want_collision=wc, counters=counters)
-        img2 = fill(img2, valid2, coll2)
         # pair 0->3: the same motion from view 0 (preprocess.py:385-394)
         img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, want_collision=wc, counters=counters)
-        img3 = fill(img3, valid3, coll3)
         # pair 0->2': concatenated flow (preprocess.py:400-411)
         flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False,
                                                     horizontal=True)  # back01.y == +0: row-local kernel, unless counters ask for the tie census
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
-        img2p = fill(img2p, valid2p, coll2p)
         # pair 1->3': (preprocess.py:414-424)
         flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False,
                                                     horizontal=True)  # flow01.y == -0
         flow13_valid = flow13_valid * valid1
         img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
-        img3p = fill(img3p, valid3p, coll3p)
+        img2, img3, img2p, img3p = _fill_leaves(inpaint, [(img2, valid2, coll2), (img3, valid3, coll3), (img2p, valid2p, coll2p),
+                                                          (img3p, valid3p, coll3p)])
     return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,
                 img2_prime=img2p, depth2_prime=depth2p, img3_prime=img3p, depth3_prime=depth3p,
                 flow01=flow01, back_flow01=back01, flow12=flow12, back_flow12=back12, flow02=flow02,
@@ -542,18 +552,16 @@ def _synthesize_group_f64(img0, depth0, sBf, cam, inpaint, counters):
         depth0_f = depth0.float()                                     # what FW sees (fw.py:43,45)
         img1 = fill(img1, valid1, coll1)
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
-        img2 = fill(img2, valid2, coll2)
         flow03 = ops.reproject_flow(depth0, cam)                      # float64 depth x ray, float32 flow (geometry.py:39-40)
         img3, depth3, back03, valid3, coll3, _ = ops.frame_splat(img0, depth0_f, flow03, None, counters=counters)
-        img3 = fill(img3, valid3, coll3)
         warp12, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1)
         flow02 = (warp12 + flow01) * flow02_valid                     # float32 + float64 -> float64 (preprocess.py:312)
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0_f, flow02, flow02_valid, counters=counters)
-        img2p = fill(img2p, valid2p, coll2p)
         flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
         flow13_valid = flow13_valid * valid1
         img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, counters=counters)
-        img3p = fill(img3p, valid3p, coll3p)
+        img2, img3, img2p, img3p = _fill_leaves(inpaint, [(img2, valid2, coll2), (img3, valid3, coll3), (img2p, valid2p, coll2p),
+                                                          (img3p, valid3p, coll3p)])
     return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,
                 img2_prime=img2p, depth2_prime=depth2p, img3_prime=img3p, depth3_prime=depth3p,
                 flow01=flow01, back_flow01=back01, flow12=flow12, back_flow12=back12, flow02=flow02,

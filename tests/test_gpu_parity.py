@@ -1383,6 +1383,40 @@ def test_preprocess_plus_augment_writes_the_reference_files(pkg, golden, tmp_pat
     print(f"[preprocess] 121 files, worst differing fraction {worst:.2e}")
 
 
+def test_driver_batched_fills_equal_one_fill_per_image(pkg, tmp_path):
+    """The driver inpaints the four leaf images of the group in one call and the 90 warped images of the five augmentation blocks in
+    another (synthesis._fill_leaves, PreprocessPlusAugment.fill_blocks).  A fill never looks across images, so every one of the 121
+    files must equal, byte for byte, what a hook that fills ONE image per call produces - and the hook must have seen all 95 images."""
+    from opticalflowfromdepth_b200 import preprocess as pp
+
+    img, raw = pkg.synthetic.diml_frame(5, 64, 96)
+    calls = {"batched": [], "single": []}
+
+    def batched(im, v, c):
+        calls["batched"].append(im.shape[0])
+        return pkg.synthesis.inpaint_cuda(im, v, c)
+
+    def single(im, v, c):
+        calls["single"].append(im.shape[0])
+        return torch.cat([pkg.synthesis.inpaint_cuda(im[b:b + 1], v[b:b + 1], c[b:b + 1]) for b in range(im.shape[0])])
+
+    outs = {}
+    for name, hook in (("batched", batched), ("single", single)):
+        ppa = pp.PreprocessPlusAugment(DEV, inpaint=hook, quiet=True, compress=False)
+        pkg.synthesis.set_seed(12345 + 9)
+        outs[name] = tmp_path / name
+        ppa((torch.from_numpy(img), torch.from_numpy(raw)), str(outs[name]), is_stereo=False)
+        ppa.close()
+    assert calls["batched"] == [1, 4, 90] and sum(calls["single"]) == 95
+    files = sorted(p.name for p in outs["batched"].glob("*.npz"))
+    assert len(files) == 121 and files == sorted(p.name for p in outs["single"].glob("*.npz"))
+    for f in files:
+        a, b = np.load(outs["batched"] / f), np.load(outs["single"] / f)
+        assert np.array_equal(a["img_depth_flow"].view(np.int32), b["img_depth_flow"].view(np.int32)), f
+    # the fills did something: the warped first image of a rotated pair has no hole pixels left where the mask said hole
+    assert float((np.load(outs["batched"] / "0_7_1.npz")["img_depth_flow"][0:3] == 0).mean()) < 0.05
+
+
 def _compare_preprocess_files(out, g, pp, label):
     """121 files of one PreprocessPlusAugment.forward against the golden made by the reference's own forward on the CPU."""
     want_files = sorted(k[:-6] for k in g if k.endswith("__data"))
