@@ -375,6 +375,28 @@ int ofd_inpaint_telea(const float* img, const uint8_t* mask, int B, int H, int W
                       size_t ws_bytes, uint32_t* stats_host, ofd_stream_t stream);
 
 /*
+ * ofd_plane_ops — a table of plane operations dst[0..hw) = f(src) in one launch: how a batch of training samples is put together
+ * from the planes of a frame group on the device (BASELINE config 4).  Replaces, per sample, the reader's channel slicing of the
+ * pre-baked arrays (dataloader.py:93-126: img0 / depth / img1 / flow of pair group 0..2) and the writer's photometric functions
+ * (preprocess.py:150-163): OFD_PLANE_SCALE = img * scale (type 0), OFD_PLANE_ADD = img[channel] + shift (type 1), OFD_PLANE_GRAY =
+ * (r * 0.2989 + g * 0.5870) + b * 0.1140 with r, g, b = src, src + gray_stride, src + 2 * gray_stride (type 2), OFD_PLANE_COPY.
+ * float32 operations in exactly that order (no FMA contraction): the values torch's elementwise kernels give.
+ *   ops_dev: DEVICE table of n_ops entries (8-byte aligned); aligned16 != 0 promises that every src / dst is 16-byte aligned
+ *   (with hw % 4 == 0 the planes then move as float4).  A plane must not be both a source and a destination of the same table.
+ */
+#define OFD_PLANE_COPY 0
+#define OFD_PLANE_SCALE 1
+#define OFD_PLANE_ADD 2
+#define OFD_PLANE_GRAY 3
+typedef struct ofd_plane_op {
+    const float* src; /* device plane of hw floats (GRAY: the first of three planes gray_stride floats apart) */
+    float* dst;       /* device plane of hw floats */
+    int op;           /* OFD_PLANE_* */
+    float p;          /* scale / shift */
+} ofd_plane_op;
+int ofd_plane_ops(const ofd_plane_op* ops_dev, int n_ops, size_t hw, size_t gray_stride, int aligned16, ofd_stream_t stream);
+
+/*
  * ofd_copy_rows_to_host — device -> host copy of `rows` rows of `width_bytes` with independent pitches (one asynchronous
  * cudaMemcpy2DAsync on `stream`).  The sweep uses it to scatter each result tensor [B,c,H,W] of a frame group straight into
  * its channel slice of the page-locked [B,44,H,W] group array (preprocess.py:437-447 layout): rows = B, width = c*H*W*4,

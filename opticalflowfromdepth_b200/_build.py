@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libofd_b200.so"
 STAMP = PKG / ".libofd_b200.stamp"
-SOURCES = ["ofd_abi.cu", "ofd_splat.cu", "ofd_splat_f64.cu", "ofd_pair.cu", "ofd_flow.cu", "ofd_bilateral.cu", "ofd_host.cu", "ofd_inpaint.cu", "ofd_decode.cu"]
+SOURCES = ["ofd_abi.cu", "ofd_splat.cu", "ofd_splat_f64.cu", "ofd_pair.cu", "ofd_flow.cu", "ofd_bilateral.cu", "ofd_host.cu", "ofd_inpaint.cu", "ofd_decode.cu", "ofd_assemble.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -16,6 +16,7 @@ EPI_NONE, EPI_CONCAT, EPI_BACK = 0, 1, 2
 SRC_RELDEPTH, SRC_DISPARITY = 0, 1
 MAX_CHANNELS = 8
 PIPE_KEEP_CONST_PLANES = 1
+PLANE_COPY, PLANE_SCALE, PLANE_ADD, PLANE_GRAY = 0, 1, 2, 3
 CNT_HIT, CNT_HOLE, CNT_COLLISION, CNT_DROPPED, CNT_TIE_SRC, CNT_FRAMES, CNT_PAIRS, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 6, 8
 
 _p, _i, _sz, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
@@ -60,6 +61,7 @@ SIGNATURES = {
     "ofd_inpaint_workspace_bytes": (_sz, [_i, _i, _i]),
     "ofd_inpaint_telea": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p, _p]),
     "ofd_copy_rows_to_host": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
+    "ofd_plane_ops": (_i, [_p, _i, _sz, _sz, _i, _p]),
     "ofd_pack_u8": (_i, [_p, _p, _sz, _p, _p]),
     "ofd_host_widen_u8": (_i, [_p, _sz, _p]),
     "ofd_host_stream_fill": (_i, [_p, _sz, _f]),

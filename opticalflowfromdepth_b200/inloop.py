@@ -10,7 +10,8 @@ adjusted_gmflow/data/datasets.py:323-358).  Here the same sample is SYNTHESISED 
     (img[B,3,H,W], depth[B,1,H,W])  ->  5-pair group (synthesis.synthesize_group: 7 splats)
                                     ->  per sample: pair group g, augmentation slot a (type AUGMENT_TYPES[a]), augmented image `which`
                                     ->  geometric types 5-7: synthesis.augment_flow_batch (one native call, 6 splats per sample),
-                                        photometric types 0-2: three elementwise expressions
+                                        photometric types 0-2 and the placement of every sample's 12 planes: two tables of plane
+                                        operations, one launch each (ofd_plane_ops)
                                     ->  the trainers' 9-tuple, as CUDA tensors
 
 No file is written or read, nothing crosses PCIe but the input frames, and a sample is one of 5 x 12 x 2 variants of a FRESH random
@@ -31,12 +32,14 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 
-from . import ops, synthesis
+from . import _lib, ops, synthesis
 from .preprocess import AUGMENT_TYPES, GROUP_PAIRS
 
 NUM_CLASSES = 1 + 3  # dataloader.py:11
+_PAIR_CHANNELS = (3, 1, 3, 1, 2, 2)  # imgA, depthA, imgB, depthB, flowAB, back_flowAB (preprocess.GROUP_PAIRS order)
 
 
 @dataclass
@@ -115,58 +118,69 @@ class InLoopSampler:
         img = img.to(dev).float().contiguous()
         depth = depth.to(dev).float().contiguous()
         B, _, h, w = img.shape
+        hw = h * w
         if plan is None:
             plan = self.draw(B, (h, w))
+        types = plan.types
         with torch.cuda.device(dev):
             depth0 = depth if self.normalized else ops.normalize_depth(depth)
             grp = synthesis.synthesize_group(img, depth0, plan.sBf.to(dev), plan.cam.to(dev), inpaint=self.inpaint)
-            # the pair of every sample: (imgA, depthA, imgB, depthB, flowAB, back_flowAB) of its group
-            used = sorted(set(plan.group))
-            rows = torch.arange(B, device=dev)
-            sel = {g: torch.tensor([b for b in range(B) if plan.group[b] == g], device=dev) for g in used[1:]}
-            pair = []
-            for m in range(6):
-                t = grp[GROUP_PAIRS[used[0]][m]].float().clone()
-                for g in used[1:]:
-                    t[sel[g]] = grp[GROUP_PAIRS[g][m]].float()[sel[g]]
-                pair.append(t)
-            types = plan.types
-            first_img, first_dep, second_img, second_dep, flow, back = pair  # private copies: augmented samples are overwritten in place
-            which = torch.tensor(plan.which, device=dev)
-            # geometric augmentation (types 5-7) of the samples that drew one: one native call for the sub-batch
+            # Every sample is 12 planes (imgA 3, depthA 1, imgB 3, depthB 1, flowAB 2, back_flowAB 2) picked from the group's tensors - or,
+            # for a geometric augmentation, from what ofd_augment_pairs makes of them.  Picking, the photometric functions and the final
+            # placement are plane operations: two tables, two launches (ofd_plane_ops), whatever the batch draws.
+            f32 = {}
+
+            def plane(name, b, ch):  # device address of channel `ch` of sample `b` of a group tensor
+                t = f32.get(name)
+                if t is None:
+                    t = f32[name] = grp[name].float().contiguous()
+                return t.data_ptr() + 4 * hw * (b * t.shape[1] + ch)
+
+            out = [torch.empty((B, c, h, w), dtype=torch.float32, device=dev) for c in _PAIR_CHANNELS]
+            first_img, first_dep, second_img, second_dep, flow, back = out
+            rows = []  # (src, dst, op, p)
             geo = [b for b, t in enumerate(types) if t >= 5]
+            keep = [f32]  # everything a table points into stays referenced until the launches are issued
             if geo:
-                gi = torch.tensor(geo, device=dev)
-                sub = [x[gi].contiguous() for x in pair]
+                sub = [torch.empty((len(geo), c, h, w), dtype=torch.float32, device=dev) for c in _PAIR_CHANNELS]
+                for j, b in enumerate(geo):
+                    for m, name in enumerate(GROUP_PAIRS[plan.group[b]]):
+                        for ch in range(_PAIR_CHANNELS[m]):
+                            rows.append((plane(name, b, ch), sub[m].data_ptr() + 4 * hw * (j * _PAIR_CHANNELS[m] + ch), _lib.PLANE_COPY, 0.0))
+                ops.plane_ops(np.array(rows, dtype=ops.PLANE_OP_DTYPE), hw, dev)
+                rows = []
                 set1, set2, _ = synthesis.augment_flow_batch(*sub, kinds=[types[b] for b in geo], inpaint=self.inpaint,
                                                              params=[plan.draws[b] for b in geo])
-                w0 = (which[gi] == 0).view(-1, 1, 1, 1)
                 # set1 = (aug_imgA, aug_depthA, augA_flow, back_augA_flow, imgB, depthB); set2 = (imgA, depthA, aug1_flow, back_aug1_flow, aug_imgB, aug_depthB)
-                for dst, a, c in ((first_img, set1[0], set2[0]), (first_dep, set1[1], set2[1]), (flow, set1[2], set2[2]),
-                                  (back, set1[3], set2[3]), (second_img, set1[4], set2[4]), (second_dep, set1[5], set2[5])):
-                    dst[gi] = torch.where(w0, a.float(), c.float())
-            # photometric augmentation (types 0-2, preprocess.py:150-182) of the image `which` points at, batched per type with
-            # synthesis.photometric_apply's expressions: brightness scale / one-channel shift / grayscale
-            for wsel, tgt in ((0, first_img), (1, second_img)):
-                for t in (0, 1, 2):
-                    idx = [b for b in range(B) if types[b] == t and plan.which[b] == wsel]
-                    if not idx:
-                        continue
-                    ii = torch.tensor(idx, device=dev)
-                    src = tgt[ii]
-                    if t == 0:
-                        scale = torch.stack([plan.draws[b].reshape(()) for b in idx]).to(dev)
-                        tgt[ii] = src * scale.view(-1, 1, 1, 1)
-                    elif t == 1:
-                        ch = torch.tensor([plan.draws[b][0] for b in idx], device=dev)
-                        shift = torch.stack([plan.draws[b][1].reshape(()) for b in idx]).to(dev)
-                        src[torch.arange(len(idx), device=dev), ch] += shift.view(-1, 1, 1)
-                        tgt[ii] = src
-                    else:
-                        gray = (src[:, 0] * 0.2989 + src[:, 1] * 0.5870) + src[:, 2] * 0.1140
-                        tgt[ii] = gray.unsqueeze(1).expand_as(src)
-        label = torch.zeros((B, NUM_CLASSES), dtype=torch.float32, device=dev)
-        label[rows, torch.tensor([max(0, t - 4) for t in types], device=dev)] = 1.0  # dataloader.py:153-156
+                sets = [[t.float().contiguous() for t in s] for s in (set1, set2)]
+                keep += [sub, sets]
+                for j, b in enumerate(geo):
+                    src = sets[plan.which[b]]
+                    for m, k in enumerate((0, 1, 4, 5, 2, 3)):  # out order: imgA, depthA, imgB, depthB, flow, back_flow
+                        for ch in range(_PAIR_CHANNELS[m]):
+                            off = 4 * hw * (j * _PAIR_CHANNELS[m] + ch)
+                            rows.append((src[k].data_ptr() + off, out[m].data_ptr() + 4 * hw * (b * _PAIR_CHANNELS[m] + ch), _lib.PLANE_COPY, 0.0))
+            for b, t in enumerate(types):
+                if t >= 5:
+                    continue
+                # photometric augmentation (types 0-2, preprocess.py:150-182) of the image `which` points at: brightness scale /
+                # one-channel shift / grayscale (synthesis.photometric_apply's expressions)
+                for m, name in enumerate(GROUP_PAIRS[plan.group[b]]):
+                    for ch in range(_PAIR_CHANNELS[m]):
+                        op, p, src = _lib.PLANE_COPY, 0.0, plane(name, b, ch)
+                        if m == (0, 2)[plan.which[b]]:
+                            if t == 0:
+                                op, p = _lib.PLANE_SCALE, float(plan.draws[b])
+                            elif t == 1 and ch == int(plan.draws[b][0]):
+                                op, p = _lib.PLANE_ADD, float(plan.draws[b][1])
+                            elif t == 2:
+                                op, src = _lib.PLANE_GRAY, plane(name, b, 0)
+                        rows.append((src, out[m].data_ptr() + 4 * hw * (b * _PAIR_CHANNELS[m] + ch), op, p))
+            ops.plane_ops(np.array(rows, dtype=ops.PLANE_OP_DTYPE), hw, dev)
+            del keep
+            label_host = np.zeros((B, NUM_CLASSES), np.float32)
+            label_host[np.arange(B), [max(0, t - 4) for t in types]] = 1.0  # dataloader.py:153-156
+            label = torch.from_numpy(label_host).to(dev)
         return Batch(first_img, second_img, flow, back, first_dep, second_dep, label, plan)
 
 

@@ -560,6 +560,27 @@ def bilateral_iter_batch(packed_in, packed_orig, shapes, offsets, window: int, t
     return out
 
 
+PLANE_OP_DTYPE = [("src", "<u8"), ("dst", "<u8"), ("op", "<i4"), ("p", "<f4")]  # struct ofd_plane_op (include/ofd_b200.h)
+
+
+def plane_ops(table, hw: int, device, gray_stride: Optional[int] = None):
+    """ofd_plane_ops: `table` = numpy structured array of PLANE_OP_DTYPE (device addresses of float32 planes of `hw` elements, an
+    OFD_PLANE_* code and its parameter); one upload and one launch for the whole table.  The caller keeps the tensors behind the
+    addresses alive until the stream has run the launch (ordinary torch stream semantics: they are used on the current stream)."""
+    import numpy as np
+
+    table = np.ascontiguousarray(table, dtype=PLANE_OP_DTYPE)
+    n = int(table.shape[0])
+    if n == 0:
+        return
+    device = torch.device(device)
+    aligned = bool(((table["src"] | table["dst"]) & 15 == 0).all())
+    with torch.cuda.device(device):
+        dev_table = torch.from_numpy(table.view(np.uint8).reshape(-1)).to(device)
+        _lib.call("ofd_plane_ops", _ptr(dev_table), n, int(hw), int(hw if gray_stride is None else gray_stride), int(aligned),
+                  _stream(device))  # dev_table is allocated and read on the current stream: its reuse is stream-ordered
+
+
 def pack_u8(t, flag):
     """float32 CUDA tensor -> uint8 tensor of the same shape (ofd_pack_u8); `flag` (int32 CUDA tensor, one element, zeroed by the
     caller) is raised when some value is not exactly a uint8."""

@@ -2057,6 +2057,31 @@ def test_bench_default_arm_prints_the_contract_line():
 
 
 # BASELINE config 4 as stated: in-loop augmentation fused with flow synthesis (frames -> training samples on the GPU)
+def test_plane_ops_table_equals_torch_elementwise(pkg):
+    """ofd_plane_ops: copy / scale / add / grayscale planes of a table in one launch == the torch expressions the pre-baked path uses
+    (synthesis.photometric_apply), bit for bit; float4 path (hw % 4 == 0) and the scalar one (odd sizes, unaligned planes)."""
+    from opticalflowfromdepth_b200 import _lib
+    rng = np.random.default_rng(5)
+    for (h, w) in ((24, 36), (7, 9)):
+        hw = h * w
+        src = cu(rng.integers(0, 256, (5, 3, h, w)).astype(np.float32) + rng.random((5, 3, h, w)).astype(np.float32))
+        dst = torch.full((4, 3, h, w), -7.0, device=DEV)
+        scale, shift = np.float32(0.37311), np.float32(-19.62)
+        rows = []
+        addr = lambda t, b, c: t.data_ptr() + 4 * hw * (b * 3 + c)  # noqa: E731
+        for c in range(3):
+            rows.append((addr(src, 1, c), addr(dst, 0, c), _lib.PLANE_COPY, 0.0))
+            rows.append((addr(src, 2, c), addr(dst, 1, c), _lib.PLANE_SCALE, float(scale)))
+            rows.append((addr(src, 3, c), addr(dst, 2, c), _lib.PLANE_ADD if c == 1 else _lib.PLANE_COPY, float(shift)))
+            rows.append((addr(src, 4, 0), addr(dst, 3, c), _lib.PLANE_GRAY, 0.0))
+        pkg.ops.plane_ops(np.array(rows, dtype=pkg.ops.PLANE_OP_DTYPE), hw, DEV)
+        assert torch.equal(dst[0], src[1])
+        assert torch.equal(dst[1], pkg.synthesis.photometric_apply(src[2], 0.0, torch.tensor(scale)))
+        assert torch.equal(dst[2], pkg.synthesis.photometric_apply(src[3], 1.0, (1, torch.tensor(shift))))
+        assert torch.equal(dst[3], pkg.synthesis.photometric_apply(src[4], 2.0, None))
+    pkg.ops.plane_ops(np.zeros((0,), dtype=pkg.ops.PLANE_OP_DTYPE), 16, DEV)  # an empty table is a no-op
+
+
 def test_inloop_sampler_equals_the_prebaked_files(pkg):
     """inloop.InLoopSampler: sample b of a batch == the 8-channel array preprocess.PreprocessPlusAugment would store in
     {g}_{a}_{which+1}.npz for that frame with the same draws (preprocess.py:453-476), for every pair group the trainers read (0..2),
