@@ -346,12 +346,13 @@ def run_ours(args):
             line["cfg5_sweep_e2e"] = {"frames_per_s": world * n_sw / ts, "pairs_per_s": 5 * world * n_sw / ts, "frames_per_rank": n_sw, "batch": b_sw,
                                       "seconds": ts, "d2h_bytes_per_frame": sink.bytes // max(sink.frames, 1), "h2d_bytes_per_frame": 4 * H * W * 4,
                                       "d2h_GBps_per_gpu": sink.bytes / ts / 1e9, "pinned_output_buffers": sink.buffers_allocated,
-                                      "image_channels_as_bytes": bool(sink.byte_images), "fallback_batches": sink.fallback_batches,
+                                      "image_channels_as_bytes": bool(sink.byte_images), "constant_planes_host_filled": bool(sink.const_planes),
+                                      "fallback_batches": sink.fallback_batches,
                                       "counters": sweep.reduce_counters(sw_counters),
                                       "what": "sweep.run_sweep: host frames -> normalize_depth -> 5-pair group (reference RNG draw order per frame) -> "
                                               "44-channel float32 group array in pinned host memory (22 strided DMAs per batch, no concatenation on the device, "
-                                              "double-buffered; the 18 uint8-valued image channels cross as device-verified bytes and are widened on host threads "
-                                              "unless more than two ranks share the node); wall clock incl. host RNG, staging copy, H2D, D2H; max over ranks"}
+                                              "double-buffered; unless more than two ranks share the node the 18 uint8-valued image channels cross as device-verified bytes and are "
+                                              "widened on host threads, and the constant planes flow01.y / back_flow01.y are written by them instead of crossing); wall clock incl. host RNG, staging copy, H2D, D2H; max over ranks"}
             del sink
         except Exception as e:
             line["cfg5_sweep_e2e"] = {"error": repr(e)}

@@ -600,23 +600,35 @@ def host_widen_u8(src, dst):
     _lib.call("ofd_host_widen_u8", C.c_void_p(src.data_ptr()), C.c_size_t(src.numel()), C.c_void_p(dst.data_ptr()))
 
 
-def scatter_channels_to_host(t, host, c0: int, stream=None):
+def scatter_channels_to_host(t, host, c0: int, stream=None, n_channels: Optional[int] = None):
     """Asynchronous D2H copy of t[B,c,H,W] (CUDA, contiguous; float32 or uint8) into channels [c0, c0+c) of the page-locked CPU tensor
     host[>=B,Ctot,H,W] of the same dtype (ofd_copy_rows_to_host: ONE strided DMA, no concatenation on the device).  Runs on `stream`
-    (default: torch's current stream of t's device); the caller synchronises before reading `host`."""
+    (default: torch's current stream of t's device); the caller synchronises before reading `host`.  n_channels: only the first
+    n_channels channels of every frame of t are copied (into [c0, c0+n_channels))."""
     _check("t", t, dtype=(torch.float32, torch.uint8))
     if t.dim() != 4 or host.dim() != 4:
         raise ValueError("t and host must be 4-D [B,C,H,W]")
     B, c, H, W = t.shape
+    nc = c if n_channels is None else int(n_channels)
+    if not 0 < nc <= c:
+        raise ValueError(f"n_channels must be in 1..{c}")
     if host.is_cuda or host.dtype != t.dtype or not host.is_contiguous():
         raise ValueError("host must be a contiguous CPU tensor of t's dtype (page-locked for an asynchronous copy)")
-    if host.shape[0] < B or tuple(host.shape[2:]) != (H, W) or not (0 <= c0 and c0 + c <= host.shape[1]):
-        raise ValueError(f"host{tuple(host.shape)} cannot take channels [{c0},{c0 + c}) of a batch of {B} frames {H}x{W}")
+    if host.shape[0] < B or tuple(host.shape[2:]) != (H, W) or not (0 <= c0 and c0 + nc <= host.shape[1]):
+        raise ValueError(f"host{tuple(host.shape)} cannot take channels [{c0},{c0 + nc}) of a batch of {B} frames {H}x{W}")
     hw4 = H * W * t.element_size()
     st = C.c_void_p(stream.cuda_stream) if stream is not None else _stream(t.device)
     with torch.cuda.device(t.device):
         _lib.call("ofd_copy_rows_to_host", _ptr(t), C.c_size_t(c * hw4), C.c_void_p(host.data_ptr() + c0 * hw4),
-                  C.c_size_t(host.shape[1] * hw4), C.c_size_t(c * hw4), C.c_size_t(B), st)
+                  C.c_size_t(host.shape[1] * hw4), C.c_size_t(nc * hw4), C.c_size_t(B), st)
+
+
+def host_stream_fill(dst, value: float):
+    """ofd_host_stream_fill: a contiguous float32 CPU tensor filled with `value` (sign of zero kept) by non-temporal stores on the
+    calling thread (releases the GIL: ctypes call)."""
+    if dst.is_cuda or dst.dtype != torch.float32 or not dst.is_contiguous():
+        raise ValueError("dst must be a contiguous float32 CPU tensor")
+    _lib.call("ofd_host_stream_fill", C.c_void_p(dst.data_ptr()), C.c_size_t(dst.numel()), C.c_float(value))
 
 
 class PairPipeline:

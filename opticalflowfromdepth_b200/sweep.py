@@ -95,20 +95,29 @@ class PinnedGroupSink:
     the limit, i.e. unless more than two ranks share the node (LOCAL_WORLD_SIZE > 2: there the node's host memory is, and the extra
     host stores cost more than the PCIe bytes they save - DESIGN.md section 6).
 
+    const_planes: flow01.y and back_flow01.y of a group are the constants -0.0 and +0.0 (the virtual stereo pair moves pixels along
+    their row, preprocess.py:253,361-363): they do not cross PCIe, the delivering threads write them into the array (114 B/px per
+    frame).  Same default rule as byte_images.
+
     `on_batch(idx_list, array[B,44,H,W], release)` receives the host array once its copies have landed (when the next-but-one
     batch arrives, or at flush()).  The consumer OWNS the array until it calls release() - it may hand it to asynchronous
     writers (preprocess.NpzWriter) and release it when they are done; the sink takes another page-locked buffer from its pool
     (allocating one if none is free) instead of overwriting a buffer that is still being read.  Without on_batch the sink
     only counts and recycles two buffers."""
 
-    def __init__(self, on_batch: Optional[Callable] = None, byte_images: Optional[bool] = None, widen_threads: int = 4):
+    CONST_PLANES = {"flow01": -0.0, "back_flow01": 0.0}  # channel 1 (y) of these tensors
+
+    def __init__(self, on_batch: Optional[Callable] = None, byte_images: Optional[bool] = None, widen_threads: int = 4,
+                 const_planes: Optional[bool] = None):
         import os
         import threading
 
         self.on_batch = on_batch
+        pcie_bound = int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2
         if byte_images is None:
-            byte_images = int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2
+            byte_images = pcie_bound
         self.byte_images = bool(byte_images)
+        self.const_planes = pcie_bound if const_planes is None else bool(const_planes)
         self.frames = 0
         self.bytes = 0               # bytes that crossed PCIe
         self.buffers_allocated = 0
@@ -147,6 +156,14 @@ class PinnedGroupSink:
         entry = self._inflight.pop(0)
         host, event, idx_list, n = entry["host"], entry["event"], entry["idx"], entry["n"]
         event.synchronize()
+        if entry["const"]:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._pool = ThreadPoolExecutor(max_workers=self._widen_threads)
+            const_jobs = [self._pool.submit(ops.host_stream_fill, host[b, c], v) for b in range(n) for (c, v) in entry["const"]]
+        else:
+            const_jobs = []
         if entry["host8"] is not None:
             host8, spans = entry["host8"], entry["spans"]
             if int(entry["flag_host"][0]) == 0:
@@ -163,6 +180,8 @@ class PinnedGroupSink:
                     ops.scatter_channels_to_host(t, host, c0)
                 torch.cuda.current_stream(entry["float_images"][0][0].device).synchronize()
             self._free8.append(host8)
+        for f in const_jobs:
+            f.result()
         entry["float_images"] = None
         if self.on_batch is None:
             self._release(host)
@@ -204,7 +223,7 @@ class PinnedGroupSink:
             flag_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
         self._stream.wait_stream(torch.cuda.current_stream(dev))
         c0 = c8 = 0
-        spans, float_images, crossed = [], [], 0
+        spans, float_images, crossed, const = [], [], 0, []
         with torch.cuda.stream(self._stream):
             for name in GROUP_CHANNELS:
                 t = res[name]
@@ -218,6 +237,11 @@ class PinnedGroupSink:
                     float_images.append((t, c0))
                     c8 += t.shape[1]
                     crossed += u.numel()
+                elif self.const_planes and name in self.CONST_PLANES:
+                    ops.scatter_channels_to_host(t, host, c0, stream=self._stream, n_channels=1)  # x only; y is written at delivery
+                    t.record_stream(self._stream)
+                    const.append((c0 + 1, self.CONST_PLANES[name]))
+                    crossed += t.numel() * 2
                 else:
                     ops.scatter_channels_to_host(t, host, c0, stream=self._stream)
                     t.record_stream(self._stream)
@@ -229,7 +253,7 @@ class PinnedGroupSink:
         event = torch.cuda.Event()
         event.record(self._stream)
         self._inflight.append(dict(host=host, event=event, idx=list(idx_list), n=B, host8=host8, spans=spans, flag_host=flag_host,
-                                   float_images=float_images if images else None))
+                                   float_images=float_images if images else None, const=const))
         self.frames += len(idx_list)
         self.bytes += crossed
 

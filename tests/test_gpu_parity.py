@@ -1943,11 +1943,15 @@ def test_sweep_sink_scatters_the_group_without_a_device_concatenation(pkg):
     sink = sweep.PinnedGroupSink(on_batch)
     assert sink.byte_images                      # one rank per node here: the image channels cross as verified bytes
     sweep.run_sweep(range(n), load, DEV, batch=3, dataset_len=n, sink=sink)
-    assert sink.frames == n and sink.bytes == n * (26 * 4 + 18) * h * w and sink.fallback_batches == 0
+    assert sink.const_planes                     # ... and the two constant flow planes are written by host threads instead of crossing
+    assert sink.frames == n and sink.bytes == n * (24 * 4 + 18) * h * w and sink.fallback_batches == 0
     assert sum(len(i) for i, _, _ in held) == n
     for idx_list, arr, release in held:          # all four batches still intact although nothing was released
         for k, i in enumerate(idx_list):
             assert np.array_equal(arr[k], want[i]), i
+            # flow01.y == -0.0 and back_flow01.y == +0.0, sign included (channels 25 and 27 of the group array)
+            assert np.array_equal(arr[k].view(np.int32), want[i].view(np.int32)), i
+            assert (arr[k, 25].view(np.uint32) == 0x80000000).all() and (arr[k, 27].view(np.uint32) == 0).all()
     assert sink.buffers_allocated == len(held)   # a held buffer is never recycled
     for _, _, release in held:
         release()
@@ -1957,12 +1961,12 @@ def test_sweep_sink_scatters_the_group_without_a_device_concatenation(pkg):
     assert sink.buffers_allocated == before      # released buffers are reused
     # float transport (what ranks sharing a node with more than one other rank default to): same arrays, 176 B/px on the wire
     held.clear()
-    sink_f = sweep.PinnedGroupSink(on_batch, byte_images=False)
+    sink_f = sweep.PinnedGroupSink(on_batch, byte_images=False, const_planes=False)
     sweep.run_sweep(range(n), load, DEV, batch=4, dataset_len=n, sink=sink_f)
     assert sink_f.bytes == n * 44 * 4 * h * w
     for idx_list, arr, release in held:
         for k, i in enumerate(idx_list):
-            assert np.array_equal(arr[k], want[i]), i
+            assert np.array_equal(arr[k].view(np.int32), want[i].view(np.int32)), i
         release()
     # frames that are NOT uint8-valued: the device check fails, the batch is delivered from its float planes and the sink stops trying
     held.clear()
@@ -2004,7 +2008,7 @@ def test_bench_cfg5_legs_small(pkg):
     assert g["counters"]["pairs"] == 5 * g["counters"]["frames"]
     sw = d["cfg5_sweep_e2e"]
     assert "error" not in sw, sw
-    assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == (26 * 4 + 18) * 480 * 640 and sw["counters"]["frames"] == 48
+    assert sw["frames_per_rank"] == 48 and sw["d2h_bytes_per_frame"] == (24 * 4 + 18) * 480 * 640 and sw["counters"]["frames"] == 48
 
 
 @pytest.mark.parametrize("tag", ["cfg1_480x640", "cfg4_368x496", "cfg2_redweb", "cfg3_1080p"])

@@ -399,6 +399,7 @@ def test_group_sink_transport_default_follows_the_ranks_per_node():
             else:
                 os.environ["LOCAL_WORLD_SIZE"] = lws
             assert sweep.PinnedGroupSink().byte_images is want, lws
+            assert sweep.PinnedGroupSink().const_planes is want and sweep.PinnedGroupSink(const_planes=not want).const_planes is (not want)
             assert sweep.PinnedGroupSink(byte_images=True).byte_images is True and sweep.PinnedGroupSink(byte_images=False).byte_images is False
     finally:
         if saved is None:
