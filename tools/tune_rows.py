@@ -26,8 +26,8 @@ def child():
         print(f"rows concat {B}x{h}x{w}: best {min(ts):.4f} mean {m:.4f} ms  {40 * B * h * w / (m * 1e-3) / 1e9:.0f} GB/s on 40 B/px")
 if len(sys.argv) > 1: child()
 else:
-    for lib in (None, "opticalflowfromdepth_b200/build/variants/rows256.so"):
-        env = dict(os.environ)
-        if lib: env["OFD_LIB_PATH"] = str(ROOT / lib)
-        print("==", lib or "adaptive block", flush=True)
+    # the row-local splat: four pixels per thread (default when the planes are 16-byte aligned and W % 4 == 0) against the scalar kernel
+    for scalar in ("1", "0"):
+        env = dict(os.environ, OFD_ROWS_SCALAR=scalar)
+        print("== OFD_ROWS_SCALAR=" + scalar + (" (one pixel per thread)" if scalar == "1" else " (four pixels per thread)"), flush=True)
         subprocess.run([sys.executable, __file__, "child"], env=env)
