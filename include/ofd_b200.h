@@ -102,9 +102,12 @@ int ofd_splat_flow(const float* obj, const void* flow, int flow_dtype, const flo
  * splats of a frame group (preprocess.py:400,414).  Sources then stay in their row: the z-buffer of a row lives in shared memory (two
  * 32-bit shared-memory atomicMin passes = the serial loop's winner), no global atomics, no key workspace, ONE launch, 40 B/px instead of
  * 72 for a ConcatFlow.  float32 only, C == 2 (flow payloads), W <= 2048; same results as ofd_splat_flow on such flows (tested bit for bit).
+ * valid_mul (nullable, [B,1,H,W]): the valid plane is written as valid * valid_mul (preprocess.py:415: flow13_valid * img1_valid); the
+ * epilogue's own use of valid (ConcatFlow / BackFlow masking, :312,325) is unaffected.
  */
 int ofd_splat_flow_rows(const float* obj, const float* flow, const float* depth, int B, int C, int H, int W, float* out,
-                        float* valid, float* collision /*nullable*/, int epilogue, const float* aux, ofd_stream_t stream);
+                        float* valid, float* collision /*nullable*/, int epilogue, const float* aux, const float* valid_mul /*nullable*/,
+                        ofd_stream_t stream);
 
 /*
  * ofd_disparity_flow — Convert.depth_to_disparity + disparity_to_flow(random_sign=False)

@@ -29,7 +29,7 @@ SIGNATURES = {
     "ofd_workspace_reset": (_i, [_p, _sz, _p]),
     "ofd_splat_targets": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_splat_flow": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
-    "ofd_splat_flow_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "ofd_splat_flow_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     "ofd_disparity_flow": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "ofd_disparity_pair": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ofd_disparity_pair_ragged": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -129,11 +129,13 @@ def splat_targets(obj, safe_y, safe_x, depth, want_winner=False, counters=None):
 
 
 @_on_device
-def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None, want_collision=True, horizontal=False):
+def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False, counters=None, want_collision=True, horizontal=False,
+               valid_mul=None):
     """FW.forward (alt_cuda/fw.py:19-59) batched: obj[B,C,H,W] f32, flow[B,2,H,W] f32|f64, depth[B,1,H,W] f32.
     want_collision=False skips the collision plane (returned as None): 4 B/px less for callers that only use valid.
     horizontal=True is the caller's promise that flow[:,1] is +-0 everywhere (the pipeline's disparity flows): C == 2 float32 splats
-    then take the row-local shared-memory kernel (ofd_splat_flow_rows: one launch, no key plane); anything else ignores the hint."""
+    then take the row-local shared-memory kernel (ofd_splat_flow_rows: one launch, no key plane); anything else ignores the hint.
+    valid_mul[B,1,H,W]: the returned valid plane is valid * valid_mul (fused into the row-local kernel; the epilogue's masking uses the raw valid)."""
     _check("obj", obj, dtype=torch.float32)
     if obj.dim() != 4:
         raise ValueError("obj must be [B,C,H,W]")
@@ -142,18 +144,22 @@ def splat_flow(obj, flow, depth, epilogue=EPI_NONE, aux=None, want_winner=False,
     _check("depth", depth, dtype=torch.float32, shape=(B, 1, H, W))
     if aux is not None:
         _check("aux", aux, dtype=torch.float32, shape=(B, Cc, H, W))
+    if valid_mul is not None:
+        _check("valid_mul", valid_mul, dtype=torch.float32, shape=(B, 1, H, W))
     out = torch.empty_like(obj)
     valid = torch.empty_like(depth)
     collision = torch.empty_like(depth) if want_collision else None
     if horizontal and Cc == 2 and flow.dtype == torch.float32 and not want_winner and counters is None and W <= 2048 and H <= 65535 and B <= 65535:
         _lib.call("ofd_splat_flow_rows", _ptr(obj), _ptr(flow), _ptr(depth), B, Cc, H, W, _ptr(out), _ptr(valid), _ptr(collision),
-                  int(epilogue), _ptr(aux), _stream(obj.device))
+                  int(epilogue), _ptr(aux), _ptr(valid_mul), _stream(obj.device))
         return out, valid, collision
     winner = torch.empty((B, 1, H, W), dtype=torch.int32, device=obj.device) if want_winner else None
     ws = workspace.get(obj.device, B, H, W)
     _run_splat("ofd_splat_flow", obj.device, _ptr(obj), _ptr(flow), _DT[flow.dtype], _ptr(depth), B, Cc, H, W,
                _ptr(out), _ptr(valid), _ptr(collision), _ptr(winner), int(epilogue), _ptr(aux), _ptr(counters),
                _ptr(ws), C.c_size_t(ws.numel()), _stream(obj.device))
+    if valid_mul is not None:
+        valid = valid * valid_mul
     return (out, valid, collision, winner) if want_winner else (out, valid, collision)
 
 

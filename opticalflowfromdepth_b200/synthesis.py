@@ -524,8 +524,7 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
         # pair 1->3': (preprocess.py:414-424)
         flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False,
-                                                    horizontal=True)  # flow01.y == -0
-        flow13_valid = flow13_valid * valid1
+                                                    horizontal=True, valid_mul=valid1)  # flow01.y == -0; flow13_valid * img1_valid (:415) fused
         img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
         img2, img3, img2p, img3p = _fill_leaves(inpaint, [(img2, valid2, coll2), (img3, valid3, coll3), (img2p, valid2p, coll2p),
                                                           (img3p, valid3p, coll3p)])

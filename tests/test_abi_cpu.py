@@ -86,9 +86,9 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 @pytest.mark.parametrize("name,args,code", [
-    ("ofd_splat_flow_rows", (1, 1, 1, 1, 6, 4, 4, 1, 1, None, 0, None, None), -2),                       # C != 2
-    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4096, 1, 1, None, 0, None, None), -2),                    # W > 2048
-    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4, 1, 1, None, 1, None, None), -1),                       # concat without aux
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 6, 4, 4, 1, 1, None, 0, None, None, None), -2),                 # C != 2
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4096, 1, 1, None, 0, None, None, None), -2),              # W > 2048
+    ("ofd_splat_flow_rows", (1, 1, 1, 1, 2, 4, 4, 1, 1, None, 1, None, None, None), -1),                 # concat without aux
     ("ofd_inpaint_telea", (1, 1, 1, 8, 8, 9, 1, 256, 1 << 20, None, None), -4),                          # range 9
     ("ofd_inpaint_telea", (1, 1, 1, 8, 8, 3, 1, 256, 16, None, None), -5),                               # workspace too small
     ("ofd_inpaint_telea", (None, 1, 1, 8, 8, 3, 1, 256, 1 << 20, None, None), -1),                       # NULL image

@@ -295,6 +295,10 @@ def test_splat_flow_rows_equals_the_general_path(pkg):
                 assert np.array_equal(g.cpu().numpy(), wnt.cpu().numpy(), equal_nan=True), (b, h, w, epi, name)
             got2 = pkg.ops.splat_flow(obj, flow, depth, epilogue=epi, aux=ax, horizontal=True, want_collision=False)
             assert got2[2] is None and torch.equal(got2[1], want[1])
+            vm = (torch.rand(b, 1, h, w, device=DEV) > 0.3).float()  # a caller's mask on the valid plane only (flow13_valid * img1_valid)
+            for hz in (True, False):
+                got3 = pkg.ops.splat_flow(obj, flow, depth, epilogue=epi, aux=ax, horizontal=hz, valid_mul=vm)
+                assert torch.equal(got3[1], want[1] * vm) and np.array_equal(got3[0].cpu().numpy(), want[0].cpu().numpy(), equal_nan=True)
         assert float(want[2].sum()) > 0 or h * w < 50
     # the hint is ignored where the kernel does not apply (C != 2, float64 flow)
     obj6 = torch.rand(1, 6, 8, 16, device=DEV)
