@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 H, W = 480, 640
 # SURVEY 8d rows of the 7 splats of one frame group WITHOUT the five collision planes: they only feed utils.inpaint's
 # mask and are not produced when the group runs without a fill, as here (388 with them)
-GROUP_BYTES_PER_PX = 52 + 60 + 52 + 2 * 40 + 12 + 2 * 56   # 368
+GROUP_BYTES_PER_PX = 52 + 60 + 52 + 2 * 40 + 2 * 56   # 356 (flow13_valid * img1_valid is fused into the ConcatFlow kernel: no bytes of its own)
 PAIR_BYTES_PER_PX = 56          # img 3 + depth 1 in; img1 3, depth1 1, back_flow 2, flow 2, valid 1, collision 1 out
 FW_BYTES_PER_PX = lambda C: 4 * (2 * C + 5)  # noqa: E731  splat at the FW.forward boundary
 POOL = 16                       # distinct synthetic frames; the batch cycles through them
@@ -294,7 +294,7 @@ def run_ours(args):
     # Both legs run at EVERY N (they are the sweep the scaling claim is about); values are whole-job aggregates, max time over ranks.
     if "group" not in skip:
         # (b2) the whole group on device-resident frames (preprocess.py:356-432 minus inpaint): 7 splats with fused producers /
-        #      epilogues = 13 launches per batch; >= 10 k frames per rank from the recycled pool
+        #      epilogues = 9 launches per batch; >= 10 k frames per rank from the recycled pool
         try:
             Fq = min(F, args.group_frames)
             Kq, invKq = synthesis.Plausible.K((H, W))
@@ -316,12 +316,13 @@ def run_ours(args):
             g_counters[_lib.CNT_PAIRS] += 5 * Fq * nq
             gbytes = GROUP_BYTES_PER_PX * H * W * Fq
             line["group_480x640"] = {"frames_per_s": world * Fq / tq, "pairs_per_s": 5 * world * Fq / tq, "ms_per_step": 1e3 * tq,
-                                     "frames_per_step_per_gpu": Fq, "steps": nq, "frames_per_rank": Fq * nq, "launches_per_step": 13,
+                                     "frames_per_step_per_gpu": Fq, "steps": nq, "frames_per_rank": Fq * nq, "launches_per_step": 9,
                                      "achieved_GBps_per_gpu": gbytes / tq / 1e9, "frac_of_measured_peak": gbytes / tq / 1e9 / peak,
                                      "algorithmic_bytes_per_px": GROUP_BYTES_PER_PX,
                                      "counters": sweep.reduce_counters(g_counters),
                                      "what": "5 flow pairs per frame: stereo, 2x 6-DoF, 2x concatenated (7 splats); bytes = SURVEY 8d rows summed: "
-                                             "52 (0->1) + 60 (1->2) + 52 (0->3) + 2 x 40 (ConcatFlow) + 12 (flow13_valid * valid1) + 2 x 56 (C=7 frame splats); the "
+                                             "52 (0->1) + 60 (1->2) + 52 (0->3) + 2 x 40 (ConcatFlow) + 2 x 56 (C=7 frame splats); 9 launches: fused stereo pair, 2 x (6-DoF z-test + gather), "
+                                             "2 x (row-local ConcatFlow that also runs the next frame splat's z-test + gather); the "
                                              "collision planes (4 B/px per image splat) are not produced without an inpaint hook and not credited"}
             del camq
         except Exception as e:

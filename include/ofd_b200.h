@@ -178,6 +178,23 @@ int ofd_project(const float* cam_points, const float* P, float eps, int B, int H
 int ofd_frame_splat(const float* img, const float* depth, const float* flow, const float* valid_in, int B, int H,
                     int W, float* img_out, float* depth_out, float* back_flow, float* valid_out, float* collision,
                     float* raw_valid, uint64_t* counters, void* ws, size_t ws_bytes, ofd_stream_t stream);
+
+/*
+ * ofd_concat_frame_splat — ConcatFlow along a HORIZONTAL warp flow fused with the frame splat that consumes its result: the pairs 0->2'
+ * and 1->3' of a frame group (preprocess.py:400-411 and :414-424).
+ *   flowAC       = (FW(flowBC, warp_flow, depthB) + flowAB) * valid        ConcatFlow.forward, :307-313  (warp_flow.y == +-0, not read)
+ *   flowAC_valid = valid [* valid_mul]                                       (:415)
+ *   img_out, depth_out, back_flow, valid_out[, collision] = the frame splat of (img, depth_src, -flowAC, flowAC_valid) along flowAC by
+ *   depth_src, as ofd_frame_splat with valid_in = flowAC_valid                (:401-411)
+ * Two launches instead of three: the row-local ConcatFlow kernel also reduces the packed keys of the frame splat's z-test (sources = the
+ * pixels of the row it just produced), then the gather runs.  Same results as ofd_splat_flow_rows + ofd_frame_splat, bit for bit.
+ * float32, W % 4 == 0, W <= 2048, planes 16-byte aligned; ws as for ofd_frame_splat.
+ */
+int ofd_concat_frame_splat(const float* flowBC, const float* warp_flow, const float* depthB, const float* flowAB,
+                           const float* valid_mul /*nullable*/, const float* img, const float* depth_src, int B, int H, int W,
+                           float* flowAC, float* flowAC_valid, float* img_out, float* depth_out, float* back_flow, float* valid_out,
+                           float* collision /*nullable*/, uint64_t* counters /*nullable*/, void* ws, size_t ws_bytes,
+                           ofd_stream_t stream);
 /* The same splat when the warp flow is float64 (the dataset path: a flow composed with the float64 disparity flow,
  * preprocess.py:400-401 with cv2-loaded depth): targets are evaluated in float64 from `flow` (alt_cuda/fw.py:31,37-42), the
  * payload channels 4-5 are -flow_payload, the caller's float32 rounding of the same flow (fw.py:45 casts obj to float32). */

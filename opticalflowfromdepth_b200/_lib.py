@@ -37,6 +37,7 @@ SIGNATURES = {
     "ofd_backproject": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "ofd_project": (_i, [_p, _p, _f, _i, _i, _i, _p, _p, _p]),
     "ofd_frame_splat": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ofd_concat_frame_splat": (_i, [_p] * 7 + [_i, _i, _i] + [_p] * 9 + [_sz, _p]),
     "ofd_frame_splat_f64": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_reproject_pair": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ofd_normalize_depth": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),

@@ -287,6 +287,41 @@ def frame_splat(img, depth, flow, valid_in=None, want_collision=True, want_raw_v
     return img_o, dep_o, back, valid, coll, raw
 
 
+def concat_frame_splat_applies(flowBC, W: int, H: int, B: int) -> bool:
+    """Whether ofd_concat_frame_splat takes these shapes (float32, W % 4 == 0, W <= 2048)."""
+    return flowBC.dtype == torch.float32 and W % 4 == 0 and W <= 2048 and H <= 65535 and B <= 65535
+
+
+@_on_device
+def concat_frame_splat(flowBC, warp_flow, depthB, flowAB, img, depth_src, valid_mul=None, want_collision=True, counters=None):
+    """ConcatFlow along a horizontal warp flow fused with the frame splat along its result (preprocess.py:400-411, 414-424; pairs 0->2'
+    and 1->3' of a group): returns (flowAC, flowAC_valid, img_out, depth_out, back_flow, valid', collision|None) - what
+    splat_flow(flowBC, warp_flow, depthB, EPI_CONCAT, aux=flowAB, horizontal=True, valid_mul=valid_mul) followed by
+    frame_splat(img, depth_src, flowAC, flowAC_valid) returns, bit for bit, in two launches instead of three."""
+    _check("flowBC", flowBC, dtype=torch.float32)
+    B, c2, H, W = flowBC.shape
+    if c2 != 2:
+        raise ValueError("flowBC must be [B,2,H,W]")
+    for n, t, c in (("warp_flow", warp_flow, 2), ("depthB", depthB, 1), ("flowAB", flowAB, 2), ("img", img, 3), ("depth_src", depth_src, 1)):
+        _check(n, t, dtype=torch.float32, shape=(B, c, H, W))
+    if valid_mul is not None:
+        _check("valid_mul", valid_mul, dtype=torch.float32, shape=(B, 1, H, W))
+    dev = flowBC.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    flowAC = torch.empty((B, 2, H, W), **f32)
+    flowAC_valid = torch.empty((B, 1, H, W), **f32)
+    img_o = torch.empty((B, 3, H, W), **f32)
+    dep_o = torch.empty((B, 1, H, W), **f32)
+    back = torch.empty((B, 2, H, W), **f32)
+    valid = torch.empty((B, 1, H, W), **f32)
+    coll = torch.empty((B, 1, H, W), **f32) if want_collision else None
+    ws = workspace.get(dev, B, H, W)
+    _run_splat("ofd_concat_frame_splat", dev, _ptr(flowBC), _ptr(warp_flow), _ptr(depthB), _ptr(flowAB), _ptr(valid_mul), _ptr(img),
+               _ptr(depth_src), B, H, W, _ptr(flowAC), _ptr(flowAC_valid), _ptr(img_o), _ptr(dep_o), _ptr(back), _ptr(valid), _ptr(coll),
+               _ptr(counters), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+    return flowAC, flowAC_valid, img_o, dep_o, back, valid, coll
+
+
 @_on_device
 def reproject_pair(img, depth, cam, valid_in=None, eps=1e-7, want_collision=True, want_raw_valid=False, counters=None):
     """Fused 6-DoF flow pair (preprocess.py:372-382): the flow is computed inside the z-test and written once.

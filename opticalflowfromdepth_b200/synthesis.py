@@ -518,14 +518,23 @@ def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, want_collision=wc, counters=counters)
         # pair 0->3: the same motion from view 0 (preprocess.py:385-394)
         img3, depth3, back03, flow03, valid3, coll3, _ = ops.reproject_pair(img0, depth0, cam, None, want_collision=wc, counters=counters)
-        # pair 0->2': concatenated flow (preprocess.py:400-411)
-        flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False,
-                                                    horizontal=True)  # back01.y == +0: row-local kernel, unless counters ask for the tie census
-        img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
-        # pair 1->3': (preprocess.py:414-424)
-        flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False,
-                                                    horizontal=True, valid_mul=valid1)  # flow01.y == -0; flow13_valid * img1_valid (:415) fused
-        img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
+        B, _, h, w = img0.shape
+        if ops.concat_frame_splat_applies(flow12, w, h, B):
+            # pairs 0->2' (preprocess.py:400-411) and 1->3' (:414-424): the ConcatFlow along the horizontal flow (back01.y == +0, flow01.y == -0)
+            # also runs the z-test of the frame splat along its result - two launches per pair instead of three
+            flow02, _, img2p, depth2p, back02p, valid2p, coll2p = ops.concat_frame_splat(flow12, back01, depth1, flow01, img0, depth0,
+                                                                                            want_collision=wc, counters=counters)
+            flow13, _, img3p, depth3p, back13p, valid3p, coll3p = ops.concat_frame_splat(flow03, flow01, depth1, back01, img1, depth1,
+                                                                                            valid_mul=valid1, want_collision=wc, counters=counters)
+        else:
+            # pair 0->2': concatenated flow (preprocess.py:400-411)
+            flow02, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, epilogue=ops.EPI_CONCAT, aux=flow01, want_collision=False,
+                                                        horizontal=True)  # back01.y == +0: row-local kernel
+            img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0, flow02, flow02_valid, want_collision=wc, counters=counters)
+            # pair 1->3': (preprocess.py:414-424)
+            flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01, want_collision=False,
+                                                        horizontal=True, valid_mul=valid1)  # flow01.y == -0; flow13_valid * img1_valid (:415) fused
+            img3p, depth3p, back13p, valid3p, coll3p, _ = ops.frame_splat(img1, depth1, flow13, flow13_valid, want_collision=wc, counters=counters)
         img2, img3, img2p, img3p = _fill_leaves(inpaint, [(img2, valid2, coll2), (img3, valid3, coll3), (img2p, valid2p, coll2p),
                                                           (img3p, valid3p, coll3p)])
     return dict(img0=img0, depth0=depth0, img1=img1, depth1=depth1, img2=img2, depth2=depth2, img3=img3, depth3=depth3,

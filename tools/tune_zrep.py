@@ -62,7 +62,7 @@ def child():
     print(f"pair_480x640_b128_ms best {b:.4f} mean {m:.4f}")
     sBf = torch.full((B,), 47.0, device=dev)
     b, m = timeit(lambda: synthesis.synthesize_group(img, depth, sBf, cam))
-    print(f"group_480x640_b128_ms best {b:.4f} mean {m:.4f}  frac {368 * B * h * w / (m * 1e-3) / 6553.6e9:.3f}")
+    print(f"group_480x640_b128_ms best {b:.4f} mean {m:.4f}  frac {356 * B * h * w / (m * 1e-3) / 6553.6e9:.3f}")
     b, m = timeit(lambda: ops.reproject_pair(img[:1], depth[:1], cam[:1], None), reps=200)
     print(f"pair_480x640_b1_ms best {b:.4f} mean {m:.4f}")
 
