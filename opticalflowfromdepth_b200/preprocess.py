@@ -191,8 +191,14 @@ class PreprocessPlusAugment(nn.Module):
             if self.inpaint is not None and not defer_fill:
                 a_img0 = self.inpaint(a_img0, r["valid_img0"], r["collision_img0"])
                 a_img1 = self.inpaint(a_img1, r["valid_img1"], r["collision_img1"])
-            block[geo, 0] = torch.cat((a_img0, r["aug_depth0"], r["aug0_flow"], r["back_aug0_flow"]), 1)
-            block[geo, 1] = torch.cat((r["aug1_flow"].float(), r["back_aug1_flow"], a_img1, r["aug_depth1"]), 1)
+            # the geometric slots are 1-3, 5-7, 9-11 (AUGMENT_TYPES): strided views instead of an index tensor, whose upload would
+            # synchronise the stream in the middle of a frame
+            assert geo == [1, 2, 3, 5, 6, 7, 9, 10, 11]
+            slots = block.view(3, 4, 2, 8, h, w)[:, 1:4]
+            for ch0, t in ((0, a_img0), (3, r["aug_depth0"]), (4, r["aug0_flow"]), (6, r["back_aug0_flow"])):
+                slots[:, :, 0, ch0:ch0 + t.shape[1]] = t.view(3, 3, t.shape[1], h, w)
+            for ch0, t in ((0, r["aug1_flow"].float()), (2, r["back_aug1_flow"]), (4, a_img1), (7, r["aug_depth1"])):
+                slots[:, :, 1, ch0:ch0 + t.shape[1]] = t.view(3, 3, t.shape[1], h, w)
             for k, t in enumerate(AUGMENT_TYPES):
                 if t < 5:
                     pa = photometric_apply(imgA[0], float(t), draws[k])
@@ -212,16 +218,20 @@ class PreprocessPlusAugment(nn.Module):
             return
         with torch.cuda.device(self.device):
             imgs, valids, colls, where = [], [], [], []
-            for b, (block, (geo, v0, c0, v1, c1)) in enumerate(zip(blocks, pendings)):
-                imgs += [block[geo, 0, 0:3], block[geo, 1, 4:7]]
-                valids += [v0, v1]
-                colls += [c0, c1]
-                where += [(b, 0, slice(0, 3)), (b, 1, slice(4, 7))]
+            for block, (geo, v0, c0, v1, c1) in zip(blocks, pendings):
+                h, w = block.shape[-2:]
+                slots = block.view(3, 4, 2, 8, h, w)[:, 1:4]  # the geometric slots 1-3, 5-7, 9-11 without an index tensor
+                for which, ch, v, c in ((0, slice(0, 3), v0, c0), (1, slice(4, 7), v1, c1)):
+                    dst = slots[:, :, which, ch]
+                    imgs.append(dst.reshape(len(geo), 3, h, w))
+                    valids.append(v)
+                    colls.append(c)
+                    where.append(dst)
             filled = self.inpaint(torch.cat(imgs).contiguous(), torch.cat(valids), torch.cat(colls))
             o = 0
-            for (b, which, ch), im in zip(where, imgs):
-                n = im.shape[0]
-                blocks[b][pendings[b][0], which, ch] = filled[o:o + n]
+            for dst in where:
+                n = dst.shape[0] * dst.shape[1]
+                dst.copy_(filled[o:o + n].view(dst.shape))
                 o += n
 
     @staticmethod
@@ -238,43 +248,77 @@ class PreprocessPlusAugment(nn.Module):
             plan.append(row)
         return plan
 
-    def _to_host(self, t: torch.Tensor) -> np.ndarray:
-        """One D2H copy into page-locked memory (torch's caching host allocator recycles the block once the writer
-        threads drop their views)."""
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        host.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return host.numpy().astype(self.save_dtype, copy=False)
+    def _copy_stream(self):
+        """The D2H copies of a frame run on their own stream: they overlap the kernels of the next augmentation blocks and the fills."""
+        if getattr(self, "_cs", None) is None:
+            self._cs = torch.cuda.Stream(self.device)
+        return self._cs
 
-    def _group_to_host(self, group: Dict[str, torch.Tensor]) -> np.ndarray:
+    def _after_compute(self):
+        """The copy stream waits for everything issued so far on the compute stream."""
+        cs = self._copy_stream()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        cs.wait_event(ev)
+        return cs
+
+    def _group_to_host(self, group: Dict[str, torch.Tensor]) -> torch.Tensor:
         """The 44-channel group array of one frame (preprocess.py:437-447) assembled in page-locked host memory: each result
-        tensor goes by one strided DMA into its channel slice, no torch.cat on the device."""
+        tensor goes by one strided DMA into its channel slice, no torch.cat on the device.  Asynchronous (copy stream): the caller
+        synchronises that stream before reading the returned page-locked tensor [1,44,H,W]."""
         h, w = group["img0"].shape[-2:]
-        host = torch.empty((1, sum(group[n].shape[1] for n in GROUP_CHANNELS), h, w), dtype=torch.float32, pin_memory=True)
-        c0 = 0
+        parts = []
         for n in GROUP_CHANNELS:
             t = group[n][0:1]
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
-            ops.scatter_channels_to_host(t, host, c0)
+            parts.append(t)
+        host = torch.empty((1, sum(t.shape[1] for t in parts), h, w), dtype=torch.float32, pin_memory=True)
+        cs = self._after_compute()
+        c0 = 0
+        for t in parts:
+            ops.scatter_channels_to_host(t, host, c0, stream=cs)
             c0 += t.shape[1]
-        torch.cuda.current_stream(self.device).synchronize()
-        return host[0].numpy().astype(self.save_dtype, copy=False)
+        self._keep = getattr(self, "_keep", []) + parts  # referenced until the copy stream has been synchronised
+        return host
 
     def forward(self, datas, output_dir, is_stereo=False, n_continuous=4):
         t0 = time.time()
         group = self.synthesize(datas, is_stereo)
         os.makedirs(output_dir, exist_ok=True)
+        geo = [k for k, t in enumerate(AUGMENT_TYPES) if t >= 5]
         with torch.cuda.device(self.device):
-            self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=self._group_to_host(group))
+            self._keep = []
+            host_group = self._group_to_host(group)
             t1 = time.time()
             h, w = group["img0"].shape[-2:]
             plan = self.draw_augmentations(h, w)
-            built = [self.augment_pair_block(group, gi, plan[gi], defer_fill=True) for gi in range(len(GROUP_PAIRS))]
-            self.fill_blocks([b for b, _ in built], [p for _, p in built])
+            # Every augmentation block starts its way to the host as soon as its kernels are issued (copy stream), so the transfers of a
+            # frame - 1.2 GB at 480x640, half of its time - overlap the kernels of the following blocks and the fills.  The warped images
+            # of the geometric augmentations are inpainted afterwards in ONE batched call (fill_blocks) and only those planes cross again.
+            built, hosts = [], []
             for gi in range(len(GROUP_PAIRS)):
-                block = self._to_host(built[gi][0])
-                built[gi] = None  # the device block goes back to the allocator once its copy has landed
+                block, pending = self.augment_pair_block(group, gi, plan[gi], defer_fill=True)
+                host = torch.empty(block.shape, dtype=block.dtype, pin_memory=True)
+                cs = self._after_compute()
+                with torch.cuda.stream(cs):
+                    host.copy_(block, non_blocking=True)
+                built.append((block, pending))
+                hosts.append(host)
+            if self.inpaint is not None:
+                self.fill_blocks([b for b, _ in built], [p for _, p in built])
+                cs = self._after_compute()
+                with torch.cuda.stream(cs):
+                    for (block, _), host in zip(built, hosts):
+                        for k in geo:
+                            host[k, 0, 0:3].copy_(block[k, 0, 0:3], non_blocking=True)  # aug_img0 of file {gi}_{k}_1
+                            host[k, 1, 4:7].copy_(block[k, 1, 4:7], non_blocking=True)  # aug_img1 of file {gi}_{k}_2
+            self._copy_stream().synchronize()
+            built.clear()
+            self._keep = []
+            self.writer.submit(f"{output_dir}/group.npz", img_depth_flow=host_group[0].numpy().astype(self.save_dtype, copy=False))
+            for gi, host in enumerate(hosts):
+                block = host.numpy().astype(self.save_dtype, copy=False)
                 for k, t in enumerate(AUGMENT_TYPES):
                     for which in (0, 1):
                         extra = {"augment_img": which} if self.reader_compat else {}

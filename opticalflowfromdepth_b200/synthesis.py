@@ -371,12 +371,14 @@ def photometric_apply(img: torch.Tensor, augment_flow_type: float, draws) -> tor
         r, g, b = img.select(-3, 0), img.select(-3, 1), img.select(-3, 2)
         gray = (r * 0.2989 + g * 0.5870) + b * 0.1140
         return gray.unsqueeze(-3).expand_as(img).contiguous()
+    # the draws are float32 scalars on the host: a Python float carries the same value into the float32 kernel as a 0-dim device tensor
+    # would, without the blocking host-to-device copy (and the stream synchronisation it implies) of `.to(img.device)`
     if augment_flow_type >= 1.:
         channel, shift = draws
         out = img.clone()
-        out.select(-3, channel).add_(shift.to(img.device))
+        out.select(-3, channel).add_(float(shift))
         return out
-    return img * draws.to(img.device)
+    return img * float(draws)
 
 
 def augment_flow(img0, img0_depth, img1, img1_depth, flow01, back_flow01, device=None, augment_flow_type=None,
