@@ -124,7 +124,9 @@ class InLoopSampler:
         types = plan.types
         with torch.cuda.device(dev):
             depth0 = depth if self.normalized else ops.normalize_depth(depth)
-            grp = synthesis.synthesize_group(img, depth0, plan.sBf.to(dev), plan.cam.to(dev), inpaint=self.inpaint)
+            # host -> device through page-locked staging, asynchronously: nothing in a step synchronises the stream
+            up = lambda t: t.pin_memory().to(dev, non_blocking=True)  # noqa: E731
+            grp = synthesis.synthesize_group(img, depth0, up(plan.sBf), up(plan.cam), inpaint=self.inpaint)
             # Every sample is 12 planes (imgA 3, depthA 1, imgB 3, depthB 1, flowAB 2, back_flowAB 2) picked from the group's tensors - or,
             # for a geometric augmentation, from what ofd_augment_pairs makes of them.  Picking, the photometric functions and the final
             # placement are plane operations: two tables, two launches (ofd_plane_ops), whatever the batch draws.
@@ -180,7 +182,7 @@ class InLoopSampler:
             del keep
             label_host = np.zeros((B, NUM_CLASSES), np.float32)
             label_host[np.arange(B), [max(0, t - 4) for t in types]] = 1.0  # dataloader.py:153-156
-            label = torch.from_numpy(label_host).to(dev)
+            label = up(torch.from_numpy(label_host))
         return Batch(first_img, second_img, flow, back, first_dep, second_dep, label, plan)
 
 

@@ -617,7 +617,9 @@ def plane_ops(table, hw: int, device, gray_stride: Optional[int] = None):
     device = torch.device(device)
     aligned = bool(((table["src"] | table["dst"]) & 15 == 0).all())
     with torch.cuda.device(device):
-        dev_table = torch.from_numpy(table.view(np.uint8).reshape(-1)).to(device)
+        # page-locked staging + asynchronous copy: a pageable upload would synchronise the stream (the caching host allocator keeps
+        # the staging block until the copy has run)
+        dev_table = torch.from_numpy(table.view(np.uint8).reshape(-1)).pin_memory().to(device, non_blocking=True)
         _lib.call("ofd_plane_ops", _ptr(dev_table), n, int(hw), int(hw if gray_stride is None else gray_stride), int(aligned),
                   _stream(device))  # dev_table is allocated and read on the current stream: its reuse is stream-ordered
 
