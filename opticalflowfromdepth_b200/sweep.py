@@ -320,8 +320,11 @@ def run_sweep(indices: Sequence[int], load_frame: Callable[[int], tuple], device
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             stage["ev"][slot] = ev
-            sBf = s_host.pin_memory().to(dev, non_blocking=True)   # page-locked staging: no stream synchronisation per batch
-            cam = cam_host.pin_memory().to(dev, non_blocking=True)
+            if os.environ.get("OFD_SWEEP_PAGEABLE_UPLOADS") == "1":  # A/B knob: the synchronising uploads of before
+                sBf, cam = s_host.to(dev), cam_host.to(dev)
+            else:
+                sBf = s_host.pin_memory().to(dev, non_blocking=True)   # page-locked staging: no stream synchronisation per batch
+                cam = cam_host.pin_memory().to(dev, non_blocking=True)
             with torch.cuda.device(dev):
                 depth = ops.normalize_depth(raw)                                    # :355
             res = synthesis.synthesize_group(img, depth, sBf, cam, inpaint=inpaint, counters=counters)
