@@ -28,7 +28,7 @@ print("FW.forward:", tuple(warped.shape), "hit rate", float(valid.mean()))
 pair = synthesis.synthesize_pairs(img, depth, torch.full((B,), 47.0, device=dev))
 print("pairs:", {k: tuple(v.shape) for k, v in pair.items()})
 
-# 3. the reference's 5-pair group of every frame (preprocess.py:356-432): 13 launches for the batch
+# 3. the reference's 5-pair group of every frame (preprocess.py:356-432): 9 launches for the batch
 K, inv_K = synthesis.Plausible.K((H, W))
 cams = []
 for k in range(B):

@@ -4,7 +4,7 @@ per frame — `group.npz` (44 channels, preprocess.py:437-447) and `{group}_{k}_
 of the 5 pairs (preprocess.py:453-476) — with the same keys, shapes and values.
 
 What differs from the reference is how it gets there:
-  * the group's 7 splats run as the fused kernels of `synthesis.synthesize_group` (13 launches);
+  * the group's 7 splats run as the fused kernels of `synthesis.synthesize_group` (9 launches);
   * the 45 geometric augmentations of a frame run as FIVE `ofd_augment_pairs` calls (one per pair, batch of 9), their
     random parameters pre-drawn on the host in the reference's exact order (utils.py:96-100), so the files are the same;
   * results cross PCIe once per batch into host memory and are compressed / written by a pool of writer threads

@@ -499,8 +499,9 @@ def _fill_leaves(inpaint, leaves):
 
 def synthesize_group(img0, depth0, sBf, cam, inpaint=None, counters=None):
     """The reference's 5-pair group of one frame batch (preprocess.py:356-432), inpaint optional, all on the GPU:
-    7 splats with the flow producers and consumers fused into them = 13 kernel launches per batch chunk
-    (1 fused stereo pair, 6 x (z-test + gather)).
+    7 splats with the flow producers and consumers fused into them = 9 kernel launches per batch (1 fused stereo pair,
+    2 x (6-DoF z-test + gather), 2 x (row-local ConcatFlow that also runs the next frame splat's z-test + gather); 11 when the width
+    is not a multiple of 4).
 
     img0[B,3,H,W], depth0[B,1,H,W] f32 (normalised), sBf[B], cam1/cam0 built from the same pose: cam[B,21] float32.
     depth0 may be float64 (dataset path, utils.py:44-72): the group then follows the reference's dtype rules end to end
