@@ -208,12 +208,15 @@ def run_ours(args):
         # and is replayed to stderr at the end - not silenced
         # (unconditionally: the level may come from /etc/nccl.conf rather than the environment).  NCCL honours NCCL_DEBUG_FILE only
         # above the VERSION level, and at VERSION (what these boxes default to) it prints its banner on stdout: raise VERSION / unset to
-        # WARN - the banner then lands in the file too; INFO / TRACE requested by the caller are kept as they are.
+        # INFO (INIT subsystem) - the banner then lands in the file too; WARN / INFO / TRACE requested by the caller are kept as they are.
         if not os.environ.get("NCCL_DEBUG_FILE"):
             nccl_log = f"/tmp/ofd_nccl_{os.getpid()}_r{rank}.log"
             os.environ["NCCL_DEBUG_FILE"] = nccl_log
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"
+                # INFO restricted to the INIT subsystem: the "comm ... rank r nranks N ... Init COMPLETE" lines a reader of stderr uses to
+                # check that N ranks really formed one communicator (a few dozen lines per rank, written at start-up only)
+                os.environ["NCCL_DEBUG"] = "INFO"
+                os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     from opticalflowfromdepth_b200 import _lib, geometry, ops, sweep, synthesis
 
