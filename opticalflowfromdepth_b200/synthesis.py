@@ -565,7 +565,7 @@ def _synthesize_group_f64(img0, depth0, sBf, cam, inpaint, counters):
         img2, depth2, back12, flow12, valid2, coll2, _ = ops.reproject_pair(img1, depth1, cam, valid1, counters=counters)
         flow03 = ops.reproject_flow(depth0, cam)                      # float64 depth x ray, float32 flow (geometry.py:39-40)
         img3, depth3, back03, valid3, coll3, _ = ops.frame_splat(img0, depth0_f, flow03, None, counters=counters)
-        warp12, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1)
+        warp12, flow02_valid, _ = ops.splat_flow(flow12, back01, depth1, want_collision=False, horizontal=True)  # back01 is float32 with y == +0: row-local kernel
         flow02 = (warp12 + flow01) * flow02_valid                     # float32 + float64 -> float64 (preprocess.py:312)
         img2p, depth2p, back02p, valid2p, coll2p, _ = ops.frame_splat(img0, depth0_f, flow02, flow02_valid, counters=counters)
         flow13, flow13_valid, _ = ops.splat_flow(flow03, flow01, depth1, epilogue=ops.EPI_CONCAT, aux=back01)
