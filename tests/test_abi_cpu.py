@@ -97,6 +97,14 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     ("ofd_resize_bilinear_aa", (1, 0, 1, 4, 4, 8, 8, 1, None, None), -1),                                # two-axis resize without tmp
     ("ofd_resize_bilinear_aa", (1, 0, 1, 4, 4, 0, 8, 1, 1, None), -2),                                   # empty output
     ("ofd_pair_pipeline_run_flags", (None, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0), -1),                        # NULL pipeline
+    ("ofd_plane_ops", (8, -1, 16, 16, 1, None), -2),                                                     # negative table size
+    ("ofd_plane_ops", (None, 3, 16, 16, 1, None), -1),                                                   # NULL table
+    ("ofd_plane_ops", (4, 3, 16, 16, 1, None), -4),                                                      # table not 8-byte aligned
+    ("ofd_concat_frame_splat", (16, 16, 16, 16, None, 16, 16, 1, 4, 6, 16, 16, 16, 16, 16, 16, None, None, 256, 1 << 20, None), -2),   # W % 4 != 0
+    ("ofd_concat_frame_splat", (16, 16, 16, 16, None, 16, 16, 1, 4, 4096, 16, 16, 16, 16, 16, 16, None, None, 256, 1 << 20, None), -2),  # W > 2048
+    ("ofd_concat_frame_splat", (16, 16, 16, None, None, 16, 16, 1, 4, 8, 16, 16, 16, 16, 16, 16, None, None, 256, 1 << 20, None), -1),  # NULL flowAB
+    ("ofd_concat_frame_splat", (16, 16, 16, 16, None, 16, 16, 1, 4, 8, 16, 16, 16, 16, 16, 16, None, None, 256, 16, None), -5),         # workspace too small
+    ("ofd_concat_frame_splat", (16, 20, 16, 16, None, 16, 16, 1, 4, 8, 16, 16, 16, 16, 16, 16, None, None, 256, 1 << 20, None), -4),    # plane not 16-byte aligned
 ])
 def test_round2_entry_points_reject_bad_arguments(name, args, code):
     """The entry points added in round 2 validate before touching CUDA (no GPU needed)."""
