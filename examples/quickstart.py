@@ -37,6 +37,13 @@ for k in range(B):
 group = synthesis.synthesize_group(img, depth, torch.full((B,), 47.0, device=dev), torch.cat(cams).to(dev))
 print("group:", len(group), "tensors, flow02", tuple(group["flow02"].shape))
 
+# 3b. one pair of that group by hand: pair 0->2' = ConcatFlow of flow12 along the horizontal back_flow01 fused with the frame splat of
+#     (img0, depth0) along the result (preprocess.py:400-411) - two launches, same tensors as the group's
+f02, f02_valid, img2p, depth2p, back02p, valid2p, _ = ops.concat_frame_splat(group["flow12"], group["back_flow01"], group["depth1"],
+                                                                               group["flow01"], img, depth)
+assert torch.equal(f02, group["flow02"]) and torch.equal(img2p, group["img2_prime"])
+print("pair 0->2':", tuple(f02.shape), "valid fraction", float(valid2p.mean()))
+
 # 4. in-loop geometric augmentation of a batch of pairs (one native call, 13 launches)
 s1, s2, (sf, bsf) = synthesis.augment_flow_batch(img, depth, pair["img1"], pair["depth1"], pair["flow"], pair["back_flow"],
                                                  kinds=[5, 6, 7, 6], reference_draws=False)
